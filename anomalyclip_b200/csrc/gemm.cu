@@ -1,0 +1,189 @@
+// Host launcher for the tcgen05 GEMM: builds the TMA tensor maps and enqueues the kernel.
+#include "gemm.cuh"
+
+#include <cstdarg>
+#include <mutex>
+
+#include "common.h"
+
+namespace aclip {
+
+// ------------------------------------------------------------------ error / device plumbing
+std::string& last_error() {
+  thread_local std::string msg;
+  return msg;
+}
+
+int fail(int code, const char* fmt, ...) {
+  char buf[1024];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  last_error() = buf;
+  return code;
+}
+
+int sm_count() {
+  static int cached = 0;
+  if (cached == 0) {
+    int dev = 0, n = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess &&
+        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
+      cached = n;
+    else
+      return 148;
+  }
+  return cached;
+}
+
+std::atomic<long long> g_launches{0};
+
+// ------------------------------------------------------------------ tensor maps
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_tiled_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) ==
+            cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(p);
+  });
+  return fn;
+}
+
+// bf16 tensor map with the 128-byte swizzle; dims/strides innermost first, strides in bytes for
+// dims 1..rank-1.
+static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+  EncodeTiledFn fn = encode_tiled_fn();
+  if (fn == nullptr) return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
+  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+                  const_cast<void*>(base), dims, strides_bytes, box, elem_strides,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS)
+    return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+  return ACLIP_OK;
+}
+
+template <int BLOCK_N, int PASSES>
+static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                  int max_ctas, cudaStream_t stream) {
+  using Cfg = GemmCfg<BLOCK_N, PASSES>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES>;
+  static bool configured = false;
+  if (!configured) {
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  int ctas = max_ctas > 0 ? max_ctas : sm_count();
+  if (ctas > m_tiles * n_tiles) ctas = m_tiles * n_tiles;
+  kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
+  ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
+  ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  ACLIP_REQUIRE(g.passes == 1 || g.passes == 3, "gemm: passes must be 1 or 3 (got %d)", g.passes);
+  ACLIP_REQUIRE(g.N % 32 == 0, "gemm: N=%d must be a multiple of 32", g.N);
+  ACLIP_REQUIRE(g.ldw % 8 == 0 && g.K % 8 == 0, "gemm: K=%d / ldw=%d must be multiples of 8", g.K,
+                g.ldw);
+  ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(g.a) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
+                "gemm: operands must be 16-byte aligned");
+  ACLIP_REQUIRE(g.out_f32 != nullptr || g.out_split != nullptr, "gemm: no output");
+  ACLIP_REQUIRE(g.ldc % 8 == 0 && g.ldc >= g.N, "gemm: ldc=%d invalid for N=%d", g.ldc, g.N);
+  ACLIP_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && g.ldr >= g.N), "gemm: ldr=%d invalid",
+                g.ldr);
+  ACLIP_REQUIRE(g.act >= 0 && g.act <= 2, "gemm: unknown activation %d", g.act);
+  const int planes = g.passes == 1 ? 1 : 2;
+  // 128-wide tiles when they waste fewer padded columns than 256-wide ones (e.g. N = 128, 384)
+  const bool narrow = ((g.N + 127) / 128) * 128 < ((g.N + 255) / 256) * 256;
+  const int block_n = narrow ? 128 : 256;
+
+  GemmParams p{};
+  p.M = g.M; p.N = g.N; p.K = g.K;
+  p.num_kb = (g.K + 63) / 64;
+  p.a_mode = g.a_mode;
+  p.bias = g.bias;
+  p.residual = g.residual;
+  p.res_mod = g.res_mod;
+  p.ldr = g.ldr;
+  p.act = g.act;
+  p.out_f32 = g.out_f32;
+  p.out_split = static_cast<__nv_bfloat16*>(g.out_split);
+  p.split_plane_stride = g.split_plane_stride;
+  p.ldc = g.ldc;
+  p.row_group = g.row_group > 0 ? g.row_group : 0x7fffffff;
+  p.row_group_stride = g.row_group > 0 ? g.row_group_stride : 0;
+  p.row_offset = g.row_offset;
+
+  CUtensorMap tmA, tmB;
+  if (g.a_mode == 0) {
+    ACLIP_REQUIRE(g.lda % 8 == 0 && g.lda >= g.K, "gemm: lda=%d invalid for K=%d", g.lda, g.K);
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.a_plane_stride * 2};
+    if (planes == 1) strides[1] = (cuuint64_t)g.lda * 2 * (cuuint64_t)g.M;
+    cuuint32_t box[3] = {64, 128, (cuuint32_t)planes};
+    ACLIP_REQUIRE(planes == 1 || (g.a_plane_stride % 8 == 0 && g.a_plane_stride > 0),
+                  "gemm: a_plane_stride must be a positive multiple of 8");
+    ACLIP_TRY(make_tmap(&tmA, g.a, 3, dims, strides, box));
+  } else if (g.a_mode == 1) {
+    ACLIP_REQUIRE(g.conv_c % 64 == 0, "conv3x3: C=%d must be a multiple of 64", g.conv_c);
+    ACLIP_REQUIRE(g.conv_w > 0 && 128 % g.conv_w == 0 && (g.conv_h * g.conv_w) % 128 == 0,
+                  "conv3x3: grid %dx%d unsupported (need W | 128 and 128 | H*W)", g.conv_h,
+                  g.conv_w);
+    ACLIP_REQUIRE(g.M == g.conv_s * g.conv_h * g.conv_w && g.K == 9 * g.conv_c,
+                  "conv3x3: M/K inconsistent with the grid");
+    p.conv_cin_kb = g.conv_c / 64;
+    p.conv_w = g.conv_w;
+    p.conv_h = g.conv_h;
+    const cuuint64_t C = g.conv_c, W = g.conv_w, H = g.conv_h, S = g.conv_s;
+    cuuint64_t dims[5] = {C, W, H, S, (cuuint64_t)planes};
+    cuuint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2,
+                             planes == 1 ? S * H * W * C * 2 : (cuuint64_t)g.a_plane_stride * 2};
+    cuuint32_t box[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(128 / g.conv_w), 1,
+                         (cuuint32_t)planes};
+    ACLIP_TRY(make_tmap(&tmA, g.a, 5, dims, strides, box));
+  } else {
+    return fail(ACLIP_ERR_INVALID, "gemm: unknown a_mode %d", g.a_mode);
+  }
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.N, (cuuint64_t)planes};
+    cuuint64_t strides[2] = {(cuuint64_t)g.ldw * 2, planes == 1 ? (cuuint64_t)g.ldw * 2 * g.N
+                                                                : (cuuint64_t)g.w_plane_stride * 2};
+    cuuint32_t box[3] = {64, (cuuint32_t)block_n, (cuuint32_t)planes};
+    ACLIP_REQUIRE(planes == 1 || (g.w_plane_stride % 8 == 0 && g.w_plane_stride > 0),
+                  "gemm: w_plane_stride must be a positive multiple of 8");
+    ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box));
+  }
+
+  if (block_n == 256) {
+    return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
+                         : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);
+  }
+  return g.passes == 3 ? launch<128, 3>(tmA, tmB, p, g.max_ctas, stream)
+                       : launch<128, 1>(tmA, tmB, p, g.max_ctas, stream);
+}
+
+}  // namespace aclip
+
+extern "C" int aclip_gemm(const AclipGemmArgs* args, void* stream) {
+  if (args == nullptr) return aclip::fail(ACLIP_ERR_INVALID, "aclip_gemm: args is NULL");
+  return aclip::gemm(*args, aclip::as_stream(stream));
+}

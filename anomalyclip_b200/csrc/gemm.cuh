@@ -1,0 +1,295 @@
+// Persistent, warp-specialised tcgen05 GEMM for sm_100a.
+//
+//   C[M,N] = epilogue( A[M,K] * W[N,K]^T )
+//
+// Operands are "split-bf16": every fp32 value x is carried as two bf16 planes
+// hi = bf16(x), lo = bf16(x - hi).  With PASSES == 3 the kernel issues
+// hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator, which reproduces an fp32 GEMM to
+// ~2^-16 relative error per product (the reference path is fp32 end to end, see
+// /root/reference/src/models/components/anomaly_clip.py:66-67).  PASSES == 1 is the plain
+// bf16 GEMM (hi plane only).
+//
+// Roles (192 threads, 1 CTA / SM):
+//   warp 0  lane 0 : TMA producer   (A and W tiles, 128-byte swizzle, mbarrier complete_tx)
+//   warp 1  lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
+//   warps 2..5     : epilogue       (tcgen05.ld -> bias / activation / residual -> global)
+// Pipelines: smem ring full/empty (TMA <-> MMA) and a double-buffered TMEM accumulator
+// full/empty (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// A can be addressed in two ways (GemmParams::a_mode):
+//   0  linear  : A is [plane][M][K] row-major                       (3-D tensor map)
+//   1  conv3x3 : A is an NHWC grid [plane][S][H][W][C]; the K loop runs over 9 taps x C and
+//                each tap is a TMA box shifted by (dy,dx) with hardware zero fill at the
+//                borders, i.e. an implicit-GEMM 3x3 "same" convolution  (5-D tensor map)
+#pragma once
+#include <cuda_bf16.h>
+
+#include "ptx.cuh"
+
+namespace aclip {
+
+enum : int { ACT_NONE = 0, ACT_QUICKGELU = 1, ACT_LEAKYRELU = 2 };
+
+struct GemmParams {
+  int M, N, K;
+  int num_kb;  // ceil(K / 64)
+  int a_mode;  // 0 linear, 1 conv3x3
+  int conv_cin_kb;  // Cin / 64             (conv mode)
+  int conv_w;       // grid width  W        (conv mode; 128 % W == 0)
+  int conv_h;       // grid height H        (conv mode; (H*W) % 128 == 0)
+  // epilogue
+  const float* bias;      // [N] or nullptr
+  const float* residual;  // fp32 [*, ldr] or nullptr
+  int res_mod;            // >0: residual row = m % res_mod, else residual row = output row
+  int ldr;
+  int act;
+  float* out_f32;            // fp32 [*, ldc] or nullptr
+  __nv_bfloat16* out_split;  // bf16 [2][split_rows][ldc] or nullptr (hi plane, lo plane)
+  long long split_plane_stride;  // elements between the hi and lo plane
+  int ldc;
+  // output row remap: out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset
+  int row_group, row_group_stride, row_offset;
+};
+
+template <int BLOCK_N_, int PASSES_>
+struct GemmCfg {
+  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_N = BLOCK_N_;
+  static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
+  static constexpr int UMMA_K = 16;
+  static constexpr int PASSES = PASSES_;
+  static constexpr int PLANES = PASSES_ == 1 ? 1 : 2;
+  static constexpr int A_PLANE_BYTES = BLOCK_M * 128;
+  static constexpr int B_PLANE_BYTES = BLOCK_N * 128;
+  static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
+  static constexpr int SMEM_BUDGET = 200 * 1024;
+  static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered fp32 accumulator
+  static constexpr int BAR_BYTES = 256;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
+  static constexpr int THREADS = 192;
+  static_assert(STAGES >= 2, "need at least a double buffer");
+  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+};
+
+__device__ __forceinline__ float apply_act(float x, int act) {
+  if (act == ACT_QUICKGELU) {
+    // x * sigmoid(1.702 x)  (reference: clip/model.py:183-185)
+    return x / (1.0f + __expf(-1.702f * x));
+  } else if (act == ACT_LEAKYRELU) {
+    return x > 0.0f ? x : 0.01f * x;
+  }
+  return x;
+}
+
+template <int BLOCK_N, int PASSES>
+__global__ void __launch_bounds__(192, 1)
+gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                    const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = GemmCfg<BLOCK_N, PASSES>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);
+      ptx::mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 4);  // one arrive per epilogue warp
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        const int n0 = (t % n_tiles) * BLOCK_N;
+        const int mt = t / n_tiles;
+        const int m0 = mt * Cfg::BLOCK_M;
+        int img = 0, h0 = 0;
+        if (p.a_mode == 1) {
+          const int tiles_per_img = (p.conv_h * p.conv_w) / Cfg::BLOCK_M;
+          img = mt / tiles_per_img;
+          h0 = (mt % tiles_per_img) * (Cfg::BLOCK_M / p.conv_w);
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
+          if (p.a_mode == 0) {
+            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+          } else {
+            const int tap = kb / p.conv_cin_kb;
+            const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            ptx::tma_load_5d(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+          }
+          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, BLOCK_N);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+            const uint32_t koff = k * Cfg::UMMA_K * 2;  // bytes along K inside the swizzle row
+            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a_base + koff);
+            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b_base + koff);
+            ptx::mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PASSES == 3) {
+              const uint64_t a_lo = ptx::make_kmajor_sw128_desc(a_base + Cfg::A_PLANE_BYTES + koff);
+              const uint64_t b_lo = ptx::make_kmajor_sw128_desc(b_base + Cfg::B_PLANE_BYTES + koff);
+              ptx::mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
+              ptx::mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          ptx::mma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..5)
+    const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      const int n0 = (t % n_tiles) * BLOCK_N;
+      const int m0 = (t / n_tiles) * Cfg::BLOCK_M;
+      const int m = m0 + quarter * 32 + lane;
+      const bool row_ok = m < p.M;
+      long long out_row = 0, res_row = 0;
+      if (row_ok) {
+        out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride +
+                  (m % p.row_group) + p.row_offset;
+        res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
+      }
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < BLOCK_N / 32; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;  // warp-uniform
+        uint32_t raw[32];
+        ptx::tmem_ld_32x32(t_row + c * 32, raw);
+        ptx::tmem_ld_wait();
+        if (row_ok) {
+          float v[32];
+#pragma unroll
+          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+          if (p.bias != nullptr) {
+            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 b = __ldg(b4 + j);
+              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+            }
+          }
+          if (p.act != ACT_NONE) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+          }
+          if (p.residual != nullptr) {
+            const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+              const float4 r = r4[j];
+              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+            }
+          }
+          if (p.out_f32 != nullptr) {
+            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldc + n);
+#pragma unroll
+            for (int j = 0; j < 8; ++j)
+              o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+          }
+          if (p.out_split != nullptr) {
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int j = 0; j < 16; ++j) {
+              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]);
+              const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * j + 1]);
+              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+              const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+              hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+              lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+            }
+            uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ldc + n);
+            uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
+                                                 out_row * p.ldc + n);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+            }
+          }
+        }
+      }
+      // hand the accumulator buffer back to the MMA warp
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&tempty_bar[acc]);
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+}  // namespace aclip

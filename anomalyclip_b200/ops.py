@@ -1,0 +1,94 @@
+"""Python handles on the building-block operators of the C ABI.
+
+torch is used for device memory and streams only; every function here enqueues hand-written
+sm_100a kernels through `libaclip_b200.so` and raises if that library is missing.
+A "split" tensor is a bf16 tensor of shape [2, rows, ld]: plane 0 = hi, plane 1 = lo.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Optional
+
+import torch
+
+from . import _lib
+from ._lib import ACT_LEAKYRELU, ACT_NONE, ACT_QUICKGELU, GemmArgs  # noqa: F401
+
+
+def _stream() -> C.c_void_p:
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    if t.dtype != torch.float32 or not t.is_cuda:
+        raise TypeError(f"{name} must be a CUDA float32 tensor")
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def split(x: torch.Tensor, ld_out: Optional[int] = None,
+          out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """fp32 [rows, cols] -> split bf16 [2, rows, ld_out] (zero padded columns)."""
+    x = _f32c(x, "x")
+    rows, cols = x.reshape(-1, x.shape[-1]).shape
+    ld = ld_out if ld_out is not None else (cols + 7) // 8 * 8
+    if out is None:
+        out = torch.empty((2, rows, ld), dtype=torch.bfloat16, device=x.device)
+    lib = _lib.load()
+    _lib.check(lib.aclip_split_f32(x.data_ptr(), rows, cols, cols, out.data_ptr(), ld,
+                                   out.stride(0), _stream()))
+    return out
+
+
+def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
+         act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, res_mod: int = 0,
+         out_f32: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
+         want_split: bool = False, passes: int = 3, K: Optional[int] = None,
+         conv: Optional[tuple] = None, row_map: Optional[tuple] = None, out_rows: Optional[int] = None,
+         max_ctas: int = 0) -> torch.Tensor:
+    """out = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
+
+    a: split [2, M, lda] (linear) or split NHWC grid [2, S, H, W, C] with conv=(S, H, W, C).
+    w: split [2, N, ldw].
+    """
+    lib = _lib.load()
+    g = GemmArgs()
+    N = w.shape[1]
+    if conv is not None:
+        S, H, Wd, Cc = conv
+        M, Kk = S * H * Wd, 9 * Cc
+        g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
+        g.lda = Cc
+    else:
+        M = a.shape[1]
+        Kk = K if K is not None else a.shape[2]
+        g.lda = a.stride(1)
+    g.a, g.w = a.data_ptr(), w.data_ptr()
+    g.M, g.N, g.K = M, N, Kk
+    g.ldw = w.stride(1)
+    g.a_plane_stride, g.w_plane_stride = a.stride(0), w.stride(0)
+    g.passes = passes
+    g.bias = _ptr(bias)
+    g.act = act
+    g.res_mod = res_mod
+    if residual is not None:
+        g.residual, g.ldr = residual.data_ptr(), residual.stride(-2)
+    rows = out_rows if out_rows is not None else M
+    if out_f32 is None and out_split is None:
+        if want_split:
+            out_split = torch.empty((2, rows, N), dtype=torch.bfloat16, device=a.device)
+        else:
+            out_f32 = torch.empty((rows, N), dtype=torch.float32, device=a.device)
+    if out_f32 is not None:
+        g.out_f32, g.ldc = out_f32.data_ptr(), out_f32.stride(-2)
+    if out_split is not None:
+        g.out_split, g.ldc = out_split.data_ptr(), out_split.stride(1)
+        g.split_plane_stride = out_split.stride(0)
+    if row_map is not None:
+        g.row_group, g.row_group_stride, g.row_offset = row_map
+    g.max_ctas = max_ctas
+    _lib.check(lib.aclip_gemm(C.byref(g), _stream()))
+    return out_f32 if out_f32 is not None else out_split

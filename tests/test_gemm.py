@@ -1,0 +1,111 @@
+"""Parity of the tcgen05 GEMM (C ABI: aclip_gemm / aclip_split_f32) against torch fp64/fp32."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _unsplit(s):
+    return s[0].float() + s[1].float()
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from anomalyclip_b200 import ops as _ops
+    return _ops
+
+
+def test_split_roundtrip(ops):
+    torch.manual_seed(0)
+    x = torch.randn(301, 530, device="cuda") * 3
+    s = ops.split(x, ld_out=576)
+    assert s.shape == (2, 301, 576)
+    back = _unsplit(s)
+    assert torch.all(back[:, 530:] == 0)
+    # hi+lo carries 16 significand bits
+    assert _rel(back[:, :530], x) < 2e-5
+    assert torch.equal(s[0, :, :530], x.to(torch.bfloat16))
+
+
+@pytest.mark.parametrize("M,N,K", [(128, 256, 64), (300, 256, 768), (1000, 768, 768),
+                                   (197 * 8, 2304, 768), (555, 128, 256), (129, 384, 3072),
+                                   (64, 512, 768), (4096, 3072, 768)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_plain(ops, M, N, K, passes):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    out = ops.gemm(ops.split(a), ops.split(w), passes=passes)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().T
+    err = _rel(out, ref)
+    print(f"gemm M={M} N={N} K={K} passes={passes}: rel err {err:.3e}")
+    assert err < (3e-5 if passes == 3 else 1e-2)
+    if passes == 1:  # must equal the bf16-rounded product, not just be "close"
+        ref1 = a.to(torch.bfloat16).double() @ w.to(torch.bfloat16).double().T
+        assert _rel(out, ref1) < 1e-5
+
+
+def test_gemm_epilogue_bias_act_residual(ops):
+    torch.manual_seed(1)
+    M, N, K = 777, 768, 512
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    pre = a.double() @ w.double().T + bias.double()
+    for act, fn in ((ops.ACT_NONE, lambda x: x),
+                    (ops.ACT_QUICKGELU, lambda x: x * torch.sigmoid(1.702 * x)),
+                    (ops.ACT_LEAKYRELU, lambda x: torch.nn.functional.leaky_relu(x, 0.01))):
+        out = ops.gemm(ops.split(a), ops.split(w), bias=bias, act=act, residual=res)
+        ref = fn(pre) + res.double()
+        err = _rel(out, ref)
+        print(f"epilogue act={act}: rel err {err:.3e}")
+        assert err < 3e-5
+    # in-place residual update x += a @ w^T + b
+    x = res.clone()
+    ops.gemm(ops.split(a), ops.split(w), bias=bias, residual=x, out_f32=x)
+    assert _rel(x, pre + res.double()) < 3e-5
+
+
+def test_gemm_split_output_and_rowmap(ops):
+    torch.manual_seed(2)
+    frames, g = 5, 196
+    M, N, K = frames * g, 768, 768
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    pos = torch.randn(g, N, device="cuda")
+    ref = (a.double() @ w.double().T).reshape(frames, g, N) + pos.double()
+    # split output
+    s = ops.gemm(ops.split(a), ops.split(w), want_split=True)
+    assert _rel(_unsplit(s), ref.reshape(M, N) - pos.double().repeat(frames, 1)) < 3e-5
+    # periodic residual (positional table) + row remap 196 -> 197 with offset 1
+    out = torch.zeros(frames * 197, N, device="cuda")
+    ops.gemm(ops.split(a), ops.split(w), residual=pos, res_mod=g, out_f32=out,
+             row_map=(g, 197, 1))
+    out = out.reshape(frames, 197, N)
+    assert torch.all(out[:, 0] == 0)
+    assert _rel(out[:, 1:], ref) < 3e-5
+
+
+@pytest.mark.parametrize("S,Cin,Cout", [(1, 64, 256), (3, 256, 1024), (2, 1024, 256), (2, 128, 128)])
+def test_conv3x3_implicit_gemm(ops, S, Cin, Cout):
+    torch.manual_seed(3)
+    H, W = 32, 16
+    x = torch.randn(S, Cin, H, W, device="cuda")
+    wt = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.02
+    b = torch.randn(Cout, device="cuda")
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(S * H * W, Cout)
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().reshape(S * H * W, Cin)
+    a = ops.split(x_nhwc)  # [2, S*H*W, Cin] == [2, S, H, W, Cin]
+    wk = wt.permute(0, 2, 3, 1).contiguous().reshape(Cout, 9 * Cin)  # k = tap * Cin + c
+    out = ops.gemm(a, ops.split(wk), bias=b, conv=(S, H, W, Cin))
+    err = _rel(out, ref)
+    print(f"conv3x3 S={S} {Cin}->{Cout}: rel err {err:.3e}")
+    assert err < 3e-5
