@@ -1,6 +1,6 @@
 """ctypes binding of `libaclip_b200.so` (the C ABI declared in include/aclip_b200.h).
 
-There is no fallback: if the library cannot be loaded the import of any operator raises.
+There is no fallback: if the library cannot be loaded, every operator raises.
 """
 from __future__ import annotations
 
@@ -13,6 +13,8 @@ LIB_PATH = _PKG / "lib" / "libaclip_b200.so"
 ACLIP_OK = 0
 ACT_NONE, ACT_QUICKGELU, ACT_LEAKYRELU = 0, 1, 2
 
+vp, fp_ = C.c_void_p, C.c_void_p  # device pointers travel as integers
+
 
 class AclipError(RuntimeError):
     """A C-ABI call returned a negative AclipStatus."""
@@ -20,33 +22,74 @@ class AclipError(RuntimeError):
 
 class GemmArgs(C.Structure):
     _fields_ = [
-        ("a", C.c_void_p), ("w", C.c_void_p),
+        ("a", vp), ("w", vp),
         ("M", C.c_int), ("N", C.c_int), ("K", C.c_int),
         ("lda", C.c_int), ("ldw", C.c_int),
         ("a_plane_stride", C.c_longlong), ("w_plane_stride", C.c_longlong),
         ("passes", C.c_int), ("a_mode", C.c_int),
         ("conv_c", C.c_int), ("conv_h", C.c_int), ("conv_w", C.c_int), ("conv_s", C.c_int),
-        ("bias", C.c_void_p), ("residual", C.c_void_p),
+        ("bias", vp), ("residual", vp),
         ("res_mod", C.c_int), ("ldr", C.c_int), ("act", C.c_int),
-        ("out_f32", C.c_void_p), ("out_split", C.c_void_p),
-        ("split_plane_stride", C.c_longlong), ("ldc", C.c_int),
+        ("out_f32", vp), ("out_split", vp),
+        ("split_plane_stride", C.c_longlong), ("ldc", C.c_int), ("ld_split", C.c_int),
         ("row_group", C.c_int), ("row_group_stride", C.c_int), ("row_offset", C.c_int),
         ("max_ctas", C.c_int),
     ]
 
 
+class VitBlock(C.Structure):
+    _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w",
+                                  "out_b", "fc_w", "fc_b", "proj_w", "proj_b")]
+
+
+class VitWeights(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("width", "layers", "heads", "patch", "resolution",
+                                       "output_dim")] + \
+               [(n, vp) for n in ("conv1_w", "class_embedding", "positional_embedding", "ln_pre_g",
+                                  "ln_pre_b", "ln_post_g", "ln_post_b", "proj_w")] + \
+               [("blocks", C.POINTER(VitBlock))]
+
+
+class AxialAttnWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("norm_g", "norm_b", "qkv_w", "out_w", "out_b")]
+
+
+class ConvFFWeights(C.Structure):
+    _fields_ = [(n, vp) for n in ("g", "b", "conv1_w", "conv1_b", "conv2_w", "conv2_b")]
+
+
+class TemporalWeights(C.Structure):
+    _fields_ = [(n, C.c_int) for n in ("feature_dim", "num_dirs", "emb", "depth", "heads",
+                                       "num_segments", "seg_length", "concat", "ldf")] + \
+               [(n, vp) for n in ("ncentroid", "selector_w", "selector_b", "proj_w", "proj_b", "pos")] + \
+               [("attn", C.POINTER(AxialAttnWeights)), ("ff", C.POINTER(ConvFFWeights))] + \
+               [(n, vp) for n in ("head_ln_g", "head_ln_b", "head_w")] + \
+               [("head_bias", C.c_float)]
+
+
+# name -> (restype, argtypes); every symbol include/aclip_b200.h declares
+SIGNATURES = {
+    "aclip_version": (C.c_int, []),
+    "aclip_last_error": (C.c_char_p, []),
+    "aclip_launch_count": (C.c_longlong, []),
+    "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),
+    "aclip_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
+    "aclip_layernorm": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_longlong, vp, vp, C.c_float,
+                                  C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp]),
+    "aclip_vit_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, vp,
+                                      C.c_longlong, C.c_int, vp]),
+    "aclip_axial_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
+                                        C.c_int, vp, C.c_longlong, vp]),
+    "aclip_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitWeights), C.c_int]),
+    "aclip_vit_forward": (C.c_int, [C.POINTER(VitWeights), vp, C.c_int, C.c_longlong, C.c_int,
+                                    C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
+                                    C.c_size_t, C.c_int, vp]),
+    "aclip_temporal_workspace_bytes": (C.c_size_t, [C.POINTER(TemporalWeights), C.c_longlong]),
+    "aclip_temporal_forward": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
+                                         vp, vp, vp, C.c_size_t, C.c_int, vp]),
+}
+
 _lib = None
-
-
-def _declare(lib: C.CDLL) -> None:
-    lib.aclip_version.restype = C.c_int
-    lib.aclip_last_error.restype = C.c_char_p
-    lib.aclip_launch_count.restype = C.c_longlong
-    lib.aclip_split_f32.argtypes = [C.c_void_p, C.c_longlong, C.c_int, C.c_int, C.c_void_p,
-                                    C.c_int, C.c_longlong, C.c_void_p]
-    lib.aclip_gemm.argtypes = [C.POINTER(GemmArgs), C.c_void_p]
-    for name in ("aclip_split_f32", "aclip_gemm"):
-        getattr(lib, name).restype = C.c_int
 
 
 def load() -> C.CDLL:
@@ -64,7 +107,10 @@ def load() -> C.CDLL:
         raise AclipError(
             f"cannot load {LIB_PATH}: {exc}. The sm_100a CUDA library is required; "
             "there is no CPU or PyTorch fallback for the hot path.") from exc
-    _declare(lib)
+    for name, (restype, argtypes) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library lacks a declared symbol
+        fn.restype = restype
+        fn.argtypes = argtypes
     _lib = lib
     return lib
 

@@ -16,6 +16,28 @@ int fail(int code, const char* fmt, ...);
 int sm_count();
 extern std::atomic<long long> g_launches;  // kernels launched by this library
 int gemm(const AclipGemmArgs& g, cudaStream_t stream);
+struct RowMap;
+int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
+              long long plane_stride, cudaStream_t stream);
+int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
+              const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
+              void* out_split, long long ld_split, long long plane_stride, cudaStream_t stream);
+int score_head(const float* x1, const float* x2, long long rows, int E, const float* gamma,
+               const float* beta, float eps, const float* w, float bias, const float* sim,
+               int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
+               float* probs_out, cudaStream_t stream);
+int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
+             const float* std3, void* out_split, long long plane_stride, cudaStream_t stream);
+int cls_rows(float* x, int B, int tokens, int width, const float* cls, const float* pos,
+             cudaStream_t stream);
+int center_regroup(const float* feats, long long rows, int D, const float* centroid,
+                   const RowMap& map, void* out_split, int ld_out, long long plane_stride,
+                   cudaStream_t stream);
+int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                  int heads, void* out_split, long long out_plane_stride, int ld_out,
+                  cudaStream_t stream);
+int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E, int heads,
+                    int axis, void* out_split, long long plane_stride, cudaStream_t stream);
 
 #define ACLIP_CUDA_OK(expr)                                                              \
   do {                                                                                   \

@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "rowmap.cuh"
 
 namespace aclip {
 
@@ -69,6 +70,144 @@ int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, i
   const long long total = rows * (ld_out >> 3);
   split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       in, rows, cols, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, plane_stride, vec_ok);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+
+// ------------------------------------------------------------------------------ patchify
+// Frames (B,3,R,R) -> im2col rows for the patch-embedding GEMM (clip/model.py:246-252,267):
+// row = b*G*G + gy*G + gx, column k = c*P*P + py*P + px (the order of conv1.weight.reshape(width,-1)).
+// U8 input is normalised on the fly exactly like torchvision's ToTensor + Normalize
+// (src/utils/augmentations.py:21-34): ((v / 255) - mean) / std in fp32.
+struct Norm3 { float mean[3]; float std[3]; };
+
+template <bool U8>
+__global__ void __launch_bounds__(256)
+patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
+                __nv_bfloat16* __restrict__ out, long long plane_stride) {
+  const int G = R / P;
+  const int K = 3 * P * P;
+  const int groups_per_row = K >> 3;
+  const long long total = static_cast<long long>(B) * G * G * groups_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long row = i / groups_per_row;
+    const int k = static_cast<int>(i - row * groups_per_row) << 3;
+    const int c = k / (P * P);
+    const int py = (k - c * P * P) / P;
+    const int px = k - c * P * P - py * P;
+    const int b = static_cast<int>(row / (G * G));
+    const int cell = static_cast<int>(row - static_cast<long long>(b) * G * G);
+    const int gy = cell / G, gx = cell - gy * G;
+    const long long src = ((static_cast<long long>(b) * 3 + c) * R + gy * P + py) * R + gx * P + px;
+    float v[8];
+    if (U8) {
+      const uint2 raw = *reinterpret_cast<const uint2*>(static_cast<const uint8_t*>(frames) + src);
+      const uint32_t w[2] = {raw.x, raw.y};
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        const float pix = static_cast<float>((w[j >> 2] >> (8 * (j & 3))) & 0xffu);
+        v[j] = __fdiv_rn(__fsub_rn(__fdiv_rn(pix, 255.0f), nrm.mean[c]), nrm.std[c]);
+      }
+    } else {
+      const float4* s4 = reinterpret_cast<const float4*>(static_cast<const float*>(frames) + src);
+      const float4 a = s4[0], bb = s4[1];
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
+    }
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
+    __nv_bfloat16* dst = out + row * K + k;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
+             const float* std3, void* out_split, long long plane_stride, cudaStream_t stream) {
+  ACLIP_REQUIRE(frames != nullptr && out_split != nullptr, "patchify: null pointer");
+  ACLIP_REQUIRE(B > 0 && P % 8 == 0 && R % P == 0, "patchify: B=%d R=%d P=%d unsupported", B, R, P);
+  ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 15) == 0, "patchify: frames must be 16-byte aligned");
+  Norm3 nrm{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
+  if (is_u8) {
+    ACLIP_REQUIRE(mean3 != nullptr && std3 != nullptr, "patchify: u8 frames need mean/std");
+    for (int c = 0; c < 3; ++c) { nrm.mean[c] = mean3[c]; nrm.std[c] = std3[c]; }
+  }
+  const int G = R / P;
+  const long long total = static_cast<long long>(B) * G * G * (3 * P * P / 8);
+  auto* o = static_cast<__nv_bfloat16*>(out_split);
+  if (is_u8)
+    patchify_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  else
+    patchify_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+// ------------------------------------------------------------------------------ CLS rows
+// x[b*tokens + 0, :] = class_embedding + positional_embedding[0]   (clip/model.py:270-278)
+__global__ void cls_rows_kernel(float* __restrict__ x, int B, int tokens, int width,
+                                const float* __restrict__ cls, const float* __restrict__ pos) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * width) return;
+  const int b = i / width, c = i - b * width;
+  x[static_cast<long long>(b) * tokens * width + c] = cls[c] + pos[c];
+}
+
+int cls_rows(float* x, int B, int tokens, int width, const float* cls, const float* pos,
+             cudaStream_t stream) {
+  ACLIP_REQUIRE(x && cls && pos && B > 0, "cls_rows: bad arguments");
+  cls_rows_kernel<<<(B * width + 255) / 256, 256, 0, stream>>>(x, B, tokens, width, cls, pos);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+// ------------------------------------------------------------------------------ centre + regroup
+// Feature rows (caller order "(b n s l)") -> (x - ncentroid) as split-bf16 rows in sub-video
+// order, columns [0, D) of a buffer whose pitch may leave room for the similarity columns.
+// (selector_model.py:54 and anomaly_clip.py:143 both subtract the same centroid; done once here.)
+__global__ void __launch_bounds__(256)
+center_regroup_kernel(const float* __restrict__ feats, long long rows, int D,
+                      const float* __restrict__ centroid, RowMap map,
+                      __nv_bfloat16* __restrict__ out, int ld_out, long long plane_stride) {
+  const int groups_per_row = D >> 3;
+  const long long total = rows * groups_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups_per_row;
+    const int c = static_cast<int>(i - r * groups_per_row) << 3;
+    const float* src = feats + map.caller_row(r) * D + c;
+    const float4 a = *reinterpret_cast<const float4*>(src);
+    const float4 b = *reinterpret_cast<const float4*>(src + 4);
+    const float4 m0 = __ldg(reinterpret_cast<const float4*>(centroid + c));
+    const float4 m1 = __ldg(reinterpret_cast<const float4*>(centroid + c + 4));
+    uint32_t hi[4], lo[4];
+    split2(a.x - m0.x, a.y - m0.y, hi[0], lo[0]);
+    split2(a.z - m0.z, a.w - m0.w, hi[1], lo[1]);
+    split2(b.x - m1.x, b.y - m1.y, hi[2], lo[2]);
+    split2(b.z - m1.z, b.w - m1.w, hi[3], lo[3]);
+    __nv_bfloat16* dst = out + r * ld_out + c;
+    *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
+int center_regroup(const float* feats, long long rows, int D, const float* centroid,
+                   const RowMap& map, void* out_split, int ld_out, long long plane_stride,
+                   cudaStream_t stream) {
+  ACLIP_REQUIRE(feats && centroid && out_split, "center_regroup: null pointer");
+  ACLIP_REQUIRE(D % 8 == 0 && ld_out % 8 == 0 && ld_out >= D, "center_regroup: D=%d ld=%d unsupported", D, ld_out);
+  ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(feats) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(centroid) & 15) == 0,
+                "center_regroup: inputs must be 16-byte aligned");
+  if (rows <= 0) return ACLIP_OK;
+  center_regroup_kernel<<<grid_for(rows * (D >> 3), 256), 256, 0, stream>>>(
+      feats, rows, D, centroid, map, static_cast<__nv_bfloat16*>(out_split), ld_out, plane_stride);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

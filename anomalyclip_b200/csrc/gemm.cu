@@ -107,7 +107,15 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                     (reinterpret_cast<uintptr_t>(g.w) & 15) == 0,
                 "gemm: operands must be 16-byte aligned");
   ACLIP_REQUIRE(g.out_f32 != nullptr || g.out_split != nullptr, "gemm: no output");
-  ACLIP_REQUIRE(g.ldc % 8 == 0 && g.ldc >= g.N, "gemm: ldc=%d invalid for N=%d", g.ldc, g.N);
+  ACLIP_REQUIRE(g.out_f32 == nullptr || (g.ldc % 4 == 0 && g.ldc >= g.N),
+                "gemm: ldc=%d invalid for N=%d", g.ldc, g.N);
+  {
+    const int lds = g.ld_split > 0 ? g.ld_split : g.ldc;
+    ACLIP_REQUIRE(g.out_split == nullptr ||
+                      (lds % 8 == 0 && lds >= g.N && g.split_plane_stride % 8 == 0 &&
+                       (reinterpret_cast<uintptr_t>(g.out_split) & 15) == 0),
+                  "gemm: split output pitch %d / alignment invalid", lds);
+  }
   ACLIP_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && g.ldr >= g.N), "gemm: ldr=%d invalid",
                 g.ldr);
   ACLIP_REQUIRE(g.act >= 0 && g.act <= 2, "gemm: unknown activation %d", g.act);
@@ -129,6 +137,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.out_split = static_cast<__nv_bfloat16*>(g.out_split);
   p.split_plane_stride = g.split_plane_stride;
   p.ldc = g.ldc;
+  p.ld_split = g.ld_split > 0 ? g.ld_split : g.ldc;
   p.row_group = g.row_group > 0 ? g.row_group : 0x7fffffff;
   p.row_group_stride = g.row_group > 0 ? g.row_group_stride : 0;
   p.row_offset = g.row_offset;

@@ -47,6 +47,7 @@ struct GemmParams {
   __nv_bfloat16* out_split;  // bf16 [2][split_rows][ldc] or nullptr (hi plane, lo plane)
   long long split_plane_stride;  // elements between the hi and lo plane
   int ldc;
+  int ld_split;  // pitch of out_split (elements)
   // output row remap: out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset
   int row_group, row_group_stride, row_offset;
 };
@@ -264,9 +265,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
               lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
                       (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
             }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ldc + n);
+            uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ld_split + n);
             uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
-                                                 out_row * p.ldc + n);
+                                                 out_row * p.ld_split + n);
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);

@@ -1,0 +1,211 @@
+// Row-wise normalisation kernels (HBM-bound; one warp per row, 128-bit accesses):
+//   layernorm_kernel  nn.LayerNorm / axial-attention ChanLayerNorm -> fp32 and/or split-bf16 rows
+//   head_kernel       mean of the reversible halves -> LayerNorm -> Linear(E,1) -> sigmoid,
+//                     plus softmax(similarity) * score, written back in the caller's row order
+#include <cuda_bf16.h>
+
+#include "common.h"
+#include "rowmap.cuh"
+
+namespace aclip {
+
+namespace {
+
+constexpr int kWarpsPerCta = 8;
+constexpr int kMaxVec = 6;  // float4 per lane: D <= 768
+
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
+         (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+// mode 0: (x - mean) / sqrt(var + eps) * g + b      nn.LayerNorm (clip/model.py:174-180)
+// mode 1: (x - mean) / (sqrt(var) + eps) * g + b    ChanLayerNorm of axial_attention (eps on std)
+template <int MODE>
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long ldx,
+                 const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                 float* __restrict__ out_f32, long long ld_f32,
+                 __nv_bfloat16* __restrict__ out_split, long long ld_split,
+                 long long plane_stride) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = D >> 2;
+  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
+  float4 v[kMaxVec];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i] = xr[c];
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float var = warp_sum(q) / static_cast<float>(D);
+  const float rstd = MODE == 0 ? rsqrtf(var + eps) : 1.0f / (sqrtf(var) + eps);
+#pragma unroll
+  for (int i = 0; i < kMaxVec; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      float4 y;
+      y.x = v[i].x * rstd * g.x + b.x;
+      y.y = v[i].y * rstd * g.y + b.y;
+      y.z = v[i].z * rstd * g.z + b.z;
+      y.w = v[i].w * rstd * g.w + b.w;
+      if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * ld_f32)[c] = y;
+      if (out_split != nullptr) {
+        const __nv_bfloat16 h0 = __float2bfloat16_rn(y.x), h1 = __float2bfloat16_rn(y.y);
+        const __nv_bfloat16 h2 = __float2bfloat16_rn(y.z), h3 = __float2bfloat16_rn(y.w);
+        const __nv_bfloat16 l0 = __float2bfloat16_rn(y.x - __bfloat162float(h0));
+        const __nv_bfloat16 l1 = __float2bfloat16_rn(y.y - __bfloat162float(h1));
+        const __nv_bfloat16 l2 = __float2bfloat16_rn(y.z - __bfloat162float(h2));
+        const __nv_bfloat16 l3 = __float2bfloat16_rn(y.w - __bfloat162float(h3));
+        __nv_bfloat16* dst = out_split + row * ld_split + 4 * c;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
+        *reinterpret_cast<uint2*>(dst + plane_stride) =
+            make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+      }
+    }
+  }
+}
+
+// One warp per grid row (sub-video order).  E <= 256.
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+head_kernel(const float* __restrict__ x1, const float* __restrict__ x2, long long rows, int E,
+            const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+            const float* __restrict__ w, float bias, const float* __restrict__ sim, int ld_sim,
+            int ncls, RowMap map, float* __restrict__ scores, float* __restrict__ sim_out,
+            float* __restrict__ probs_out) {
+  const int lane = threadIdx.x & 31;
+  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  const int nvec = E >> 2;
+  float4 v[2];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 a = reinterpret_cast<const float4*>(x1 + row * E)[c];
+      const float4 b = reinterpret_cast<const float4*>(x2 + row * E)[c];
+      // torch.stack(x.chunk(2, dim=1)).mean(dim=0): (a + b) / 2
+      v[i] = make_float4((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f,
+                         (a.w + b.w) * 0.5f);
+      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(E);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(E) + eps);
+  float dot = 0.f;
+#pragma unroll
+  for (int i = 0; i < 2; ++i) {
+    const int c = lane + i * 32;
+    if (c < nvec) {
+      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+      dot += (v[i].x * rstd * g.x + b.x) * ww.x + (v[i].y * rstd * g.y + b.y) * ww.y +
+             (v[i].z * rstd * g.z + b.z) * ww.z + (v[i].w * rstd * g.w + b.w) * ww.w;
+    }
+  }
+  const float z = warp_sum(dot) + bias;
+  const float score = 1.0f / (1.0f + expf(-z));  // nn.Sigmoid (classification_head.py:14)
+  const long long orow = map.caller_row(row);
+  // softmax(similarity, dim=1) * score     (anomaly_clip_module.py:473-477)
+  const float sv = lane < ncls ? sim[row * ld_sim + lane] : -INFINITY;
+  const float mx = warp_max(sv);
+  const float e = lane < ncls ? expf(sv - mx) : 0.f;
+  const float den = warp_sum(e);
+  if (lane == 0) scores[orow] = score;
+  if (lane < ncls) {
+    if (sim_out != nullptr) sim_out[orow * ncls + lane] = sv;
+    if (probs_out != nullptr) probs_out[orow * ncls + lane] = (e / den) * score;
+  }
+}
+
+}  // namespace
+
+int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
+              const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
+              void* out_split, long long ld_split, long long plane_stride, cudaStream_t stream) {
+  ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
+  ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
+  ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
+                    (out_split == nullptr || ld_split % 4 == 0),
+                "layernorm: pitches must be multiples of 4");
+  ACLIP_REQUIRE(mode == 0 || mode == 1, "layernorm: mode must be 0 (LayerNorm) or 1 (ChanLayerNorm)");
+  ACLIP_REQUIRE(out_f32 != nullptr || out_split != nullptr, "layernorm: no output");
+  if (rows <= 0) return ACLIP_OK;
+  const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  auto* os = static_cast<__nv_bfloat16*>(out_split);
+  if (mode == 0)
+    layernorm_kernel<0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  else
+    layernorm_kernel<1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+int score_head(const float* x1, const float* x2, long long rows, int E, const float* gamma,
+               const float* beta, float eps, const float* w, float bias, const float* sim,
+               int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
+               float* probs_out, cudaStream_t stream) {
+  ACLIP_REQUIRE(x1 && x2 && gamma && beta && w && sim && scores, "score_head: null pointer");
+  ACLIP_REQUIRE(E % 4 == 0 && E <= 256, "score_head: E=%d unsupported", E);
+  ACLIP_REQUIRE(ncls >= 1 && ncls <= 32 && ld_sim >= ncls, "score_head: ncls=%d unsupported", ncls);
+  if (rows <= 0) return ACLIP_OK;
+  const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  head_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(x1, x2, rows, E, gamma, beta, eps, w, bias,
+                                                      sim, ld_sim, ncls, map, scores, sim_out,
+                                                      probs_out);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+}  // namespace aclip
+
+extern "C" int aclip_layernorm(const float* x, long long rows, int D, long long ldx,
+                               const float* gamma, const float* beta, float eps, int mode,
+                               float* out_f32, long long ld_f32, void* out_split,
+                               long long ld_split, long long plane_stride, void* stream) {
+  return aclip::layernorm(x, rows, D, ldx, gamma, beta, eps, mode, out_f32, ld_f32, out_split,
+                          ld_split, plane_stride, aclip::as_stream(stream));
+}

@@ -1,0 +1,289 @@
+"""Host side of the two C-ABI entry points: weight packing and call wrappers.
+
+torch is used here for device memory, streams and one-off weight re-layout at checkpoint load;
+the arithmetic of the hot path happens in `aclip_vit_forward` / `aclip_temporal_forward`
+(hand-written sm_100a kernels).  Nothing in this module has a CPU or PyTorch fallback.
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib, ops
+from .synthetic import CLIP_MEAN, CLIP_STD
+
+Weights = Dict[str, torch.Tensor]
+
+
+def _require_cuda(device: torch.device) -> None:
+    if device.type != "cuda":
+        raise _lib.AclipError(
+            "the AnomalyCLIP hot path runs only on a CUDA (sm_100a) device; there is no CPU "
+            f"fallback (got device '{device}')")
+
+
+class _Workspace:
+    """A cached, 1024-byte aligned device scratch buffer."""
+
+    def __init__(self) -> None:
+        self._buf: Optional[torch.Tensor] = None
+        self.nbytes = 0
+
+    def get(self, nbytes: int, device: torch.device) -> int:
+        if self._buf is None or self.nbytes < nbytes or self._buf.device != device:
+            self._buf = None  # release before growing
+            self._buf = torch.empty(nbytes + 1024, dtype=torch.uint8, device=device)
+            self.nbytes = nbytes
+        return (self._buf.data_ptr() + 1023) // 1024 * 1024
+
+
+def _dev_f32(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    return t.detach().to(device=device, dtype=torch.float32).contiguous()
+
+
+def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
+    """fp32 [N, K] -> contiguous split-bf16 [2, N, K] on the device (aclip_split_f32)."""
+    t = _dev_f32(t, device)
+    assert t.dim() == 2 and t.shape[1] % 8 == 0, t.shape
+    return ops.split(t)
+
+
+# ================================================================================ ViT encoder
+class PackedVit:
+    """VisionTransformer state_dict (clip/model.py:233-264 names) -> AclipVitWeights."""
+
+    def __init__(self, sd: Weights, device: torch.device, heads: Optional[int] = None) -> None:
+        _require_cuda(device)
+        self.device = device
+        conv = sd["conv1.weight"]
+        self.width, _, self.patch, _ = conv.shape
+        tokens = sd["positional_embedding"].shape[0]
+        grid = int(round((tokens - 1) ** 0.5))
+        assert grid * grid + 1 == tokens, "positional_embedding is not a square grid + CLS"
+        self.resolution = grid * self.patch
+        self.tokens = tokens
+        self.output_dim = sd["proj"].shape[1]
+        self.heads = heads if heads is not None else self.width // 64  # clip/model.py:487
+        self.layers = 0
+        while f"transformer.resblocks.{self.layers}.ln_1.weight" in sd:
+            self.layers += 1
+
+        keep = self._keep = []
+
+        def f32(name):
+            t = _dev_f32(sd[name], device)
+            keep.append(t)
+            return t.data_ptr()
+
+        def spl(t):
+            s = _split_weight(t, device)
+            keep.append(s)
+            return s.data_ptr()
+
+        self.blocks = (_lib.VitBlock * max(self.layers, 1))()
+        for i in range(self.layers):
+            p = f"transformer.resblocks.{i}."
+            b = self.blocks[i]
+            b.ln1_g, b.ln1_b = f32(p + "ln_1.weight"), f32(p + "ln_1.bias")
+            b.ln2_g, b.ln2_b = f32(p + "ln_2.weight"), f32(p + "ln_2.bias")
+            b.qkv_w, b.qkv_b = spl(sd[p + "attn.in_proj_weight"]), f32(p + "attn.in_proj_bias")
+            b.out_w, b.out_b = spl(sd[p + "attn.out_proj.weight"]), f32(p + "attn.out_proj.bias")
+            b.fc_w, b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
+            b.proj_w, b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
+        w = self.struct = _lib.VitWeights()
+        w.width, w.layers, w.heads = self.width, self.layers, self.heads
+        w.patch, w.resolution, w.output_dim = self.patch, self.resolution, self.output_dim
+        w.conv1_w = spl(conv.reshape(self.width, -1))
+        w.class_embedding = f32("class_embedding")
+        w.positional_embedding = f32("positional_embedding")
+        w.ln_pre_g, w.ln_pre_b = f32("ln_pre.weight"), f32("ln_pre.bias")
+        w.ln_post_g, w.ln_post_b = f32("ln_post.weight"), f32("ln_post.bias")
+        w.proj_w = spl(sd["proj"].t())
+        w.blocks = C.cast(self.blocks, C.POINTER(_lib.VitBlock))
+
+
+class VitEncoder:
+    """frames -> 512-d features through `aclip_vit_forward`."""
+
+    def __init__(self, packed: PackedVit, micro_batch: int = 256, passes: int = 3) -> None:
+        self.packed = packed
+        self.micro_batch = micro_batch
+        self.passes = passes
+        self._ws = _Workspace()
+        self._mean = (C.c_float * 3)(*CLIP_MEAN)
+        self._std = (C.c_float * 3)(*CLIP_STD)
+
+    def __call__(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        p = self.packed
+        if not frames.is_cuda:
+            raise _lib.AclipError("VitEncoder: frames must already be on the CUDA device")
+        if frames.dtype not in (torch.float32, torch.uint8):
+            raise TypeError(f"VitEncoder: frames must be float32 (normalised) or uint8, got {frames.dtype}")
+        if frames.dim() != 4 or tuple(frames.shape[1:]) != (3, p.resolution, p.resolution):
+            raise ValueError(f"VitEncoder: expected (N,3,{p.resolution},{p.resolution}), got {tuple(frames.shape)}")
+        frames = frames.contiguous()
+        n = frames.shape[0]
+        if out is None:
+            out = torch.empty((n, p.output_dim), dtype=torch.float32, device=frames.device)
+        if n == 0:
+            return out
+        lib = _lib.load()
+        mb = max(1, min(self.micro_batch, n))
+        nbytes = lib.aclip_vit_workspace_bytes(C.byref(p.struct), mb)
+        ws = self._ws.get(nbytes, frames.device)
+        _lib.check(lib.aclip_vit_forward(
+            C.byref(p.struct), frames.data_ptr(), int(frames.dtype == torch.uint8), n, mb,
+            self._mean, self._std, out.data_ptr(), ws, nbytes, self.passes,
+            torch.cuda.current_stream().cuda_stream))
+        return out
+
+
+# ================================================================================ temporal path
+def selector_operands(text_features: torch.Tensor, ncentroid: torch.Tensor, normal_id: int,
+                      bn_mean: torch.Tensor, bn_var: torch.Tensor, bn_eps: float = 1e-5
+                      ) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Fold the constants of SelectorModel.forward (selector_model.py:44-65) into one GEMM operand:
+    rows = normalised re-centred text directions x BatchNorm eval scale, bias = -mean * scale.
+    Returned padded to 32 rows (the GEMM's column granule)."""
+    t = torch.cat((text_features[:normal_id], text_features[normal_id + 1:]), dim=0)  # :44-50
+    t = t - ncentroid                                                                 # :53
+    t = t / t.norm(dim=-1, keepdim=True)                                              # :57-59
+    scale = torch.rsqrt(bn_var + bn_eps)
+    w = torch.zeros((32, t.shape[1]), dtype=torch.float32, device=t.device)
+    b = torch.zeros(32, dtype=torch.float32, device=t.device)
+    w[: t.shape[0]] = t * scale[:, None]
+    b[: t.shape[0]] = -bn_mean * scale
+    return w, b
+
+
+class PackedTemporal:
+    """selector_model.* / temporal_model.* state_dict entries -> AclipTemporalWeights."""
+
+    def __init__(self, sd: Weights, device: torch.device, *, num_classes: int, normal_id: int,
+                 emb_size: int, depth: int, heads: int, num_segments: int, seg_length: int,
+                 concat_features: bool, feature_dim: int = 512) -> None:
+        _require_cuda(device)
+        self.device = device
+        self.num_classes, self.normal_id = num_classes, normal_id
+        self.num_dirs = num_classes - 1
+        if self.num_dirs > 32:
+            raise ValueError("at most 33 classes are supported")
+        E = emb_size
+        keep = self._keep = []
+        self._dir_keep: Sequence[torch.Tensor] = ()
+        self._dir_key = None
+
+        def f32t(t):
+            t = _dev_f32(t, device)
+            keep.append(t)
+            return t.data_ptr()
+
+        def spl(t):
+            s = _split_weight(t, device)
+            keep.append(s)
+            return s.data_ptr()
+
+        pre = "temporal_model."
+        self.bn_mean = _dev_f32(sd["selector_model.bn_layer.running_mean"], device)
+        self.bn_var = _dev_f32(sd["selector_model.bn_layer.running_var"], device)
+        w = self.struct = _lib.TemporalWeights()
+        w.feature_dim, w.num_dirs, w.emb, w.depth, w.heads = feature_dim, self.num_dirs, E, depth, heads
+        w.num_segments, w.seg_length, w.concat = num_segments, seg_length, int(concat_features)
+        w.ldf = feature_dim + (32 if concat_features else 0)
+
+        pw = sd[pre + "projection.weight"].detach().to(torch.float32)
+        in_dim = feature_dim + self.num_dirs * int(concat_features)
+        if tuple(pw.shape) != (E, in_dim):
+            raise ValueError(f"projection.weight is {tuple(pw.shape)}, expected {(E, in_dim)}")
+        if concat_features:  # reference input is [similarity | x]; packed rows are [x | similarity | 0]
+            pw = torch.cat((pw[:, self.num_dirs:], pw[:, : self.num_dirs],
+                            pw.new_zeros(E, 32 - self.num_dirs)), dim=1)
+        w.proj_w, w.proj_b = spl(pw), f32t(sd[pre + "projection.bias"])
+        p0 = sd[pre + "axial_attn.pos_emb.param_0"].to(torch.float32)  # (1,E,n,1)
+        p1 = sd[pre + "axial_attn.pos_emb.param_1"].to(torch.float32)  # (1,E,1,l)
+        pos = (p0 + p1)[0].permute(1, 2, 0).reshape(num_segments * seg_length, E)
+        w.pos = f32t(pos)
+
+        self.attn = (_lib.AxialAttnWeights * max(2 * depth, 1))()
+        self.ff = (_lib.ConvFFWeights * max(2 * depth, 1))()
+        for d in range(depth):
+            for j, fg in enumerate(("f", "g")):
+                q = f"{pre}axial_attn.layers.blocks.{2 * d}.{fg}.net.fn."
+                a = self.attn[2 * d + j]
+                a.norm_g, a.norm_b = f32t(sd[q + "norm.weight"]), f32t(sd[q + "norm.bias"])
+                wq, wkv = sd[q + "fn.to_q.weight"], sd[q + "fn.to_kv.weight"]
+                if tuple(wq.shape) != (E, E):
+                    raise ValueError("dim_heads must be emb_size // heads (the reference's default)")
+                a.qkv_w = spl(torch.cat((wq, wkv), dim=0).to(torch.float32))
+                a.out_w, a.out_b = spl(sd[q + "fn.to_out.weight"]), f32t(sd[q + "fn.to_out.bias"])
+                q = f"{pre}axial_attn.layers.blocks.{2 * d + 1}.{fg}.net."
+                c = self.ff[2 * d + j]
+                c.g, c.b = f32t(sd[q + "0.g"].reshape(E)), f32t(sd[q + "0.b"].reshape(E))
+                c.conv1_w = spl(sd[q + "1.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(4 * E, 9 * E))
+                c.conv1_b = f32t(sd[q + "1.bias"])
+                c.conv2_w = spl(sd[q + "3.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(E, 36 * E))
+                c.conv2_b = f32t(sd[q + "3.bias"])
+        w.attn = C.cast(self.attn, C.POINTER(_lib.AxialAttnWeights))
+        w.ff = C.cast(self.ff, C.POINTER(_lib.ConvFFWeights))
+        w.head_ln_g = f32t(sd[pre + "classifier.layer_norm.weight"])
+        w.head_ln_b = f32t(sd[pre + "classifier.layer_norm.bias"])
+        w.head_w = f32t(sd[pre + "classifier.linear.weight"].reshape(E))
+        w.head_bias = float(sd[pre + "classifier.linear.bias"].reshape(-1)[0])
+
+    def set_directions(self, text_features: torch.Tensor, ncentroid: torch.Tensor) -> None:
+        """(Re)build the selector operand; a no-op when called again with the same tensors."""
+        key = (text_features.data_ptr(), text_features._version, ncentroid.data_ptr(),
+               ncentroid._version)
+        if key == self._dir_key:
+            return
+        tf = _dev_f32(text_features, self.device)
+        m = _dev_f32(ncentroid, self.device)
+        if tf.shape[0] != self.num_classes:
+            raise ValueError(f"text_features has {tf.shape[0]} rows, expected {self.num_classes}")
+        sw, sb = selector_operands(tf, m, self.normal_id, self.bn_mean, self.bn_var)
+        sws = ops.split(sw)
+        self._dir_keep = (m, sws, sb, text_features, ncentroid)
+        self.struct.ncentroid = m.data_ptr()
+        self.struct.selector_w = sws.data_ptr()
+        self.struct.selector_b = sb.data_ptr()
+        self._dir_key = key
+
+
+class TemporalScorer:
+    """feature rows -> (similarity, scores, class_probs) through `aclip_temporal_forward`."""
+
+    def __init__(self, packed: PackedTemporal, passes: int = 3,
+                 max_chunk_sub_videos: int = 512) -> None:
+        self.packed = packed
+        self.passes = passes
+        self.max_chunk = max_chunk_sub_videos
+        self._ws = _Workspace()
+
+    def __call__(self, features: torch.Tensor, segment_size: int = 1, want_probs: bool = True):
+        p = self.packed
+        if p.struct.selector_w is None:
+            raise _lib.AclipError("TemporalScorer: set_directions() has not been called")
+        if not features.is_cuda or features.dtype != torch.float32:
+            raise TypeError("TemporalScorer: features must be a CUDA float32 tensor")
+        feats = features.reshape(-1, features.shape[-1]).contiguous()
+        unit = p.struct.num_segments * p.struct.seg_length
+        n_rows = feats.shape[0]
+        if feats.shape[1] != p.struct.feature_dim or n_rows % (unit * segment_size) != 0:
+            raise ValueError(f"TemporalScorer: {tuple(feats.shape)} rows are not a multiple of "
+                             f"num_segments*seg_length*segment_size = {unit * segment_size}")
+        sub_videos = n_rows // unit
+        dev = feats.device
+        sim = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev)
+        scores = torch.empty((n_rows,), dtype=torch.float32, device=dev)
+        probs = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev) if want_probs else None
+        lib = _lib.load()
+        chunk = max(1, min(sub_videos, self.max_chunk))
+        nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), chunk)
+        ws = self._ws.get(nbytes, dev)
+        _lib.check(lib.aclip_temporal_forward(
+            C.byref(p.struct), feats.data_ptr(), sub_videos, segment_size, sim.data_ptr(),
+            scores.data_ptr(), probs.data_ptr() if probs is not None else None, ws, nbytes,
+            self.passes, torch.cuda.current_stream().cuda_stream))
+        return sim, scores, probs

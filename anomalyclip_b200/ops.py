@@ -85,10 +85,50 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if out_f32 is not None:
         g.out_f32, g.ldc = out_f32.data_ptr(), out_f32.stride(-2)
     if out_split is not None:
-        g.out_split, g.ldc = out_split.data_ptr(), out_split.stride(1)
+        g.out_split, g.ld_split = out_split.data_ptr(), out_split.stride(1)
         g.split_plane_stride = out_split.stride(0)
     if row_map is not None:
         g.row_group, g.row_group_stride, g.row_offset = row_map
     g.max_ctas = max_ctas
     _lib.check(lib.aclip_gemm(C.byref(g), _stream()))
     return out_f32 if out_f32 is not None else out_split
+
+
+def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5,
+              chan_mode: bool = False, want_f32: bool = True, want_split: bool = False):
+    """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std)."""
+    x = _f32c(x, "x")
+    rows, D = x.reshape(-1, x.shape[-1]).shape
+    out_f32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
+    out_split = torch.empty((2, rows, D), dtype=torch.bfloat16, device=x.device) if want_split else None
+    lib = _lib.load()
+    _lib.check(lib.aclip_layernorm(
+        x.data_ptr(), rows, D, D, _f32c(gamma, "gamma").data_ptr(), _f32c(beta, "beta").data_ptr(),
+        eps, 1 if chan_mode else 0, _ptr(out_f32), D, _ptr(out_split), D,
+        out_split.stride(0) if out_split is not None else 0, _stream()))
+    if want_f32 and want_split:
+        return out_f32, out_split
+    return out_f32 if want_f32 else out_split
+
+
+def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int) -> torch.Tensor:
+    """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64]."""
+    W = heads * 64
+    out = torch.empty((2, B * L, W), dtype=torch.bfloat16, device=qkv_split.device)
+    lib = _lib.load()
+    _lib.check(lib.aclip_vit_attention(qkv_split.data_ptr(), qkv_split.stride(0),
+                                       qkv_split.stride(1), B, L, heads, out.data_ptr(),
+                                       out.stride(0), out.stride(1), _stream()))
+    return out
+
+
+def axial_attention(qkv: torch.Tensor, sub_videos: int, n: int, l: int, heads: int,
+                    axis: int) -> torch.Tensor:
+    """qkv: fp32 [sub_videos*n*l, 3E] in sub-video order -> split [2, rows, E]."""
+    qkv = _f32c(qkv, "qkv")
+    E = qkv.shape[1] // 3
+    out = torch.empty((2, qkv.shape[0], E), dtype=torch.bfloat16, device=qkv.device)
+    lib = _lib.load()
+    _lib.check(lib.aclip_axial_attention(qkv.data_ptr(), sub_videos, n, l, E, heads, axis,
+                                         out.data_ptr(), out.stride(0), _stream()))
+    return out

@@ -75,7 +75,8 @@ typedef struct AclipGemmArgs {
   float* out_f32;        /* fp32 [*][ldc] or NULL */
   void* out_split;       /* bf16 [2][*][ldc] or NULL */
   long long split_plane_stride;
-  int ldc;
+  int ldc;               /* pitch of out_f32 (and of out_split when ld_split == 0) */
+  int ld_split;          /* pitch of out_split, 0 = ldc */
   /* output row remap (0,0,0 = identity):
    * out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset */
   int row_group, row_group_stride, row_offset;
@@ -84,6 +85,107 @@ typedef struct AclipGemmArgs {
 
 /* tcgen05 / TMA GEMM with fused epilogue. N must be a multiple of 32, K a multiple of 8. */
 int aclip_gemm(const AclipGemmArgs* args, void* stream);
+
+/* nn.LayerNorm (mode 0, clip/model.py:174-180) or axial_attention's ChanLayerNorm (mode 1:
+ * (x-mean)/(std+eps)) over rows of D fp32 values; writes fp32 and/or split-bf16 rows. */
+int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
+                    const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
+                    void* out_split, long long ld_split, long long plane_stride, void* stream);
+
+/* softmax(Q K^T / 8) V for B frames of L tokens, `heads` heads of 64 dims; qkv_split is the
+ * split-bf16 [2][B*L][ld_in] output of the in_proj GEMM (q | k | v), out_split [2][B*L][ld_out].
+ * Replaces nn.MultiheadAttention inside ResidualAttentionBlock.attention (clip/model.py:206-212). */
+int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                        int heads, void* out_split, long long out_plane_stride, int ld_out,
+                        void* stream);
+
+/* Axial self-attention over fp32 qkv rows [sub_videos*n*l][3E] in sub-video order; axis 0 = along
+ * the n segments, axis 1 = along the l frames.  Output split-bf16 [2][rows][E].
+ * Replaces axial_attention.SelfAttention under PermuteToFrom (temporal_model.py:32-39,64). */
+int aclip_axial_attention(const float* qkv, long long sub_videos, int n, int l, int E, int heads,
+                          int axis, void* out_split, long long plane_stride, void* stream);
+
+/* ------------------------------------------------------------------------------------------
+ * The two hot-path entry points.  Weight structs hold DEVICE pointers to tensors the caller
+ * packed once per checkpoint ("split" = bf16 [2][rows][cols], planes contiguous); the structs
+ * themselves and the per-layer arrays they point to live in HOST memory.
+ * ---------------------------------------------------------------------------------------- */
+
+typedef struct AclipVitBlock {      /* one ResidualAttentionBlock, clip/model.py:188-217 */
+  const float *ln1_g, *ln1_b, *ln2_g, *ln2_b;
+  const void* qkv_w;  const float* qkv_b;   /* attn.in_proj_weight  split [2][3W][W]  */
+  const void* out_w;  const float* out_b;   /* attn.out_proj.weight split [2][W][W]   */
+  const void* fc_w;   const float* fc_b;    /* mlp.c_fc.weight      split [2][4W][W]  */
+  const void* proj_w; const float* proj_b;  /* mlp.c_proj.weight    split [2][W][4W]  */
+} AclipVitBlock;
+
+typedef struct AclipVitWeights {    /* VisionTransformer, clip/model.py:233-264 */
+  int width, layers, heads, patch, resolution, output_dim;
+  const void* conv1_w;                /* conv1.weight.reshape(W, 3*P*P) split [2][W][3PP] */
+  const float* class_embedding;       /* [W] */
+  const float* positional_embedding;  /* [(R/P)^2 + 1][W] */
+  const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
+  const void* proj_w;                 /* proj^T split [2][output_dim][W] */
+  const AclipVitBlock* blocks;        /* host array [layers] */
+} AclipVitWeights;
+
+size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
+
+/* features_out[num_frames][output_dim] = VisionTransformer.forward(frames)  (clip/model.py:266-290).
+ * frames: (num_frames,3,R,R) fp32 already normalised, or uint8 (frames_are_u8 != 0), in which case
+ * ToTensor + Normalize(mean3_host, std3_host) (src/utils/augmentations.py:21-34) run on the GPU.
+ * Frames are processed in micro-batches of `micro_batch` through `workspace`
+ * (>= aclip_vit_workspace_bytes(w, micro_batch) bytes, 1024-byte aligned).
+ * passes = 3: split-bf16 GEMMs (fp32-faithful, the parity mode); passes = 1: plain bf16 GEMMs. */
+int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
+                      long long num_frames, int micro_batch, const float* mean3_host,
+                      const float* std3_host, float* features_out, void* workspace,
+                      size_t workspace_bytes, int passes, void* stream);
+
+typedef struct AclipAxialAttnWeights { /* PreNorm(SelfAttention), one per axis per depth */
+  const float *norm_g, *norm_b;       /* nn.LayerNorm(E) */
+  const void* qkv_w;                  /* [to_q.weight ; to_kv.weight] split [2][3E][E], no bias */
+  const void* out_w; const float* out_b; /* to_out split [2][E][E], bias [E] */
+} AclipAxialAttnWeights;
+
+typedef struct AclipConvFFWeights {   /* ChanLayerNorm -> conv3x3 -> LeakyReLU -> conv3x3 */
+  const float *g, *b;                 /* [E] */
+  const void* conv1_w; const float* conv1_b; /* split [2][4E][9*E], k = (ky*3+kx)*E + c */
+  const void* conv2_w; const float* conv2_b; /* split [2][E][9*4E] */
+} AclipConvFFWeights;
+
+typedef struct AclipTemporalWeights { /* SelectorModel (test branch) + TemporalModel + head */
+  int feature_dim;      /* 512 */
+  int num_dirs;         /* C - 1 similarity columns (<= 32) */
+  int emb, depth, heads, num_segments, seg_length;
+  int concat;           /* concat_features: temporal input = [similarity, x - ncentroid] */
+  int ldf;              /* pitch of the packed feature rows: feature_dim (+ 32 if concat) */
+  const float* ncentroid;   /* [feature_dim] */
+  const void* selector_w;   /* split [2][32][feature_dim]: normalised, re-centred text directions
+                               scaled by the BatchNorm eval factor; rows >= num_dirs are zero */
+  const float* selector_b;  /* [32]: -running_mean / sqrt(running_var + eps), zero padded */
+  const void* proj_w;       /* projection.weight with columns reordered to [x | sim | 0],
+                               split [2][emb][ldf] */
+  const float* proj_b;      /* [emb] */
+  const float* pos;         /* [n*l][emb]: pos_emb.param_0[i] + pos_emb.param_1[k] */
+  const AclipAxialAttnWeights* attn; /* host array [2*depth]: (axis n, axis l) per depth */
+  const AclipConvFFWeights* ff;      /* host array [2*depth]: (f, g) per depth */
+  const float *head_ln_g, *head_ln_b, *head_w; /* classifier.layer_norm, classifier.linear.weight */
+  float head_bias;
+} AclipTemporalWeights;
+
+size_t aclip_temporal_workspace_bytes(const AclipTemporalWeights* w, long long sub_videos);
+
+/* AnomalyCLIP.forward(test_mode=True) after the image encoder (anomaly_clip.py:132-154) fused with
+ * test_step's softmax(similarity) * score (anomaly_clip_module.py:473-477).
+ * features: fp32 [N][feature_dim], rows in the caller's "(b n s l)" order, N = sub_videos*n*l with
+ * sub_videos = b*segment_size.  Outputs in the same row order: similarity_out [N][num_dirs],
+ * scores_out [N], class_probs_out [N][num_dirs] (may be NULL).  Sub-videos are processed in as
+ * large chunks as `workspace` allows. */
+int aclip_temporal_forward(const AclipTemporalWeights* w, const float* features,
+                           long long sub_videos, int segment_size, float* similarity_out,
+                           float* scores_out, float* class_probs_out, void* workspace,
+                           size_t workspace_bytes, int passes, void* stream);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,95 @@
+"""aclip_temporal_forward (selector + temporal transformer + head + class probabilities) against
+the CPU oracle for the three dataset configurations of the reference."""
+import pytest
+import torch
+
+from oracle import anomalyclip_oracle as oracle
+from tests.parity import assert_parity
+from tests.util_weights import (PRESETS, make_features, make_ncentroid, make_state_dict,
+                                make_text_features)
+
+pytestmark = pytest.mark.gpu
+
+
+def _scorer(cfg, sd, passes=3, max_chunk=512):
+    from anomalyclip_b200.engine import PackedTemporal, TemporalScorer
+    packed = PackedTemporal(sd, torch.device("cuda"), num_classes=cfg.num_classes,
+                            normal_id=cfg.normal_id, emb_size=cfg.emb_size, depth=cfg.depth,
+                            heads=cfg.heads, num_segments=cfg.num_segments,
+                            seg_length=cfg.seg_length, concat_features=cfg.concat_features)
+    return TemporalScorer(packed, passes=passes, max_chunk_sub_videos=max_chunk)
+
+
+def _oracle(cfg, sd, feats, text, m, s):
+    return oracle.anomaly_clip_forward(
+        sd, feats, m, text, segment_size=s, normal_id=cfg.normal_id,
+        num_segments=cfg.num_segments, seg_length=cfg.seg_length, depth=cfg.depth,
+        heads=cfg.heads, concat_features=cfg.concat_features)
+
+
+@pytest.mark.parametrize("name,segment_size", [("ucfcrime", 1), ("ucfcrime", 2), ("shanghaitech", 1),
+                                               ("shanghaitech", 3), ("xdviolence", 2)])
+def test_temporal_path_matches_oracle(name, segment_size):
+    cfg = PRESETS[name]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    feats = make_features(cfg, segment_size, seed=segment_size)          # (1,1,s*512,512)
+    sim_ref, sc_ref = _oracle(cfg, sd, feats, text, m, segment_size)
+    probs_ref, _ = oracle.test_step_postprocess(sim_ref, sc_ref)
+    scorer = _scorer(cfg, sd)
+    scorer.packed.set_directions(text, m)
+    sim, sc, probs = scorer(feats.cuda(), segment_size)
+    assert_parity(sim, sim_ref, f"{name} similarity")
+    assert_parity(sc, sc_ref, f"{name} scores")
+    assert_parity(probs, probs_ref, f"{name} class probabilities")
+    assert torch.equal(probs.argmax(1).cpu(), probs_ref.argmax(1)), "argmax class differs"
+    assert torch.equal(probs.topk(5, dim=1).indices.cpu(), probs_ref.topk(5, dim=1).indices)
+
+
+def test_batch_of_videos_and_chunked_workspace():
+    """b=2 videos x s=2 sub-videos; forcing 1-sub-video chunks must not change anything."""
+    cfg = PRESETS["ucfcrime"]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    feats = make_features(cfg, 4, seed=11).reshape(2, 1, 2 * cfg.unit, 512)
+    sim_ref, sc_ref = _oracle(cfg, sd, feats, text, m, 2)
+    a = _scorer(cfg, sd)
+    a.packed.set_directions(text, m)
+    sim, sc, _ = a(feats.cuda(), 2)
+    assert_parity(sim, sim_ref, "batched similarity")
+    assert_parity(sc, sc_ref, "batched scores")
+    b = _scorer(cfg, sd, max_chunk=1)
+    b.packed.set_directions(text, m)
+    sim1, sc1, _ = b(feats.cuda(), 2)
+    assert torch.equal(sim, sim1) and torch.equal(sc, sc1)
+
+
+def test_full_path_frames_to_scores_matches_oracle():
+    """ShanghaiTech-shaped wiring: frames -> ViT (2 layers to keep the CPU oracle quick) ->
+    selector -> temporal -> scores, load_from_features=False."""
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    from tests.util_weights import make_frames_u8, normalise_frames
+    cfg = PRESETS["shanghaitech"]
+    sd = make_state_dict(cfg, with_vit=True, vit_layers=2)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    frames = normalise_frames(make_frames_u8(cfg.unit, seed=1))
+    sim_ref, sc_ref = oracle.anomaly_clip_forward(
+        sd, frames.unsqueeze(0), m, text, segment_size=1, normal_id=cfg.normal_id,
+        num_segments=cfg.num_segments, seg_length=cfg.seg_length, depth=cfg.depth,
+        heads=cfg.heads, concat_features=cfg.concat_features, load_from_features=False)
+    vit_sd = {k[len("image_encoder."):]: v for k, v in sd.items() if k.startswith("image_encoder.")}
+    enc = VitEncoder(PackedVit(vit_sd, torch.device("cuda")), micro_batch=256)
+    scorer = _scorer(cfg, sd)
+    scorer.packed.set_directions(text, m)
+    sim, sc, _ = scorer(enc(frames.cuda()), 1)
+    assert_parity(sim, sim_ref, "full path similarity")
+    assert_parity(sc, sc_ref, "full path scores")
+
+
+def test_rows_must_fill_whole_sub_videos():
+    cfg = PRESETS["xdviolence"]
+    sd = make_state_dict(cfg, with_vit=False)
+    scorer = _scorer(cfg, sd)
+    scorer.packed.set_directions(make_text_features(cfg), make_ncentroid(cfg))
+    with pytest.raises(ValueError):
+        scorer(torch.zeros(100, 512, device="cuda"), 1)
