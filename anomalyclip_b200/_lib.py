@@ -67,12 +67,23 @@ class TemporalWeights(C.Structure):
                [("head_bias", C.c_float)]
 
 
+class TimingRow(C.Structure):
+    _fields_ = [("name", C.c_char * 32), ("launches", C.c_longlong), ("ms", C.c_double),
+                ("flops", C.c_double), ("bytes", C.c_double)]
+
+
 # name -> (restype, argtypes); every symbol include/aclip_b200.h declares
 SIGNATURES = {
     "aclip_version": (C.c_int, []),
     "aclip_last_error": (C.c_char_p, []),
     "aclip_launch_count": (C.c_longlong, []),
+    "aclip_timing_enable": (C.c_int, [C.c_int]),
+    "aclip_timing_collect": (C.c_int, [C.POINTER(TimingRow), C.c_int]),
     "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),
+    "aclip_center_regroup": (C.c_int, [vp, C.c_longlong, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp,
+                                       C.c_int, C.c_longlong, vp]),
+    "aclip_patchify": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
+                                 C.POINTER(C.c_float), vp, C.c_longlong, vp]),
     "aclip_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "aclip_layernorm": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_longlong, vp, vp, C.c_float,
                                   C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp]),
@@ -123,3 +134,18 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().aclip_launch_count())
+
+
+def timing_enable(on: bool) -> None:
+    check(load().aclip_timing_enable(int(on)))
+
+
+def timing_collect() -> dict:
+    """{kernel kind: {launches, ms, flops, bytes}} since the last collect (synchronises)."""
+    rows = (TimingRow * 16)()
+    n = load().aclip_timing_collect(rows, 16)
+    if n < 0:
+        check(n)
+    return {rows[i].name.decode(): {"launches": int(rows[i].launches), "ms": rows[i].ms,
+                                    "flops": rows[i].flops, "bytes": rows[i].bytes}
+            for i in range(n) if rows[i].launches > 0}

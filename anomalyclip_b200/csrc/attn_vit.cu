@@ -273,9 +273,12 @@ int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, i
   }
   const float sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid(2, heads, B);
+  timing_begin(KIND_VIT_ATTENTION, stream);
   vit_attention_kernel<<<grid, ATT_THREADS, smem, stream>>>(
       static_cast<const __nv_bfloat16*>(qkv_split), in_plane_stride, ld_in, L, LP, heads * HD,
       static_cast<__nv_bfloat16*>(out_split), out_plane_stride, ld_out, sl2);
+  timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
+             (double)B * L * heads * HD * (3 * 4.0 + 4.0));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

@@ -139,6 +139,7 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
   const float scale = 1.0f / sqrtf(static_cast<float>(eh));
   const int smem = heads * 2 * MAX_L * eh * static_cast<int>(sizeof(float));
   auto* o = static_cast<__nv_bfloat16*>(out_split);
+  timing_begin(KIND_AXIAL_ATTENTION, stream);
   if (eh == 32) {
     static bool configured = false;
     if (!configured) {
@@ -152,6 +153,7 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
     axial_attention_kernel<16><<<static_cast<unsigned>(seqs), heads * 32, smem, stream>>>(
         qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride);
   }
+  timing_end(KIND_AXIAL_ATTENTION, stream, 4.0 * seqs * (double)L * L * E, (double)seqs * L * E * 16.0);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

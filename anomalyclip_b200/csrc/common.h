@@ -66,6 +66,15 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
     if (_rc != ACLIP_OK) return _rc;                                                     \
   } while (0)
 
+// Optional per-kernel-kind device timing (cudaEvent pairs around each launch), used by bench.py
+// for the roofline numbers.  Off by default; when off the cost is one relaxed atomic load.
+enum KernelKind : int {
+  KIND_GEMM = 0, KIND_VIT_ATTENTION, KIND_LAYERNORM, KIND_PATCHIFY, KIND_CLS_ROWS,
+  KIND_CENTER_REGROUP, KIND_AXIAL_ATTENTION, KIND_SCORE_HEAD, KIND_SPLIT, KIND_COUNT
+};
+void timing_begin(int kind, cudaStream_t stream);
+void timing_end(int kind, cudaStream_t stream, double flops, double bytes);
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace aclip

@@ -68,8 +68,10 @@ int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, i
   if (rows == 0) return ACLIP_OK;
   const bool vec_ok = (ld_in % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
   const long long total = rows * (ld_out >> 3);
+  timing_begin(KIND_SPLIT, stream);
   split_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
       in, rows, cols, ld_in, static_cast<__nv_bfloat16*>(out), ld_out, plane_stride, vec_ok);
+  timing_end(KIND_SPLIT, stream, 0.0, (double)rows * (4.0 * cols + 4.0 * ld_out));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -139,10 +141,12 @@ int patchify(const void* frames, int is_u8, int B, int R, int P, const float* me
   const int G = R / P;
   const long long total = static_cast<long long>(B) * G * G * (3 * P * P / 8);
   auto* o = static_cast<__nv_bfloat16*>(out_split);
+  timing_begin(KIND_PATCHIFY, stream);
   if (is_u8)
     patchify_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
   else
     patchify_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  timing_end(KIND_PATCHIFY, stream, 0.0, (double)B * 3 * R * R * ((is_u8 ? 1.0 : 4.0) + 4.0));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -161,7 +165,9 @@ __global__ void cls_rows_kernel(float* __restrict__ x, int B, int tokens, int wi
 int cls_rows(float* x, int B, int tokens, int width, const float* cls, const float* pos,
              cudaStream_t stream) {
   ACLIP_REQUIRE(x && cls && pos && B > 0, "cls_rows: bad arguments");
+  timing_begin(KIND_CLS_ROWS, stream);
   cls_rows_kernel<<<(B * width + 255) / 256, 256, 0, stream>>>(x, B, tokens, width, cls, pos);
+  timing_end(KIND_CLS_ROWS, stream, 0.0, 4.0 * B * width);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -206,8 +212,10 @@ int center_regroup(const float* feats, long long rows, int D, const float* centr
                     (reinterpret_cast<uintptr_t>(centroid) & 15) == 0,
                 "center_regroup: inputs must be 16-byte aligned");
   if (rows <= 0) return ACLIP_OK;
+  timing_begin(KIND_CENTER_REGROUP, stream);
   center_regroup_kernel<<<grid_for(rows * (D >> 3), 256), 256, 0, stream>>>(
       feats, rows, D, centroid, map, static_cast<__nv_bfloat16*>(out_split), ld_out, plane_stride);
+  timing_end(KIND_CENTER_REGROUP, stream, (double)rows * D, (double)rows * D * 8.0);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -219,4 +227,22 @@ extern "C" int aclip_split_f32(const float* in, long long rows, int cols, int ld
                                void* out_split, int ld_out, long long plane_stride, void* stream) {
   return aclip::split_f32(in, rows, cols, ld_in, out_split, ld_out, plane_stride,
                           aclip::as_stream(stream));
+}
+
+extern "C" int aclip_center_regroup(const float* feats, long long rows, int D,
+                                    const float* centroid, int num_segments, int segment_size,
+                                    int seg_length, void* out_split, int ld_out,
+                                    long long plane_stride, void* stream) {
+  if (num_segments < 1 || segment_size < 1 || seg_length < 1)
+    return aclip::fail(ACLIP_ERR_INVALID, "center_regroup: n, s, l must be >= 1");
+  const aclip::RowMap map{num_segments, segment_size, seg_length, 0};
+  return aclip::center_regroup(feats, rows, D, centroid, map, out_split, ld_out, plane_stride,
+                               aclip::as_stream(stream));
+}
+
+extern "C" int aclip_patchify(const void* frames, int frames_are_u8, int B, int R, int P,
+                              const float* mean3_host, const float* std3_host, void* out_split,
+                              long long plane_stride, void* stream) {
+  return aclip::patchify(frames, frames_are_u8, B, R, P, mean3_host, std3_host, out_split,
+                         plane_stride, aclip::as_stream(stream));
 }

@@ -90,7 +90,17 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   int ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > m_tiles * n_tiles) ctas = m_tiles * n_tiles;
+  timing_begin(KIND_GEMM, stream);
   kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  {
+    const double planes = PASSES == 1 ? 1.0 : 2.0;
+    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
+    // algorithmic: 2MNK flops (one product per term, whatever the number of passes); bytes = each
+    // operand once + outputs (+ residual) once; the conv mode reads each activation once, not 9x
+    const double a_elems = p.a_mode == 1 ? (double)p.M * (p.K / 9) : (double)p.M * p.K;
+    timing_end(KIND_GEMM, stream, 2.0 * p.M * (double)p.N * p.K,
+               planes * 2.0 * (a_elems + (double)p.N * p.K) + out_b * (double)p.M * p.N);
+  }
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

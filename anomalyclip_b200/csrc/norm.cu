@@ -172,12 +172,15 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   if (rows <= 0) return ACLIP_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   auto* os = static_cast<__nv_bfloat16*>(out_split);
+  timing_begin(KIND_LAYERNORM, stream);
   if (mode == 0)
     layernorm_kernel<0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   else
     layernorm_kernel<1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  timing_end(KIND_LAYERNORM, stream, 8.0 * rows * D,
+             (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? 4.0 : 0.0)));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -192,9 +195,11 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
   ACLIP_REQUIRE(ncls >= 1 && ncls <= 32 && ld_sim >= ncls, "score_head: ncls=%d unsupported", ncls);
   if (rows <= 0) return ACLIP_OK;
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
+  timing_begin(KIND_SCORE_HEAD, stream);
   head_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(x1, x2, rows, E, gamma, beta, eps, w, bias,
                                                       sim, ld_sim, ncls, map, scores, sim_out,
                                                       probs_out);
+  timing_end(KIND_SCORE_HEAD, stream, 12.0 * rows * E, (double)rows * (8.0 * E + 4.0 * ld_sim + 4.0 + 8.0 * ncls));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

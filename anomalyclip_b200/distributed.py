@@ -1,0 +1,81 @@
+"""Multi-GPU plumbing of the path: sub-videos shard across ranks with no data-path collective;
+the only exchange is ONE all-gather of the per-frame result rows [score | class_probs] at the end
+(SURVEY 8e).  The reference has no working multi-GPU inference (its test_step is
+`@rank_zero_only`, anomaly_clip_module.py:458), so this is new surface, kept minimal.
+
+One process per GPU, `torch.distributed` with the NCCL backend on the B200 box (NVLink 5 /
+NVSwitch); the same code runs under gloo on CPU for the world_size-2 tests.
+"""
+from __future__ import annotations
+
+from typing import Callable, List, Optional, Sequence, Tuple
+
+import torch
+import torch.distributed as dist
+
+
+def partition(num_units: int, world_size: int) -> List[Tuple[int, int]]:
+    """Contiguous, balanced (start, count) blocks of sub-videos, one per rank; the first
+    `num_units % world_size` ranks take one extra unit."""
+    if num_units < 0 or world_size < 1:
+        raise ValueError("partition: num_units >= 0 and world_size >= 1 required")
+    base, extra = divmod(num_units, world_size)
+    out, start = [], 0
+    for r in range(world_size):
+        cnt = base + (1 if r < extra else 0)
+        out.append((start, cnt))
+        start += cnt
+    return out
+
+
+def gather_rows(local: torch.Tensor, counts: Sequence[int], group: Optional[dist.ProcessGroup] = None
+                ) -> torch.Tensor:
+    """All-gather of row blocks of (possibly) different heights: `local` is this rank's
+    [counts[rank], width] block; returns the concatenation [sum(counts), width] on every rank.
+    A single collective: blocks are padded to the tallest one."""
+    if not (dist.is_available() and dist.is_initialized()):
+        return local
+    world = dist.get_world_size(group)
+    rank = dist.get_rank(group)
+    if len(counts) != world or local.shape[0] != counts[rank]:
+        raise ValueError("gather_rows: counts do not describe the local block")
+    tallest = max(counts)
+    if tallest == 0:
+        return local
+    width = local.shape[1:]
+    send = local
+    if local.shape[0] != tallest:
+        send = local.new_zeros((tallest, *width))
+        send[: local.shape[0]] = local
+    send = send.contiguous()
+    recv = send.new_empty((world * tallest, *width))
+    dist.all_gather_into_tensor(recv, send, group=group) if _has_flat_gather(send) else \
+        _gather_list(recv, send, world, tallest, group)
+    if all(c == tallest for c in counts):
+        return recv
+    return torch.cat([recv[r * tallest: r * tallest + c] for r, c in enumerate(counts)], dim=0)
+
+
+def _has_flat_gather(t: torch.Tensor) -> bool:
+    return t.is_cuda  # NCCL: one flat all-gather; gloo (CPU tests): list form
+
+
+def _gather_list(recv, send, world, tallest, group) -> None:
+    parts = [recv[r * tallest: (r + 1) * tallest] for r in range(world)]
+    dist.all_gather(parts, send, group=group)
+
+
+def run_sharded(num_units: int, unit_rows: int, compute: Callable[[int, int], torch.Tensor],
+                group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Run `compute(first_unit, unit_count) -> [unit_count*unit_rows, width]` on this rank's block
+    of sub-videos and return the gathered rows of ALL units in unit order."""
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    blocks = partition(num_units, world)
+    start, cnt = blocks[rank]
+    local = compute(start, cnt)
+    if local.shape[0] != cnt * unit_rows:
+        raise ValueError("run_sharded: compute returned the wrong number of rows")
+    return gather_rows(local, [c * unit_rows for _, c in blocks], group)

@@ -1,0 +1,419 @@
+"""Host-side mirror of the reference's model components for the inference path.
+
+Same class names, constructor arguments, `forward` signatures and state_dict key names as
+/root/reference/src/models/components/{anomaly_clip,selector_model,temporal_model,
+classification_head}.py and clip/model.py::VisionTransformer, so that a reference checkpoint
+loads with `load_state_dict` and `src/eval.py`'s `_target_` strings resolve (see `src/` shim).
+
+The torch.nn modules below only OWN the parameters; their arithmetic runs in the CUDA library
+(`engine.VitEncoder` / `engine.TemporalScorer`).  Only the text tower (a per-checkpoint constant,
+SURVEY 2 "text side") is evaluated with stock PyTorch, once, and cached.  The training branch
+(`test_mode=False`) is out of scope and raises.
+"""
+from __future__ import annotations
+
+import math
+from collections import OrderedDict
+from typing import List, Optional, Sequence
+
+import torch
+import torch.nn.functional as F
+from torch import nn
+
+from . import engine
+from ._lib import AclipError
+
+ARCHS = {  # clip/model.py:462-511 would infer these from the OpenAI state_dict
+    "ViT-B/16": dict(width=768, layers=12, patch=16, resolution=224, embed_dim=512, text_width=512,
+                     text_layers=12, text_heads=8, context_length=77, vocab_size=49408),
+    "ViT-B/32": dict(width=768, layers=12, patch=32, resolution=224, embed_dim=512, text_width=512,
+                     text_layers=12, text_heads=8, context_length=77, vocab_size=49408),
+}
+
+
+def _versions(module: nn.Module) -> tuple:
+    """Changes whenever a parameter/buffer is replaced, moved or modified in place."""
+    return tuple((t.data_ptr(), t._version) for t in list(module.parameters()) + list(module.buffers()))
+
+
+class _Block(nn.Module):
+    """Parameter holder with ResidualAttentionBlock's names (clip/model.py:188-204)."""
+
+    def __init__(self, width: int, heads: int) -> None:
+        super().__init__()
+        self.attn = nn.MultiheadAttention(width, heads)
+        self.ln_1 = nn.LayerNorm(width)
+        self.mlp = nn.Sequential(OrderedDict([("c_fc", nn.Linear(width, width * 4)),
+                                              ("gelu", nn.Identity()),
+                                              ("c_proj", nn.Linear(width * 4, width))]))
+        self.ln_2 = nn.LayerNorm(width)
+
+
+class _Transformer(nn.Module):
+    def __init__(self, width: int, layers: int, heads: int) -> None:
+        super().__init__()
+        self.width, self.layers, self.heads = width, layers, heads
+        self.resblocks = nn.Sequential(*[_Block(width, heads) for _ in range(layers)])
+        proj_std = (width ** -0.5) * ((2 * layers) ** -0.5)  # clip/model.py:374-381
+        for blk in self.resblocks:
+            nn.init.normal_(blk.attn.in_proj_weight, std=width ** -0.5)
+            nn.init.normal_(blk.attn.out_proj.weight, std=proj_std)
+            nn.init.normal_(blk.mlp.c_fc.weight, std=(2 * width) ** -0.5)
+            nn.init.normal_(blk.mlp.c_proj.weight, std=proj_std)
+
+
+class VisionTransformer(nn.Module):
+    """clip/model.py:233-290.  forward(frames (B,3,R,R) fp32 normalised | uint8) -> (B, output_dim)."""
+
+    def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int,
+                 output_dim: int, micro_batch: int = 256, passes: int = 3) -> None:
+        super().__init__()
+        self.input_resolution, self.output_dim = input_resolution, output_dim
+        self.heads, self.micro_batch, self.passes = heads, micro_batch, passes
+        self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
+        scale = width ** -0.5
+        self.class_embedding = nn.Parameter(scale * torch.randn(width))
+        self.positional_embedding = nn.Parameter(
+            scale * torch.randn((input_resolution // patch_size) ** 2 + 1, width))
+        self.ln_pre = nn.LayerNorm(width)
+        self.transformer = _Transformer(width, layers, heads)
+        self.ln_post = nn.LayerNorm(width)
+        self.proj = nn.Parameter(scale * torch.randn(width, output_dim))
+        self._encoder: Optional[engine.VitEncoder] = None
+        self._key = None
+
+    def encoder(self) -> engine.VitEncoder:
+        key = _versions(self)
+        if self._encoder is None or key != self._key:
+            device = self.proj.device
+            packed = engine.PackedVit({k: v for k, v in self.state_dict().items()}, device, self.heads)
+            self._encoder, self._key = engine.VitEncoder(packed, self.micro_batch, self.passes), key
+        return self._encoder
+
+    @torch.no_grad()
+    def forward(self, x: torch.Tensor) -> torch.Tensor:
+        return self.encoder()(x)
+
+
+class ClassificationHead(nn.Module):
+    """classification_head.py:4-15 (parameter holder; evaluated inside aclip_temporal_forward)."""
+
+    def __init__(self, emb_size: int, n_classes: int) -> None:
+        super().__init__()
+        if n_classes != 1:
+            raise ValueError("the anomaly head has a single output (reference: output_size = 1)")
+        self.layer_norm = nn.LayerNorm(emb_size)
+        self.linear = nn.Linear(emb_size, n_classes)
+
+
+class _AxialSelfAttention(nn.Module):
+    def __init__(self, dim: int, heads: int, dim_heads: Optional[int]) -> None:
+        super().__init__()
+        hidden = (dim // heads if dim_heads is None else dim_heads) * heads
+        self.to_q = nn.Linear(dim, hidden, bias=False)
+        self.to_kv = nn.Linear(dim, 2 * hidden, bias=False)
+        self.to_out = nn.Linear(hidden, dim)
+
+
+class _Wrap(nn.Module):
+    """Gives a child the attribute name the axial_attention package uses (net / fn)."""
+
+    def __init__(self, **children: nn.Module) -> None:
+        super().__init__()
+        for k, v in children.items():
+            self.add_module(k, v)
+
+
+class _ChanLayerNorm(nn.Module):
+    def __init__(self, dim: int) -> None:
+        super().__init__()
+        self.g = nn.Parameter(torch.ones(1, dim, 1, 1))
+        self.b = nn.Parameter(torch.zeros(1, dim, 1, 1))
+
+
+class _AxialPositionalEmbedding(nn.Module):
+    def __init__(self, dim: int, shape: Sequence[int]) -> None:
+        super().__init__()
+        self.param_0 = nn.Parameter(torch.randn(1, dim, shape[0], 1))
+        self.param_1 = nn.Parameter(torch.randn(1, dim, 1, shape[1]))
+
+
+class AxialImageTransformer(nn.Module):
+    """Parameter holder with axial_attention 0.6.1's state_dict names (reversible=True):
+    layers.blocks.{2d}.{f,g}.net.fn.{norm, fn.{to_q,to_kv,to_out}},
+    layers.blocks.{2d+1}.{f,g}.net.{0.g, 0.b, 1.weight, 1.bias, 3.weight, 3.bias}."""
+
+    def __init__(self, dim: int, depth: int, heads: int = 8, dim_heads: Optional[int] = None,
+                 reversible: bool = True, axial_pos_emb_shape: Optional[Sequence[int]] = None) -> None:
+        super().__init__()
+        if not reversible or axial_pos_emb_shape is None:
+            raise ValueError("the reference uses reversible=True with an axial positional embedding")
+        self.pos_emb = _AxialPositionalEmbedding(dim, axial_pos_emb_shape)
+        blocks: List[nn.Module] = []
+        for _ in range(depth):
+            def attn():
+                return _Wrap(net=_Wrap(fn=_Wrap(norm=nn.LayerNorm(dim),
+                                                fn=_AxialSelfAttention(dim, heads, dim_heads))))
+
+            def ff():
+                return _Wrap(net=nn.Sequential(_ChanLayerNorm(dim), nn.Conv2d(dim, dim * 4, 3, padding=1),
+                                               nn.LeakyReLU(inplace=True),
+                                               nn.Conv2d(dim * 4, dim, 3, padding=1)))
+
+            blocks.append(_Wrap(f=attn(), g=attn()))
+            blocks.append(_Wrap(f=ff(), g=ff()))
+        self.layers = _Wrap(blocks=nn.ModuleList(blocks))
+
+
+class TemporalModel(nn.Module):
+    """temporal_model.py:8-40 (parameter holder; evaluated inside aclip_temporal_forward)."""
+
+    def __init__(self, input_size: int, emb_size: int, output_size: int, heads: int,
+                 dim_heads: Optional[int], depth: int, num_segments: int, seg_length: int) -> None:
+        super().__init__()
+        self.input_size, self.emb_size, self.output_size = input_size, emb_size, output_size
+        self.heads, self.dim_heads, self.depth = heads, dim_heads, depth
+        self.num_segments, self.seg_length = num_segments, seg_length
+        self.projection = nn.Linear(input_size, emb_size)
+        self.axial_attn = AxialImageTransformer(dim=emb_size, depth=depth, heads=heads,
+                                                dim_heads=dim_heads, reversible=True,
+                                                axial_pos_emb_shape=(num_segments, seg_length))
+        self.classifier = ClassificationHead(emb_size, output_size)
+
+    def forward(self, features, segment_size, test_mode):
+        raise AclipError("TemporalModel runs fused with the selector and the head inside "
+                         "AnomalyCLIP.forward (aclip_temporal_forward); call that instead")
+
+
+class SelectorModel(nn.Module):
+    """selector_model.py:5-69, test-mode branch."""
+
+    def __init__(self, classnames: list, normal_id: int, logit_scale, num_segments: int,
+                 seg_length: int, select_idx_dropout_topk: float, select_idx_dropout_bottomk: float,
+                 num_topk: int, num_bottomk: int) -> None:
+        super().__init__()
+        self.classnames, self.normal_id = classnames, normal_id
+        self.logit_scale = logit_scale if isinstance(logit_scale, nn.Parameter) else nn.Parameter(
+            torch.as_tensor(float(logit_scale)))
+        self.num_segments, self.seg_length = num_segments, seg_length
+        self.select_idx_dropout_topk = select_idx_dropout_topk
+        self.select_idx_dropout_bottomk = select_idx_dropout_bottomk
+        self.num_topk, self.num_bottomk = num_topk, num_bottomk
+        self.bn_layer = nn.BatchNorm1d(len(classnames) - 1, affine=False)
+
+    @torch.no_grad()
+    def forward(self, image_features, text_features, labels, ncentroid, test_mode):
+        """Stand-alone similarity (test mode): the centring kernel + one tcgen05 GEMM."""
+        if not test_mode:
+            raise NotImplementedError("SelectorModel's training branch (top-k selection) is out of scope")
+        from . import ops
+        x = image_features.reshape(-1, image_features.shape[-1])
+        dev = x.device
+        w, b = engine.selector_operands(text_features.to(dev, torch.float32),
+                                        ncentroid.to(dev, torch.float32), self.normal_id,
+                                        self.bn_layer.running_mean.to(dev), self.bn_layer.running_var.to(dev),
+                                        self.bn_layer.eps)
+        xs = ops.center(x.to(torch.float32), ncentroid.to(dev, torch.float32))
+        out = ops.gemm(xs, ops.split(w), bias=b)
+        return out[:, : len(self.classnames) - 1].contiguous()
+
+
+# ------------------------------------------------------------------------------------- text side
+class _QuickGELU(nn.Module):
+    def forward(self, x):
+        return x * torch.sigmoid(1.702 * x)
+
+
+class PromptLearner(nn.Module):
+    """coop.py:10-90 without the tokenizer: owns ctx / token_prefix / token_suffix (the
+    checkpoint carries the two buffers) and concatenates them (class_token_position 'end')."""
+
+    def __init__(self, n_cls: int, n_ctx: int, ctx_dim: int, context_length: int,
+                 shared_context: bool) -> None:
+        super().__init__()
+        ctx = torch.empty(n_ctx, ctx_dim) if shared_context else torch.empty(n_cls, n_ctx, ctx_dim)
+        nn.init.normal_(ctx, std=0.02)
+        self.ctx = nn.Parameter(ctx)
+        self.register_buffer("token_prefix", torch.zeros(n_cls, 1, ctx_dim))
+        self.register_buffer("token_suffix", torch.zeros(n_cls, context_length - 1 - n_ctx, ctx_dim))
+        self.n_cls, self.n_ctx = n_cls, n_ctx
+
+    def forward(self) -> torch.Tensor:
+        ctx = self.ctx
+        if ctx.dim() == 2:
+            ctx = ctx.unsqueeze(0).expand(self.n_cls, -1, -1)
+        return torch.cat([self.token_prefix, ctx, self.token_suffix], dim=1)  # coop.py:82-90
+
+
+class TextEncoder(nn.Module):
+    """text_encoder.py:5-25 over CLIP's causal text transformer (clip/model.py:188-217,335-349)."""
+
+    def __init__(self, width: int, layers: int, heads: int, context_length: int, embed_dim: int) -> None:
+        super().__init__()
+        self.transformer = _Transformer(width, layers, heads)
+        self.positional_embedding = nn.Parameter(0.01 * torch.randn(context_length, width))
+        self.ln_final = nn.LayerNorm(width)
+        self.text_projection = nn.Parameter(width ** -0.5 * torch.randn(width, embed_dim))
+
+    def forward(self, prompts: torch.Tensor, eot_index: torch.Tensor) -> torch.Tensor:
+        x = prompts + self.positional_embedding
+        L = x.shape[1]
+        mask = torch.full((L, L), float("-inf"), device=x.device).triu_(1)  # clip/model.py:343-349
+        heads = self.transformer.heads
+        for blk in self.transformer.resblocks:
+            h = F.layer_norm(x, (x.shape[-1],), blk.ln_1.weight, blk.ln_1.bias, blk.ln_1.eps)
+            q, k, v = F.linear(h, blk.attn.in_proj_weight, blk.attn.in_proj_bias).chunk(3, dim=-1)
+            B, _, D = q.shape
+            hd = D // heads
+            q = q.reshape(B, L, heads, hd).transpose(1, 2) * hd ** -0.5
+            k = k.reshape(B, L, heads, hd).transpose(1, 2)
+            v = v.reshape(B, L, heads, hd).transpose(1, 2)
+            p = torch.softmax(q @ k.transpose(-1, -2) + mask, dim=-1)
+            o = (p @ v).transpose(1, 2).reshape(B, L, D)
+            x = x + F.linear(o, blk.attn.out_proj.weight, blk.attn.out_proj.bias)
+            h = F.layer_norm(x, (x.shape[-1],), blk.ln_2.weight, blk.ln_2.bias, blk.ln_2.eps)
+            h = F.linear(h, blk.mlp.c_fc.weight, blk.mlp.c_fc.bias)
+            x = x + F.linear(h * torch.sigmoid(1.702 * h), blk.mlp.c_proj.weight, blk.mlp.c_proj.bias)
+        x = F.layer_norm(x, (x.shape[-1],), self.ln_final.weight, self.ln_final.bias, self.ln_final.eps)
+        return x[torch.arange(x.shape[0], device=x.device), eot_index] @ self.text_projection
+
+
+def eot_positions(token_suffix: torch.Tensor, pad_embedding: torch.Tensor, n_ctx: int) -> torch.Tensor:
+    """Position of the EOT token in each prompt (what `tokenized_prompts.argmax(-1)` gives in
+    text_encoder.py:23), recovered without the tokenizer: after EOT every position holds the
+    embedding of the padding token 0, so EOT is the last suffix row that differs from it."""
+    differs = (token_suffix != pad_embedding.view(1, 1, -1)).any(dim=-1)          # (n_cls, S)
+    idx = torch.arange(differs.shape[1], device=differs.device).expand_as(differs)
+    last = torch.where(differs, idx, torch.full_like(idx, -1)).max(dim=1).values
+    if (last < 0).any():
+        raise ValueError("token_suffix holds no EOT row: load a checkpoint or pass text_features")
+    return last + 1 + n_ctx
+
+
+# ------------------------------------------------------------------------------------- the net
+class AnomalyCLIP(nn.Module):
+    """anomaly_clip.py:17-233.  Same kwargs; extra optional ones: `classnames` (instead of reading
+    `labels_file`), `micro_batch`, `passes`, `build_text_tower` (False: supply text features with
+    `set_text_features`)."""
+
+    def __init__(self, **kwargs) -> None:
+        super().__init__()
+        cfg = dict(kwargs)
+        get = cfg.get
+        self.arch = get("arch", "ViT-B/16")
+        self.labels_file = get("labels_file")
+        self.emb_size, self.depth, self.heads = get("emb_size"), get("depth"), get("heads")
+        self.dim_heads = get("dim_heads") or None
+        self.num_segments, self.seg_length = get("num_segments"), get("seg_length")
+        self.concat_features = bool(get("concat_features", False))
+        self.normal_id = get("normal_id")
+        self.stride = get("stride", 1) or 1
+        self.load_from_features = bool(get("load_from_features", True))
+        self.select_idx_dropout_topk = get("select_idx_dropout_topk", 0.7)
+        self.select_idx_dropout_bottomk = get("select_idx_dropout_bottomk", 0.7)
+        self.ncrops = get("ncrops", 1) or 1
+        self.num_topk, self.num_bottomk = get("num_topk", 3), get("num_bottomk", 3)
+        if self.arch not in ARCHS:
+            raise ValueError(f"arch {self.arch!r} unsupported; known: {sorted(ARCHS)}")
+        a = ARCHS[self.arch]
+
+        classnames = get("classnames")
+        if classnames is None:
+            import pandas as pd
+            classes_df = pd.read_csv(self.labels_file)
+            classnames = [c for _, c in classes_df.values.tolist()]
+        self.classnames = sorted(classnames)                                     # :69-70
+        n_cls = len(self.classnames)
+
+        self.embedding_dim = a["text_width"]
+        self.image_encoder = VisionTransformer(a["resolution"], a["patch"], a["width"], a["layers"],
+                                               a["width"] // 64, a["embed_dim"],
+                                               micro_batch=get("micro_batch", 256),
+                                               passes=get("passes", 3))
+        self.has_text_tower = bool(get("build_text_tower", True))
+        if self.has_text_tower:
+            self.prompt_learner = PromptLearner(n_cls, get("n_ctx", 8), a["text_width"],
+                                                a["context_length"], bool(get("shared_context", False)))
+            self.text_encoder = TextEncoder(a["text_width"], a["text_layers"], a["text_heads"],
+                                            a["context_length"], a["embed_dim"])
+            self.token_embedding = nn.Embedding(a["vocab_size"], a["text_width"])
+            nn.init.normal_(self.token_embedding.weight, std=0.02)
+        self.selector_model = SelectorModel(
+            classnames=self.classnames, normal_id=self.normal_id,
+            logit_scale=nn.Parameter(torch.ones([]) * math.log(1 / 0.07)),
+            num_segments=self.num_segments, seg_length=self.seg_length,
+            select_idx_dropout_topk=self.select_idx_dropout_topk,
+            select_idx_dropout_bottomk=self.select_idx_dropout_bottomk,
+            num_topk=self.num_topk, num_bottomk=self.num_bottomk)
+        input_size = a["embed_dim"] + (n_cls - 1) * int(self.concat_features)     # :91-93
+        self.temporal_model = TemporalModel(input_size=input_size, emb_size=self.emb_size,
+                                            output_size=1, heads=self.heads, dim_heads=self.dim_heads,
+                                            depth=self.depth, num_segments=self.num_segments,
+                                            seg_length=self.seg_length)
+        self.passes = get("passes", 3)
+        self._text_features: Optional[torch.Tensor] = None
+        self._text_key = None
+        self._scorer: Optional[engine.TemporalScorer] = None
+        self._scorer_key = None
+        self.class_probs: Optional[torch.Tensor] = None  # softmax(similarity)*score of the last call
+
+    # ---- text directions: a per-checkpoint constant, computed once (the reference recomputes it
+    # on every forward, anomaly_clip.py:136,217-221)
+    def set_text_features(self, text_features: torch.Tensor) -> None:
+        self._text_features, self._text_key = text_features.detach().to(torch.float32), "explicit"
+
+    @torch.no_grad()
+    def get_text_features(self) -> torch.Tensor:
+        if self._text_key == "explicit":
+            return self._text_features
+        if not self.has_text_tower:
+            raise AclipError("no text tower was built: call set_text_features(text_features) first")
+        key = _versions(self.prompt_learner) + _versions(self.text_encoder)
+        if self._text_features is None or key != self._text_key:
+            eot = eot_positions(self.prompt_learner.token_suffix, self.token_embedding.weight[0],
+                                self.prompt_learner.n_ctx)
+            self._text_features = self.text_encoder(self.prompt_learner(), eot).to(torch.float32)
+            self._text_key = key
+        return self._text_features
+
+    def scorer(self) -> engine.TemporalScorer:
+        key = _versions(self.selector_model) + _versions(self.temporal_model)
+        if self._scorer is None or key != self._scorer_key:
+            dev = self.temporal_model.projection.weight.device
+            sd = {k: v for k, v in self.state_dict().items()
+                  if k.startswith(("selector_model.", "temporal_model."))}
+            packed = engine.PackedTemporal(
+                sd, dev, num_classes=len(self.classnames), normal_id=self.normal_id,
+                emb_size=self.emb_size, depth=self.depth, heads=self.heads,
+                num_segments=self.num_segments, seg_length=self.seg_length,
+                concat_features=self.concat_features, feature_dim=ARCHS[self.arch]["embed_dim"])
+            self._scorer, self._scorer_key = engine.TemporalScorer(packed, passes=self.passes), key
+        return self._scorer
+
+    @torch.no_grad()
+    def forward(self, image_features, labels, ncentroid, segment_size=1, test_mode=False):
+        if not test_mode:
+            raise NotImplementedError("AnomalyCLIP: the training branch (test_mode=False) is out of "
+                                      "scope of the B200 inference path")
+        segment_size = int(segment_size)
+        dev = image_features.device
+        if not self.load_from_features:                                         # :118-131
+            b, t, c, h, w = image_features.shape
+            feats = self.image_encoder(image_features.reshape(-1, c, h, w))
+            unit = self.num_segments * segment_size * self.seg_length
+            # "(b ncrops n s l) d -> b ncrops (n s l) d"
+            image_features = feats.reshape(-1, self.ncrops, unit, feats.shape[-1])
+        b, ncrops, t, d = image_features.shape                                  # :132
+        rows = image_features.reshape(-1, d)                                    # :134
+        scorer = self.scorer()
+        text = self.get_text_features()
+        if text.device != dev:  # keep the cached constant on the compute device
+            text = self._text_features = text.to(dev)
+        scorer.packed.set_directions(text, ncentroid.to(dev))
+        similarity, scores, probs = scorer(rows.to(torch.float32), segment_size)
+        if self.stride != 1:                                                    # :149-150
+            similarity = similarity.repeat_interleave(self.stride, dim=0)
+            scores = scores.repeat_interleave(self.stride, dim=0)
+            probs = probs.repeat_interleave(self.stride, dim=0)
+        self.class_probs = probs
+        return similarity, scores.view(-1)                                      # :152-154

@@ -132,3 +132,17 @@ def axial_attention(qkv: torch.Tensor, sub_videos: int, n: int, l: int, heads: i
     _lib.check(lib.aclip_axial_attention(qkv.data_ptr(), sub_videos, n, l, E, heads, axis,
                                          out.data_ptr(), out.stride(0), _stream()))
     return out
+
+
+def center(x: torch.Tensor, centroid: torch.Tensor, regroup: Optional[tuple] = None,
+           ld_out: Optional[int] = None) -> torch.Tensor:
+    """(x - centroid) as split rows; regroup=(n, s, l) also reorders "(b n s l)" -> "(b s) n l"."""
+    x = _f32c(x, "x")
+    rows, D = x.shape
+    ld = ld_out if ld_out is not None else D
+    out = torch.zeros((2, rows, ld), dtype=torch.bfloat16, device=x.device)
+    n, s, l = regroup if regroup is not None else (1, 1, 1)
+    lib = _lib.load()
+    _lib.check(lib.aclip_center_regroup(x.data_ptr(), rows, D, _f32c(centroid, "centroid").data_ptr(),
+                                        n, s, l, out.data_ptr(), ld, out.stride(0), _stream()))
+    return out

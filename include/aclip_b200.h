@@ -47,6 +47,18 @@ const char* aclip_last_error(void);
 /* Number of kernels this library has launched in the calling process (all streams). */
 long long aclip_launch_count(void);
 
+/* Optional device timing of every kernel this library launches (cudaEvent pairs on the launch
+ * stream), grouped by kernel kind, with the ALGORITHMIC flops / bytes of the launches: bench.py
+ * derives its roofline numbers from this.  Enable, run, then collect (collect synchronises on
+ * the recorded events and resets the table).  Returns the number of rows written. */
+typedef struct AclipTimingRow {
+  char name[32];
+  long long launches;
+  double ms, flops, bytes;
+} AclipTimingRow;
+int aclip_timing_enable(int on);
+int aclip_timing_collect(AclipTimingRow* rows, int max_rows);
+
 /* ------------------------------------------------------------------------------------------
  * Building-block operators
  * ---------------------------------------------------------------------------------------- */
@@ -55,6 +67,20 @@ long long aclip_launch_count(void);
  * zero-filled so that the result can feed a GEMM whose K is padded. */
 int aclip_split_f32(const float* in, long long rows, int cols, int ld_in, void* out_split,
                     int ld_out, long long plane_stride, void* stream);
+
+/* (x - centroid) of fp32 feature rows [rows][D] -> split-bf16 rows of pitch ld_out, regrouped from
+ * the caller's "(b n s l)" order to sub-video order "(b s) n l" (temporal_model.py:46-53);
+ * n = s = l = 1 keeps the order.  Replaces the two centroid subtractions of the reference
+ * (selector_model.py:54, anomaly_clip.py:143). */
+int aclip_center_regroup(const float* feats, long long rows, int D, const float* centroid,
+                         int num_segments, int segment_size, int seg_length, void* out_split,
+                         int ld_out, long long plane_stride, void* stream);
+
+/* Frames (B,3,R,R), fp32 normalised or uint8 (then ToTensor + Normalize run here), -> im2col rows
+ * [2][B*(R/P)^2][3*P*P] (split-bf16) for the patch-embedding GEMM (clip/model.py:246-252,267). */
+int aclip_patchify(const void* frames, int frames_are_u8, int B, int R, int P,
+                   const float* mean3_host, const float* std3_host, void* out_split,
+                   long long plane_stride, void* stream);
 
 typedef struct AclipGemmArgs {
   /* operands (bf16 split planes) */

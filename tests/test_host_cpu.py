@@ -1,0 +1,157 @@
+"""CPU-only checks: the C-ABI library loads and exports every declared symbol, host logic
+(partitioning, row gather under gloo, EOT recovery, state_dict names, no CPU fallback)."""
+import os
+import re
+import socket
+from pathlib import Path
+
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def test_library_exports_every_declared_symbol():
+    from anomalyclip_b200 import _lib
+    header = (ROOT / "include" / "aclip_b200.h").read_text()
+    declared = set(re.findall(r"\b(aclip_[a-z0-9_]+)\s*\(", header))
+    assert declared, "no declarations found"
+    lib = _lib.load()
+    for name in sorted(declared):
+        assert hasattr(lib, name), f"{name} is declared in the header but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert lib.aclip_version() >= 100
+
+
+def test_invalid_arguments_return_status_not_crash():
+    from anomalyclip_b200 import _lib
+    lib = _lib.load()
+    assert lib.aclip_gemm(None, None) == -1
+    assert b"NULL" in lib.aclip_last_error()
+    assert lib.aclip_vit_forward(None, None, 0, 0, 0, None, None, None, None, 0, 3, None) == -1
+    assert lib.aclip_temporal_forward(None, None, 0, 1, None, None, None, None, 0, 3, None) == -1
+    assert lib.aclip_vit_workspace_bytes(None, 4) == 0
+
+
+def test_no_cpu_fallback():
+    from anomalyclip_b200._lib import AclipError
+    from anomalyclip_b200.engine import PackedVit
+    from tests.util_weights import make_vit_weights
+    with pytest.raises(AclipError, match="no CPU"):
+        PackedVit(make_vit_weights(layers=1), torch.device("cpu"))
+
+
+def test_product_code_never_imports_the_oracle():
+    for path in (ROOT / "anomalyclip_b200").rglob("*.py"):
+        text = path.read_text()
+        assert "import oracle" not in text and "from oracle" not in text, path
+    for path in (ROOT / "src").rglob("*.py"):
+        assert "oracle" not in path.read_text(), path
+
+
+def test_partition_is_balanced_and_contiguous():
+    from anomalyclip_b200.distributed import partition
+    assert partition(4, 8) == [(0, 1), (1, 1), (2, 1), (3, 1), (4, 0), (4, 0), (4, 0), (4, 0)]
+    assert partition(10, 4) == [(0, 3), (3, 3), (6, 2), (8, 2)]
+    for units in range(0, 40):
+        for world in (1, 2, 3, 8):
+            blocks = partition(units, world)
+            assert sum(c for _, c in blocks) == units
+            assert all(blocks[i][0] + blocks[i][1] == blocks[i + 1][0] for i in range(world - 1))
+            assert max(c for _, c in blocks) - min(c for _, c in blocks) <= 1
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, units, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anomalyclip_b200.distributed import run_sharded
+    unit_rows, width = 4, 3
+
+    def compute(start, count):  # stands in for the GPU path: row r of unit u is [u, r, rank]
+        u = torch.arange(start, start + count).repeat_interleave(unit_rows)
+        r = torch.arange(unit_rows).repeat(count)
+        return torch.stack((u, r, torch.full_like(u, rank)), dim=1).float()
+
+    rows = run_sharded(units, unit_rows, compute)
+    q.put((rank, rows.tolist()))  # plain lists: no shared-memory handles to outlive the worker
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("units", [4, 5, 1])
+def test_sharded_run_gathers_all_rows_in_unit_order_gloo(units):
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, world, port, units, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = {r: torch.tensor(v).reshape(-1, 3) for r, v in (q.get(timeout=120) for _ in range(world))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert torch.equal(got[0], got[1])
+    rows = got[0]
+    assert rows.shape == (units * 4, 3)
+    assert rows[:, 0].tolist() == [float(u) for u in range(units) for _ in range(4)]
+    assert rows[:, 1].tolist() == [float(r) for _ in range(units) for r in range(4)]
+    first = (units + 1) // 2  # rank 0 owns the first ceil(units/2) units
+    assert rows[: first * 4, 2].eq(0).all() and rows[first * 4:, 2].eq(1).all()
+
+
+def test_eot_positions_without_tokenizer():
+    from anomalyclip_b200.models import eot_positions
+    torch.manual_seed(0)
+    n_cls, n_ctx, dim, ctx_len = 3, 8, 16, 77
+    emb = torch.randn(50, dim)
+    name_lens = [1, 3, 2]
+    tokens = torch.zeros(n_cls, ctx_len, dtype=torch.long)
+    for i, nl in enumerate(name_lens):  # SOS X*8 name... '.' EOT 0 0 0 ...
+        seq = [48] + [5] * n_ctx + list(range(10, 10 + nl)) + [7, 49]
+        tokens[i, : len(seq)] = torch.tensor(seq)
+    suffix = emb[tokens][:, 1 + n_ctx:, :]
+    assert eot_positions(suffix, emb[0], n_ctx).tolist() == tokens.argmax(-1).tolist()
+
+
+def test_mirror_state_dict_has_the_reference_key_names():
+    from anomalyclip_b200.models import AnomalyCLIP
+    from tests.util_weights import PRESETS, make_state_dict
+    cfg = PRESETS["shanghaitech"]
+    net = AnomalyCLIP(arch="ViT-B/16", classnames=[f"c{i}" for i in range(cfg.num_classes)],
+                      emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, dim_heads=None,
+                      num_segments=32, seg_length=16, concat_features=True, normal_id=cfg.normal_id,
+                      stride=1, load_from_features=True, ncrops=1, n_ctx=8)
+    keys = set(net.state_dict())
+    synth = make_state_dict(cfg, with_vit=True)
+    assert set(synth) <= keys, sorted(set(synth) - keys)[:5]
+    for k, v in synth.items():
+        assert tuple(net.state_dict()[k].shape) == tuple(v.shape), k
+    for k in ("prompt_learner.ctx", "prompt_learner.token_prefix", "prompt_learner.token_suffix",
+              "token_embedding.weight", "text_encoder.positional_embedding",
+              "text_encoder.text_projection", "text_encoder.ln_final.weight",
+              "text_encoder.transformer.resblocks.11.attn.in_proj_weight",
+              "image_encoder.transformer.resblocks.0.mlp.c_fc.weight",
+              "temporal_model.axial_attn.layers.blocks.3.g.net.3.weight",
+              "temporal_model.axial_attn.layers.blocks.0.f.net.fn.fn.to_kv.weight"):
+        assert k in keys, k
+    assert net.state_dict()["prompt_learner.token_suffix"].shape == (cfg.num_classes, 68, 512)
+    with pytest.raises(NotImplementedError):
+        net(torch.zeros(1, 1, 512, 512), None, torch.zeros(512), 1, False)
+
+
+def test_target_paths_of_the_reference_configs_resolve():
+    import importlib
+    for target in ("src.models.anomaly_clip_module.AnomalyCLIPModule",
+                   "src.models.components.anomaly_clip.AnomalyCLIP",
+                   "src.models.components.selector_model.SelectorModel",
+                   "src.models.components.temporal_model.TemporalModel",
+                   "src.models.components.classification_head.ClassificationHead"):
+        mod, name = target.rsplit(".", 1)
+        assert hasattr(importlib.import_module(mod), name), target

@@ -1,0 +1,77 @@
+"""The reference-facing API (AnomalyCLIP / AnomalyCLIPModule mirror) end to end on the GPU."""
+import pytest
+import torch
+
+from oracle import anomalyclip_oracle as oracle
+from tests.parity import assert_parity
+from tests.util_weights import (PRESETS, make_features, make_ncentroid, make_state_dict,
+                                make_text_features)
+
+pytestmark = pytest.mark.gpu
+
+
+def _net(cfg, load_from_features=True, **extra):
+    from anomalyclip_b200.models import AnomalyCLIP
+    net = AnomalyCLIP(arch="ViT-B/16", classnames=[f"c{i:02d}" for i in range(cfg.num_classes)],
+                      emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, dim_heads=None,
+                      num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                      concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=cfg.stride,
+                      load_from_features=load_from_features, ncrops=cfg.ncrops,
+                      build_text_tower=False, **extra)
+    return net
+
+
+@pytest.mark.parametrize("name", ["ucfcrime", "shanghaitech", "xdviolence"])
+def test_forward_and_test_step_on_features(name):
+    from anomalyclip_b200.module import AnomalyCLIPModule
+    cfg = PRESETS[name]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    net = _net(cfg)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not unexpected and all(k.startswith("image_encoder.") for k in missing)
+    net.set_text_features(text)
+    net.cuda().eval()
+    module = AnomalyCLIPModule(net, num_classes=cfg.num_classes)
+    module.ncentroid = m
+
+    feats = make_features(cfg, 2, seed=5)                       # (1, 1, 1024, 512): cfg1's shape
+    sim_ref, sc_ref = oracle.anomaly_clip_forward(
+        sd, feats, m, text, segment_size=2, normal_id=cfg.normal_id, num_segments=cfg.num_segments,
+        seg_length=cfg.seg_length, depth=cfg.depth, heads=cfg.heads,
+        concat_features=cfg.concat_features)
+    sim, sc = module(feats.cuda(), None, m, 2, True)
+    assert_parity(sim, sim_ref, f"{name} module similarity")
+    assert_parity(sc, sc_ref, f"{name} module scores")
+
+    num_real = 1000                                              # 24 padded frames are trimmed
+    labels = torch.zeros(1, num_real, dtype=torch.long)
+    out = module.test_step((feats, labels, 0, torch.tensor([2]), "video"), 0)
+    probs_ref, sc_trim = oracle.test_step_postprocess(sim_ref, sc_ref, num_real)
+    assert out["abnormal_scores"].shape == (num_real,) and out["class_probs"].shape == (num_real, cfg.num_classes - 1)
+    assert_parity(out["class_probs"], probs_ref, f"{name} class_probs")
+    assert torch.equal(out["class_probs"].argmax(1).cpu(), probs_ref.argmax(1))
+    # the selector on its own (SelectorModel.forward, test branch)
+    sel = net.selector_model(feats.cuda(), text.cuda(), None, m.cuda(), True)
+    assert_parity(sel, sim_ref, f"{name} SelectorModel.forward")
+
+
+def test_weights_changed_after_first_call_are_repacked():
+    cfg = PRESETS["xdviolence"]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    net = _net(cfg)
+    net.load_state_dict(sd, strict=False)
+    net.set_text_features(text)
+    net.cuda().eval()
+    feats = make_features(cfg, 1, seed=2).cuda()
+    _, a = net(feats, None, m, 1, True)
+    sd2 = make_state_dict(cfg, with_vit=False, seed=77)
+    net.load_state_dict(sd2, strict=False)
+    _, b = net(feats, None, m, 1, True)
+    _, ref = oracle.anomaly_clip_forward(
+        sd2, feats.cpu(), m, text, segment_size=1, normal_id=cfg.normal_id,
+        num_segments=cfg.num_segments, seg_length=cfg.seg_length, depth=cfg.depth, heads=cfg.heads,
+        concat_features=cfg.concat_features)
+    assert not torch.allclose(a, b)
+    assert_parity(b, ref, "scores after reloading weights")
