@@ -33,7 +33,7 @@ class GemmArgs(C.Structure):
         ("out_f32", vp), ("out_split", vp),
         ("split_plane_stride", C.c_longlong), ("ldc", C.c_int), ("ld_split", C.c_int),
         ("row_group", C.c_int), ("row_group_stride", C.c_int), ("row_offset", C.c_int),
-        ("max_ctas", C.c_int),
+        ("max_ctas", C.c_int), ("kernel", C.c_int),
     ]
 
 

@@ -106,6 +106,36 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   return ACLIP_OK;
 }
 
+template <int PASSES>
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
+                       int max_ctas, cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<PASSES>;
+  auto kernel = gemm2_tcgen05_kernel<PASSES>;
+  static bool configured = false;
+  if (!configured) {
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    configured = true;
+  }
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  int clusters = (max_ctas > 0 ? max_ctas : sm_count()) / 2;
+  if (clusters > m_tiles * n_tiles) clusters = m_tiles * n_tiles;
+  if (clusters < 1) clusters = 1;
+  timing_begin(KIND_GEMM, stream);
+  kernel<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  {
+    const double planes = PASSES == 1 ? 1.0 : 2.0;
+    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
+    const double a_elems = p.a_mode == 1 ? (double)p.M * (p.K / 9) : (double)p.M * p.K;
+    timing_end(KIND_GEMM, stream, 2.0 * p.M * (double)p.N * p.K,
+               planes * 2.0 * (a_elems + (double)p.N * p.K) + out_b * (double)p.M * p.N);
+  }
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
@@ -132,7 +162,12 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   const int planes = g.passes == 1 ? 1 : 2;
   // 128-wide tiles when they waste fewer padded columns than 256-wide ones (e.g. N = 128, 384)
   const bool narrow = ((g.N + 127) / 128) * 128 < ((g.N + 255) / 256) * 256;
-  const int block_n = narrow ? 128 : 256;
+  // CTA-pair kernel (256 x 256 tiles over two SMs) whenever N tiles evenly and there is enough
+  // work to fill the machine; kernel = 1 / 2 forces the single-CTA / pair kernel (tests).
+  ACLIP_REQUIRE(g.kernel >= 0 && g.kernel <= 2, "gemm: kernel must be 0 (auto), 1 or 2");
+  ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
+  const bool pair = g.kernel == 2 || (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
+  const int block_n = pair ? 128 : (narrow ? 128 : 256);  // rows of W per TMA box
 
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
@@ -192,6 +227,9 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box));
   }
 
+  if (pair)
+    return g.passes == 3 ? launch_pair<3>(tmA, tmB, p, g.max_ctas, stream)
+                         : launch_pair<1>(tmA, tmB, p, g.max_ctas, stream);
   if (block_n == 256) {
     return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
                          : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);

@@ -77,11 +77,83 @@ struct GemmCfg {
 __device__ __forceinline__ float apply_act(float x, int act) {
   if (act == ACT_QUICKGELU) {
     // x * sigmoid(1.702 x)  (reference: clip/model.py:183-185)
-    return x / (1.0f + __expf(-1.702f * x));
+    return __fdividef(x, 1.0f + __expf(-1.702f * x));
   } else if (act == ACT_LEAKYRELU) {
     return x > 0.0f ? x : 0.01f * x;
   }
   return x;
+}
+
+// Epilogue of one 32-column chunk of one accumulator row per thread: TMEM -> registers ->
+// bias -> activation -> residual -> fp32 and/or split-bf16 global stores.
+__device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
+                                               bool row_ok, long long out_row, long long res_row) {
+  uint32_t raw[32];
+  ptx::tmem_ld_32x32(taddr, raw);
+  ptx::tmem_ld_wait();
+  if (!row_ok) return;
+  float v[32];
+#pragma unroll
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  if (p.bias != nullptr) {
+    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(b4 + j);
+      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    }
+  }
+  if (p.act != ACT_NONE) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+  }
+  if (p.residual != nullptr) {
+    const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 r = r4[j];
+      v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+    }
+  }
+  if (p.out_f32 != nullptr) {
+    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldc + n);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  }
+  if (p.out_split != nullptr) {
+    uint32_t hi[16], lo[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) {
+      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]);
+      const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * j + 1]);
+      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
+      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
+      hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
+              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
+      lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
+              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+    }
+    uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ld_split + n);
+    uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
+                                         out_row * p.ld_split + n);
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
+      ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+    }
+  }
+}
+
+__device__ __forceinline__ void epilogue_rows(const GemmParams& p, int m, bool& row_ok,
+                                              long long& out_row, long long& res_row) {
+  row_ok = m < p.M;
+  out_row = 0; res_row = 0;
+  if (row_ok) {
+    out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride + (m % p.row_group) +
+              p.row_offset;
+    res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
+  }
 }
 
 template <int BLOCK_N, int PASSES>
@@ -219,62 +291,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;  // warp-uniform
-        uint32_t raw[32];
-        ptx::tmem_ld_32x32(t_row + c * 32, raw);
-        ptx::tmem_ld_wait();
-        if (row_ok) {
-          float v[32];
-#pragma unroll
-          for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
-          if (p.bias != nullptr) {
-            const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 b = __ldg(b4 + j);
-              v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
-            }
-          }
-          if (p.act != ACT_NONE) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
-          }
-          if (p.residual != nullptr) {
-            const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-              const float4 r = r4[j];
-              v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
-            }
-          }
-          if (p.out_f32 != nullptr) {
-            float4* o4 = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldc + n);
-#pragma unroll
-            for (int j = 0; j < 8; ++j)
-              o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-          }
-          if (p.out_split != nullptr) {
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int j = 0; j < 16; ++j) {
-              const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]);
-              const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * j + 1]);
-              const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-              const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-              hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-              lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-                      (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-            }
-            uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ld_split + n);
-            uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
-                                                 out_row * p.ld_split + n);
-#pragma unroll
-            for (int j = 0; j < 4; ++j) {
-              oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-              ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
-            }
-          }
-        }
+        epilogue_chunk(p, t_row + c * 32, n, row_ok, out_row, res_row);
       }
       // hand the accumulator buffer back to the MMA warp
       ptx::tc_fence_before();
@@ -290,6 +307,189 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-pair variant (tcgen05 cta_group::2): a cluster of two CTAs computes a 256 x 256 tile.
+// Each CTA stages 128 rows of A (its half of M) and 128 rows of W (its half of N) per 64-wide
+// K block, so a stage is 64 KB instead of 96 KB (3 stages instead of 2) and the L2 -> SMEM traffic
+// per MMA drops by a third; the leader CTA's single MMA thread issues M=256 x N=256 x K=16
+// instructions that read both CTAs' shared memory and write both CTAs' TMEM.
+// Roles per CTA (320 threads): warp 0 = TMA producer, warp 1 = MMA issuer (leader only),
+// warps 2..9 = epilogue (two warps per TMEM lane quarter, 128 columns each).
+template <int PASSES_>
+struct Gemm2Cfg {
+  static constexpr int CTA_M = 128;     // rows of A per CTA
+  static constexpr int CTA_N = 128;     // rows of W per CTA
+  static constexpr int BLOCK_M = 256;   // per cluster
+  static constexpr int BLOCK_N = 256;
+  static constexpr int BLOCK_K = 64;
+  static constexpr int UMMA_K = 16;
+  static constexpr int PASSES = PASSES_;
+  static constexpr int PLANES = PASSES_ == 1 ? 1 : 2;
+  static constexpr int A_PLANE_BYTES = CTA_M * 128;
+  static constexpr int B_PLANE_BYTES = CTA_N * 128;
+  static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
+  static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
+  static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
+  static constexpr int EPI_WARPS = 8;
+  static constexpr int THREADS = 64 + EPI_WARPS * 32;
+};
+
+template <int PASSES>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
+gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+  using Cfg = Gemm2Cfg<PASSES>;
+  constexpr int STAGES = Cfg::STAGES;
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
+  const int cluster_id = blockIdx.x >> 1;
+  const int num_clusters = gridDim.x >> 1;
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // leader's producer (arrive.expect_tx for both CTAs)
+      ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);                        // multicast tcgen05.commit
+      ptx::mbar_init(&tempty_bar[a], 2 * Cfg::EPI_WARPS);      // epilogue warps of both CTAs
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // barriers and TMEM of BOTH CTAs are ready before anyone touches them
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  const int total_tiles = m_tiles * n_tiles;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (both CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        const int n0 = (t % n_tiles) * Cfg::BLOCK_N + static_cast<int>(rank) * Cfg::CTA_N;
+        const int mt = (t / n_tiles) * 2 + static_cast<int>(rank);  // 128-row tile index
+        const int m0 = mt * Cfg::CTA_M;
+        int img = 0, h0 = 0;
+        if (p.a_mode == 1) {
+          const int tiles_per_img = (p.conv_h * p.conv_w) / Cfg::CTA_M;
+          img = mt / tiles_per_img;
+          h0 = (mt % tiles_per_img) * (Cfg::CTA_M / p.conv_w);
+        }
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (p.a_mode == 0) {
+            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+          } else {
+            const int tap = kb / p.conv_cin_kb;
+            const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
+            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+            ptx::tma_load_5d_pair(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+          }
+          ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (leader CTA only)
+    if (rank == 0 && lane == 0) {
+      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
+          const uint32_t b_base = a_base + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+#pragma unroll
+          for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+            const uint32_t koff = k * Cfg::UMMA_K * 2;
+            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a_base + koff);
+            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b_base + koff);
+            ptx::mma_bf16_ss_pair(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            if (PASSES == 3) {
+              const uint64_t a_lo = ptx::make_kmajor_sw128_desc(a_base + Cfg::A_PLANE_BYTES + koff);
+              const uint64_t b_lo = ptx::make_kmajor_sw128_desc(b_base + Cfg::B_PLANE_BYTES + koff);
+              ptx::mma_bf16_ss_pair(d_tmem, a_lo, b_hi, idesc, 1u);
+              ptx::mma_bf16_ss_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+            }
+          }
+          ptx::mma_commit_pair(&empty_bar[stage], 0x3);  // frees the slot in both CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_pair(&tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;            // TMEM lane quarter this warp may read
+    const int col_half = (warp - 2) >> 2;    // which 128 of the 256 columns
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      const int n0 = (t % n_tiles) * Cfg::BLOCK_N + col_half * 128;
+      const int m0 = (t / n_tiles) * Cfg::BLOCK_M + static_cast<int>(rank) * Cfg::CTA_M;
+      const int m = m0 + quarter * 32 + lane;
+      bool row_ok;
+      long long out_row, res_row;
+      epilogue_rows(p, m, row_ok, out_row, res_row);
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
+                             (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;  // warp-uniform
+        epilogue_chunk(p, t_row + c * 32, n, row_ok, out_row, res_row);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(&tempty_bar[acc], 0);  // leader's barrier
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();  // nobody leaves while the pair may still touch its smem / TMEM / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
   }
 }
 

@@ -107,6 +107,7 @@ typedef struct AclipGemmArgs {
    * out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset */
   int row_group, row_group_stride, row_offset;
   int max_ctas;          /* 0 = one persistent CTA per SM */
+  int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256) */
 } AclipGemmArgs;
 
 /* tcgen05 / TMA GEMM with fused epilogue. N must be a multiple of 32, K a multiple of 8. */

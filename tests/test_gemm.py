@@ -109,3 +109,58 @@ def test_conv3x3_implicit_gemm(ops, S, Cin, Cout):
     err = _rel(out, ref)
     print(f"conv3x3 S={S} {Cin}->{Cout}: rel err {err:.3e}")
     assert err < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (512, 256, 768), (300, 512, 768), (1000, 768, 768),
+                                   (197 * 8, 2304, 768), (129, 768, 3072), (4096, 3072, 768),
+                                   (50432, 768, 768)])
+@pytest.mark.parametrize("passes", [3, 1])
+def test_gemm_cta_pair_kernel(ops, M, N, K, passes):
+    """The cta_group::2 kernel (256x256 tiles over two SMs) against fp64 and against the
+    single-CTA kernel (identical accumulation order -> identical bits)."""
+    torch.manual_seed(M + N + K + 1)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    sa, sw = ops.split(a), ops.split(w)
+    out2 = ops.gemm(sa, sw, bias=bias, residual=res, act=ops.ACT_QUICKGELU, passes=passes, kernel=2)
+    out1 = ops.gemm(sa, sw, bias=bias, residual=res, act=ops.ACT_QUICKGELU, passes=passes, kernel=1)
+    torch.cuda.synchronize()
+    pre = a.double() @ w.double().T + bias.double()
+    ref = pre * torch.sigmoid(1.702 * pre) + res.double()
+    err = _rel(out2, ref)
+    print(f"pair gemm M={M} N={N} K={K} passes={passes}: rel err {err:.3e}")
+    assert err < (3e-5 if passes == 3 else 1e-2)
+    assert torch.equal(out1, out2)
+
+
+def test_gemm_cta_pair_split_output_rowmap_and_conv(ops):
+    torch.manual_seed(7)
+    frames, g = 6, 196
+    M, N, K = frames * g, 768, 768
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    pos = torch.randn(g, N, device="cuda")
+    ref = (a.double() @ w.double().T).reshape(frames, g, N) + pos.double()
+    out = torch.zeros(frames * 197, N, device="cuda")
+    ops.gemm(ops.split(a), ops.split(w), residual=pos, res_mod=g, out_f32=out, row_map=(g, 197, 1),
+             kernel=2)
+    out = out.reshape(frames, 197, N)
+    assert torch.all(out[:, 0] == 0)
+    assert _rel(out[:, 1:], ref) < 3e-5
+    s = ops.gemm(ops.split(a), ops.split(w), want_split=True, kernel=2)
+    assert _rel(_unsplit(s), a.double() @ w.double().T) < 3e-5
+    # implicit-GEMM conv on the pair kernel
+    S, Cin, Cout, H, W = 3, 256, 1024, 32, 16
+    x = torch.randn(S, Cin, H, W, device="cuda")
+    wt = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.02
+    b = torch.randn(Cout, device="cuda")
+    cref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    cref = cref.permute(0, 2, 3, 1).reshape(S * H * W, Cout)
+    xs = ops.split(x.permute(0, 2, 3, 1).contiguous().reshape(S * H * W, Cin))
+    wk = ops.split(wt.permute(0, 2, 3, 1).contiguous().reshape(Cout, 9 * Cin))
+    c2 = ops.gemm(xs, wk, bias=b, conv=(S, H, W, Cin), kernel=2)
+    c1 = ops.gemm(xs, wk, bias=b, conv=(S, H, W, Cin), kernel=1)
+    assert _rel(c2, cref) < 3e-5
+    assert torch.equal(c1, c2)
