@@ -88,7 +88,7 @@ SIGNATURES = {
     "aclip_layernorm": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_longlong, vp, vp, C.c_float,
                                   C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp]),
     "aclip_vit_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, vp,
-                                      C.c_longlong, C.c_int, vp]),
+                                      C.c_longlong, C.c_int, C.c_int, vp]),
     "aclip_axial_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, vp, C.c_longlong, vp]),
     "aclip_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitWeights), C.c_int]),

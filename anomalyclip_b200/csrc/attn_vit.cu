@@ -249,9 +249,9 @@ vit_attention_kernel(const __nv_bfloat16* __restrict__ qkv, long long in_plane_s
 
 }  // namespace
 
-int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
-                  int heads, void* out_split, long long out_plane_stride, int ld_out,
-                  cudaStream_t stream) {
+int vit_attention_mma(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                      int heads, void* out_split, long long out_plane_stride, int ld_out,
+                      cudaStream_t stream) {
   ACLIP_REQUIRE(qkv_split != nullptr && out_split != nullptr, "vit_attention: null pointer");
   ACLIP_REQUIRE(B > 0 && heads > 0 && L > 0, "vit_attention: empty problem");
   const int LP = (L + 15) / 16 * 16;
@@ -286,9 +286,24 @@ int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, i
 
 }  // namespace aclip
 
+namespace aclip {
+// kernel: 0 = default (tcgen05), 1 = warp-level mma.sync kernel, 2 = tcgen05 kernel
+int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                  int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
+                  cudaStream_t stream) {
+  ACLIP_REQUIRE(kernel >= 0 && kernel <= 2, "vit_attention: kernel must be 0, 1 or 2");
+  if (kernel == 1)
+    return vit_attention_mma(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                             out_plane_stride, ld_out, stream);
+  return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                          out_plane_stride, ld_out, stream);
+}
+}  // namespace aclip
+
 extern "C" int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in,
                                    int B, int L, int heads, void* out_split,
-                                   long long out_plane_stride, int ld_out, void* stream) {
+                                   long long out_plane_stride, int ld_out, int kernel,
+                                   void* stream) {
   return aclip::vit_attention(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
-                              out_plane_stride, ld_out, aclip::as_stream(stream));
+                              out_plane_stride, ld_out, kernel, aclip::as_stream(stream));
 }

@@ -1,0 +1,417 @@
+// ViT self-attention on the 5th-generation tensor cores (tcgen05 + TMEM), split-bf16 x3.
+//
+//   softmax(Q K^T / 8) V per (frame, head), L = 197 tokens, head dim 64, no mask
+//   (nn.MultiheadAttention inside ResidualAttentionBlock.attention, clip/model.py:206-212).
+//
+// Persistent CTAs (one per SM) walk over (frame, head) items; each item is two 128-row query
+// tiles.  Per tile:   S = Q K^T        tcgen05.mma  M=128, N=LP (keys, 16-padded), K=64, A and B from smem
+//                     P = softmax(S)   4 warps, one thread per row, S read from TMEM, P written back
+//                                      to TMEM in place as packed bf16 (hi plane, then lo plane)
+//                     O = P V          tcgen05.mma  M=128, N=64, K=LP, A from TMEM, B = V from smem
+//                                      (MN-major descriptor: V is stored [key][dim])
+//                     O / rowsum -> split-bf16 rows in global memory.
+// Every product is issued as hi*hi + lo*hi + hi*lo (Q, K, V arrive as hi/lo planes from the QKV
+// GEMM; P is split by the softmax threads).
+//
+// Roles: warp 0 = TMA producer (Q tiles double buffered, K, V), warp 1 = MMA issuer,
+// warps 2..5 = softmax + output.  TMEM: S0 [0,224) S1 [224,448) O [448,512); the score
+// accumulator is double buffered so that the tensor pipe computes S of tile j+1 and O of tile j-1
+// while the softmax warps work on tile j.
+#include <cuda_bf16.h>
+
+#include <mutex>
+
+#include "common.h"
+#include "ptx.cuh"
+
+namespace aclip {
+
+namespace {
+
+constexpr int HD = 64;
+constexpr int TILE_Q = 128;
+constexpr int S_STRIDE = 224;           // TMEM columns per score buffer
+constexpr int O_COL = 2 * S_STRIDE;     // 448
+constexpr int PLO_OFF = S_STRIDE / 2;   // packed lo plane starts here inside a score buffer
+constexpr int MAX_LP = 208 + 16;        // 224 keys at most
+constexpr int Q_PLANE = TILE_Q * 128;   // bytes of one bf16 plane of a Q tile
+constexpr int ATT_THREADS = 192;
+
+struct AttnTcParams {
+  int L, LP, heads, items;  // items = frames * heads
+  float sl2;                // log2(e) / sqrt(64)
+  __nv_bfloat16* out;
+  long long out_plane_stride;
+  int ld_out;
+  int width;                // heads * 64: column offset of K (and 2x for V) inside a qkv row
+};
+
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32"
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];\n"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]),
+        "=r"(v[7]), "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]),
+        "=r"(v[14]), "=r"(v[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t* v) {
+  asm volatile(
+      "tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};\n" ::"r"(taddr),
+      "r"(v[0]), "r"(v[1]), "r"(v[2]), "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+      : "memory");
+}
+__device__ __forceinline__ void tmem_st_wait() {
+  asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ float fast_exp2(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+// D[tmem] (+)= A[tmem] * B[smem]
+__device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, uint64_t b_desc,
+                                            uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// MN-major operand stored as rows of 128 bytes (64 bf16 along MN) with the 128-byte swizzle:
+// K advances by one row (128 B), groups of 8 K rows are SBO = 1024 B apart.
+__device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;            // LBO (single MN atom: unused)
+  d |= static_cast<uint64_t>(1024 >> 4) << 32;    // SBO
+  d |= static_cast<uint64_t>(1) << 46;            // descriptor version (sm_100)
+  d |= static_cast<uint64_t>(2) << 61;            // SWIZZLE_128B
+  return d;
+}
+__device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return static_cast<uint32_t>(__bfloat16_as_ushort(a)) |
+         (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
+}
+
+// one 16-key group of probabilities: exp, row sum, hi/lo split, packed two keys per column
+__device__ __forceinline__ void softmax_group(const uint32_t (&raw)[16], int key0, int L, float sl2,
+                                              float mb, float& sum, uint32_t* hi, uint32_t* lo) {
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    const int k = key0 + 2 * j;
+    float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * j]), sl2, -mb));
+    float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -mb));
+    if (k >= L) p0 = 0.f;
+    if (k + 1 >= L) p1 = 0.f;
+    sum += p0 + p1;
+    const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
+    hi[j] = pack2(h0, h1);
+    lo[j] = pack2(__float2bfloat16_rn(p0 - __bfloat162float(h0)),
+                  __float2bfloat16_rn(p1 - __bfloat162float(h1)));
+  }
+}
+
+__global__ void __launch_bounds__(ATT_THREADS, 1)
+vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
+                        const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p) {
+  extern __shared__ uint8_t att_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(att_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  const int kv_plane = p.LP * 128;            // bytes of one plane of K (or V)
+  uint8_t* sK = smem;                         // [2 planes][LP][128 B]
+  uint8_t* sV = sK + 2 * kv_plane;
+  uint8_t* sQ = sV + 2 * kv_plane;            // [2 slots][2 planes][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + 2 * 2 * Q_PLANE);
+  uint64_t* k_full = bars + 0;  uint64_t* k_empty = bars + 1;
+  uint64_t* v_full = bars + 2;  uint64_t* v_empty = bars + 3;
+  uint64_t* q_full = bars + 4;  uint64_t* q_empty = bars + 6;   // [2]
+  uint64_t* s_full = bars + 8;  uint64_t* p_full = bars + 10;   // [2]
+  uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 13;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmQ);
+    ptx::prefetch_tmap(&tmKV);
+    ptx::mbar_init(k_full, 1);  ptx::mbar_init(k_empty, 1);
+    ptx::mbar_init(v_full, 1);  ptx::mbar_init(v_empty, 1);
+    for (int i = 0; i < 2; ++i) {
+      ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
+      ptx::mbar_init(&s_full[i], 1);  ptx::mbar_init(&p_full[i], 4);
+    }
+    ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, 4);
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc(tmem_slot, 512);
+    ptx::tmem_relinquish();
+  }
+  ptx::tc_fence_before();
+  __syncthreads();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
+                       static_cast<int>(gridDim.x);
+  const int my_tiles = 2 * my_items;
+
+  if (warp == 0) {
+    // ------------------------------------------------------------------ TMA producer
+    if (lane == 0) {
+      for (int it = 0; it < my_items; ++it) {
+        const int item = blockIdx.x + it * gridDim.x;
+        const int b = item / p.heads, h = item - b * p.heads;
+        const int row0 = b * p.L;
+        ptx::mbar_wait(k_empty, (it & 1) ^ 1);
+        ptx::mbar_expect_tx(k_full, 2 * kv_plane);
+        ptx::tma_load_3d(sK, &tmKV, k_full, p.width + h * HD, row0, 0);
+        for (int q = 0; q < 2; ++q) {
+          ptx::mbar_wait(&q_empty[q], (it & 1) ^ 1);
+          ptx::mbar_expect_tx(&q_full[q], 2 * Q_PLANE);
+          ptx::tma_load_3d(sQ + q * 2 * Q_PLANE, &tmQ, &q_full[q], h * HD, row0 + q * TILE_Q, 0);
+        }
+        ptx::mbar_wait(v_empty, (it & 1) ^ 1);
+        ptx::mbar_expect_tx(v_full, 2 * kv_plane);
+        ptx::tma_load_3d(sV, &tmKV, v_full, 2 * p.width + h * HD, row0, 0);
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------------ MMA issuer
+    if (lane == 0) {
+      const uint32_t idesc_qk = ptx::make_idesc_bf16_f32(TILE_Q, p.LP);
+      const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(TILE_Q, HD) | (1u << 16);  // B is MN-major
+      const uint32_t k_base = ptx::smem_u32(sK), v_base = ptx::smem_u32(sV);
+      const int ksteps = p.LP >> 4;
+
+      auto issue_qk = [&](int J) {  // S[J % 2] = Q_J K^T
+        const int it = J >> 1, q = J & 1;
+        if (q == 0) { ptx::mbar_wait(k_full, it & 1); }
+        ptx::mbar_wait(&q_full[q], it & 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + q * S_STRIDE;
+        const uint32_t q_base = ptx::smem_u32(sQ + q * 2 * Q_PLANE);
+#pragma unroll
+        for (int k = 0; k < HD / 16; ++k) {
+          const uint32_t koff = k * 32;
+          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(q_base + koff);
+          const uint64_t a_lo = ptx::make_kmajor_sw128_desc(q_base + Q_PLANE + koff);
+          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(k_base + koff);
+          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(k_base + kv_plane + koff);
+          ptx::mma_bf16_ss(d, a_hi, b_hi, idesc_qk, k != 0 ? 1u : 0u);
+          ptx::mma_bf16_ss(d, a_lo, b_hi, idesc_qk, 1u);
+          ptx::mma_bf16_ss(d, a_hi, b_lo, idesc_qk, 1u);
+        }
+        ptx::mma_commit(&s_full[q]);
+        ptx::mma_commit(&q_empty[q]);
+        if (q == 1) ptx::mma_commit(k_empty);
+      };
+      auto issue_pv = [&](int J) {  // O = P_J V
+        const int it = J >> 1, q = J & 1;
+        if (q == 0) { ptx::mbar_wait(v_full, it & 1); }
+        ptx::mbar_wait(&p_full[q], it & 1);
+        ptx::mbar_wait(o_empty, (J & 1) ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d = tmem_base + O_COL;
+        const uint32_t a_hi0 = tmem_base + q * S_STRIDE;
+        const uint32_t a_lo0 = a_hi0 + PLO_OFF;
+        for (int k = 0; k < ksteps; ++k) {
+          const uint64_t b_hi = make_mnmajor_sw128_desc(v_base + k * 2048);
+          const uint64_t b_lo = make_mnmajor_sw128_desc(v_base + kv_plane + k * 2048);
+          mma_bf16_ts(d, a_hi0 + 8 * k, b_hi, idesc_pv, k != 0 ? 1u : 0u);
+          mma_bf16_ts(d, a_lo0 + 8 * k, b_hi, idesc_pv, 1u);
+          mma_bf16_ts(d, a_hi0 + 8 * k, b_lo, idesc_pv, 1u);
+        }
+        ptx::mma_commit(o_full);
+        if (q == 1) ptx::mma_commit(v_empty);
+      };
+
+      if (my_tiles > 0) issue_qk(0);
+      for (int J = 0; J < my_tiles; ++J) {
+        if (J + 1 < my_tiles) issue_qk(J + 1);  // score tile J+1 while the softmax warps work on J
+        issue_pv(J);
+      }
+    }
+  } else {
+    // ------------------------------------------------------------------ softmax + output warps
+    const int quarter = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int row_in_tile = quarter * 32 + lane;
+    const int groups = p.LP >> 4;  // 16-key groups (13 for L = 197)
+    float inv_sum_prev = 0.f;
+
+    auto write_output = [&](int J, float inv_sum) {  // O_J / rowsum -> global split rows
+      ptx::mbar_wait(o_full, J & 1);
+      ptx::tc_fence_after();
+      uint32_t o[64];
+      {
+        uint32_t (&lo32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
+        uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
+        ptx::tmem_ld_32x32(tmem_base + O_COL + lane_off, lo32);
+        ptx::tmem_ld_32x32(tmem_base + O_COL + 32 + lane_off, hi32);
+        ptx::tmem_ld_wait();
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_empty);
+      const int it = J >> 1, q = J & 1;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / p.heads, h = item - b * p.heads;
+      const int r = q * TILE_Q + row_in_tile;
+      if (r < p.L) {
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.L + r) * p.ld_out + h * HD;
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          uint32_t hi[4], lo[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = __uint_as_float(o[8 * c + 2 * j]) * inv_sum;
+            const float bb = __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum;
+            const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(bb);
+            hi[j] = pack2(h0, h1);
+            lo[j] = pack2(__float2bfloat16_rn(a - __bfloat162float(h0)),
+                          __float2bfloat16_rn(bb - __bfloat162float(h1)));
+          }
+          *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+          *reinterpret_cast<uint4*>(dst + 8 * c + p.out_plane_stride) =
+              make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        }
+      }
+    };
+
+    for (int J = 0; J < my_tiles; ++J) {
+      const int slot = J & 1;
+      const uint32_t s_addr = tmem_base + slot * S_STRIDE + lane_off;
+      ptx::mbar_wait(&s_full[slot], (J >> 1) & 1);
+      ptx::tc_fence_after();
+      // pass 1: row maximum over the L real keys
+      float mx = -INFINITY;
+      for (int g = 0; g < groups; ++g) {
+        uint32_t raw[16];
+        tmem_ld_x16(s_addr + 16 * g, raw);
+        ptx::tmem_ld_wait();
+#pragma unroll
+        for (int j = 0; j < 16; ++j)
+          if (16 * g + j < p.L) mx = fmaxf(mx, __uint_as_float(raw[j]));
+      }
+      const float mb = mx * p.sl2;
+      // pass 2: probabilities; hi plane overwrites the scores already consumed, lo plane is kept
+      // in registers until every score column has been read
+      float sum = 0.f;
+      uint32_t lo_keep[MAX_LP / 2];
+#pragma unroll
+      for (int g = 0; g < MAX_LP / 16; ++g) {
+        if (g < groups) {
+          uint32_t raw[16], hi[8];
+          tmem_ld_x16(s_addr + 16 * g, raw);
+          ptx::tmem_ld_wait();
+          softmax_group(raw, 16 * g, p.L, p.sl2, mb, sum, hi, &lo_keep[8 * g]);
+          tmem_st_x8(s_addr + 8 * g, hi);
+        }
+      }
+#pragma unroll
+      for (int g = 0; g < MAX_LP / 16; ++g)
+        if (g < groups) tmem_st_x8(s_addr + PLO_OFF + 8 * g, &lo_keep[8 * g]);
+      tmem_st_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(&p_full[slot]);
+      // the previous tile's output is ready by now: normalise and store it
+      if (J > 0) write_output(J - 1, inv_sum_prev);
+      inv_sum_prev = 1.0f / sum;
+    }
+    if (my_tiles > 0) write_output(my_tiles - 1, inv_sum_prev);
+  }
+
+  ptx::tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc(tmem_base, 512);
+  }
+}
+
+using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
+                                   const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
+                                   const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  static std::once_flag once;
+  std::call_once(once, [] {
+    void* ptr = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  });
+  return fn;
+}
+
+}  // namespace
+
+int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                     int heads, void* out_split, long long out_plane_stride, int ld_out,
+                     cudaStream_t stream) {
+  ACLIP_REQUIRE(qkv_split != nullptr && out_split != nullptr, "vit_attention: null pointer");
+  ACLIP_REQUIRE(B > 0 && heads > 0 && L > 0, "vit_attention: empty problem");
+  const int LP = (L + 15) / 16 * 16;
+  ACLIP_REQUIRE(LP <= MAX_LP, "vit_attention: L=%d exceeds the %d-token limit", L, MAX_LP);
+  ACLIP_REQUIRE(ld_in % 8 == 0 && ld_in >= 3 * heads * HD && ld_out % 8 == 0 &&
+                    ld_out >= heads * HD && in_plane_stride % 8 == 0 && out_plane_stride % 8 == 0,
+                "vit_attention: bad pitches");
+  ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(qkv_split) & 15) == 0 &&
+                    (reinterpret_cast<uintptr_t>(out_split) & 15) == 0,
+                "vit_attention: buffers must be 16-byte aligned");
+  ACLIP_REQUIRE(static_cast<long long>(B) * heads < (1ll << 30), "vit_attention: too many items");
+  EncodeTiledFn enc = encode_fn();
+  if (enc == nullptr) return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
+  const long long rows = static_cast<long long>(B) * L;
+  CUtensorMap tmQ, tmKV;
+  {
+    cuuint64_t dims[3] = {(cuuint64_t)ld_in, (cuuint64_t)rows, 2};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_in * 2, (cuuint64_t)in_plane_stride * 2};
+    cuuint32_t estr[3] = {1, 1, 1};
+    cuuint32_t box_q[3] = {64, TILE_Q, 2};
+    cuuint32_t box_kv[3] = {64, (cuuint32_t)LP, 2};
+    CUresult r1 = enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv_split), dims,
+                      strides, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    CUresult r2 = enc(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv_split), dims,
+                      strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                      CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
+      return fail(ACLIP_ERR_CUDA, "vit_attention: cuTensorMapEncodeTiled failed (%d, %d)", (int)r1, (int)r2);
+  }
+  AttnTcParams p{};
+  p.L = L; p.LP = LP; p.heads = heads; p.items = B * heads;
+  p.sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  p.out = static_cast<__nv_bfloat16*>(out_split);
+  p.out_plane_stride = out_plane_stride;
+  p.ld_out = ld_out;
+  p.width = heads * HD;
+  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 256 + 1024;
+  static bool configured = false;
+  if (!configured) {
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 256 + 1024));
+    configured = true;
+  }
+  int ctas = sm_count();
+  if (ctas > p.items) ctas = p.items;
+  timing_begin(KIND_VIT_ATTENTION, stream);
+  vit_attention_tc_kernel<<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
+             (double)B * L * heads * HD * (3 * 4.0 + 4.0));
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+}  // namespace aclip

@@ -34,8 +34,11 @@ int center_regroup(const float* feats, long long rows, int D, const float* centr
                    const RowMap& map, void* out_split, int ld_out, long long plane_stride,
                    cudaStream_t stream);
 int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
-                  int heads, void* out_split, long long out_plane_stride, int ld_out,
+                  int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
                   cudaStream_t stream);
+int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                     int heads, void* out_split, long long out_plane_stride, int ld_out,
+                     cudaStream_t stream);
 int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E, int heads,
                     int axis, void* out_split, long long plane_stride, cudaStream_t stream);
 

@@ -140,7 +140,7 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 3 * W;
         ACLIP_TRY(gemm(g, stream));
       }
-      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, stream));
+      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, stream));
       {
         AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes);
         g.bias = b.out_b;

@@ -112,14 +112,14 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
     return out_f32 if want_f32 else out_split
 
 
-def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int) -> torch.Tensor:
+def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int, kernel: int = 0) -> torch.Tensor:
     """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64]."""
     W = heads * 64
     out = torch.empty((2, B * L, W), dtype=torch.bfloat16, device=qkv_split.device)
     lib = _lib.load()
     _lib.check(lib.aclip_vit_attention(qkv_split.data_ptr(), qkv_split.stride(0),
                                        qkv_split.stride(1), B, L, heads, out.data_ptr(),
-                                       out.stride(0), out.stride(1), _stream()))
+                                       out.stride(0), out.stride(1), kernel, _stream()))
     return out
 
 

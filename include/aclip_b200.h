@@ -121,10 +121,11 @@ int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const 
 
 /* softmax(Q K^T / 8) V for B frames of L tokens, `heads` heads of 64 dims; qkv_split is the
  * split-bf16 [2][B*L][ld_in] output of the in_proj GEMM (q | k | v), out_split [2][B*L][ld_out].
- * Replaces nn.MultiheadAttention inside ResidualAttentionBlock.attention (clip/model.py:206-212). */
+ * Replaces nn.MultiheadAttention inside ResidualAttentionBlock.attention (clip/model.py:206-212).
+ * kernel: 0 = default (tcgen05/TMEM kernel), 1 = warp-level mma.sync kernel, 2 = tcgen05 kernel. */
 int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                         int heads, void* out_split, long long out_plane_stride, int ld_out,
-                        void* stream);
+                        int kernel, void* stream);
 
 /* Axial self-attention over fp32 qkv rows [sub_videos*n*l][3E] in sub-video order; axis 0 = along
  * the n segments, axis 1 = along the l frames.  Output split-bf16 [2][rows][E].

@@ -38,18 +38,19 @@ def test_layernorm(ops, rows, D, chan):
 
 
 @pytest.mark.parametrize("B,L,heads", [(1, 197, 12), (3, 197, 12), (2, 5, 2), (2, 64, 1), (1, 224, 3),
-                                        (4, 17, 2), (2, 130, 4)])
-def test_vit_attention(ops, B, L, heads):
+                                        (4, 17, 2), (2, 130, 4), (40, 197, 12)])
+@pytest.mark.parametrize("kernel", [2, 1])
+def test_vit_attention(ops, B, L, heads, kernel):
     torch.manual_seed(B * 1000 + L)
     W = heads * 64
     qkv = torch.randn(B * L, 3 * W, device="cuda") * 1.5
     s = ops.split(qkv)
-    out = _unsplit(ops.vit_attention(s, B, L, heads))
+    out = _unsplit(ops.vit_attention(s, B, L, heads, kernel=kernel))
     x = _unsplit(s).double().reshape(B, L, 3, heads, 64)
     q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
     p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
     ref = (p @ v).transpose(1, 2).reshape(B * L, W)
-    assert_parity(out, ref, f"vit attention B={B} L={L} h={heads}", rtol=1e-4)
+    assert_parity(out, ref, f"vit attention kernel={kernel} B={B} L={L} h={heads}", rtol=1e-4)
 
 
 @pytest.mark.parametrize("E,heads", [(256, 8), (128, 8), (64, 2)])
