@@ -11,6 +11,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "split.cuh"
 
 namespace aclip {
 
@@ -46,13 +47,7 @@ __device__ __forceinline__ void mma16816(float (&d)[4], const uint32_t (&a)[4], 
       : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ void split_pair(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-  hi = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-       (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-  lo = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-       (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  split_pack2(a, b, hi, lo);
 }
 __device__ __forceinline__ float quad_max(float v) {
   v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, 1));

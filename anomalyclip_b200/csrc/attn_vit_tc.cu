@@ -5,7 +5,7 @@
 //
 // Persistent CTAs (one per SM) walk over (frame, head) items; each item is two 128-row query
 // tiles.  Per tile:   S = Q K^T        tcgen05.mma  M=128, N=LP (keys, 16-padded), K=64, A and B from smem
-//                     P = softmax(S)   4 warps, one thread per row, S read from TMEM, P written back
+//                     P = softmax(S)   8 warps, two threads per row (half of the keys each), S read from TMEM, P written back
 //                                      to TMEM in place as packed bf16 (hi plane, then lo plane)
 //                     O = P V          tcgen05.mma  M=128, N=64, K=LP, A from TMEM, B = V from smem
 //                                      (MN-major descriptor: V is stored [key][dim])
@@ -14,7 +14,7 @@
 // GEMM; P is split by the softmax threads).
 //
 // Roles: warp 0 = TMA producer (Q tiles double buffered, K, V), warp 1 = MMA issuer,
-// warps 2..5 = softmax + output.  TMEM: S0 [0,224) S1 [224,448) O [448,512); the score
+// warps 2..9 = softmax + output (two warps per TMEM lane quarter, half of the keys each).  TMEM: S0 [0,224) S1 [224,448) O [448,512); the score
 // accumulator is double buffered so that the tensor pipe computes S of tile j+1 and O of tile j-1
 // while the softmax warps work on tile j.
 #include <cuda_bf16.h>
@@ -23,6 +23,7 @@
 
 #include "common.h"
 #include "ptx.cuh"
+#include "split.cuh"
 
 namespace aclip {
 
@@ -35,7 +36,9 @@ constexpr int O_COL = 2 * S_STRIDE;     // 448
 constexpr int PLO_OFF = S_STRIDE / 2;   // packed lo plane starts here inside a score buffer
 constexpr int MAX_LP = 208 + 16;        // 224 keys at most
 constexpr int Q_PLANE = TILE_Q * 128;   // bytes of one bf16 plane of a Q tile
-constexpr int ATT_THREADS = 192;
+constexpr int SOFTMAX_WARPS = 8;
+constexpr int ATT_THREADS = 64 + SOFTMAX_WARPS * 32;
+constexpr int HALF_GROUPS = MAX_LP / 32;  // 16-key groups per softmax warp (7)
 
 struct AttnTcParams {
   int L, LP, heads, items;  // items = frames * heads
@@ -98,22 +101,28 @@ __device__ __forceinline__ uint32_t pack2(__nv_bfloat16 a, __nv_bfloat16 b) {
          (static_cast<uint32_t>(__bfloat16_as_ushort(b)) << 16);
 }
 
-// one 16-key group of probabilities: exp, row sum, hi/lo split, packed two keys per column
-__device__ __forceinline__ void softmax_group(const uint32_t (&raw)[16], int key0, int L, float sl2,
-                                              float mb, float& sum, uint32_t* hi, uint32_t* lo) {
+// one 16-key group: scores (fp32 bit patterns) -> probabilities, in place: v[0..8) = packed hi
+// plane, v[8..16) = packed lo plane (two keys per 32-bit column); returns the partial row sum.
+// MASK: the group straddles L (keys >= L get probability 0).
+template <bool MASK>
+__device__ __forceinline__ float softmax_group(uint32_t (&v)[16], int key0, int L, float sl2, float mb) {
+  float sum = 0.f;
+  uint32_t hi[8], lo[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    const int k = key0 + 2 * j;
-    float p0 = fast_exp2(fmaf(__uint_as_float(raw[2 * j]), sl2, -mb));
-    float p1 = fast_exp2(fmaf(__uint_as_float(raw[2 * j + 1]), sl2, -mb));
-    if (k >= L) p0 = 0.f;
-    if (k + 1 >= L) p1 = 0.f;
+    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+    if (MASK) {
+      const int k = key0 + 2 * j;
+      if (k >= L) p0 = 0.f;
+      if (k + 1 >= L) p1 = 0.f;
+    }
     sum += p0 + p1;
-    const __nv_bfloat16 h0 = __float2bfloat16_rn(p0), h1 = __float2bfloat16_rn(p1);
-    hi[j] = pack2(h0, h1);
-    lo[j] = pack2(__float2bfloat16_rn(p0 - __bfloat162float(h0)),
-                  __float2bfloat16_rn(p1 - __bfloat162float(h1)));
+    split_pack2(p0, p1, hi[j], lo[j]);
   }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) { v[j] = hi[j]; v[8 + j] = lo[j]; }
+  return sum;
 }
 
 __global__ void __launch_bounds__(ATT_THREADS, 1)
@@ -133,6 +142,8 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint64_t* s_full = bars + 8;  uint64_t* p_full = bars + 10;   // [2]
   uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 13;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
+  float* max_buf = reinterpret_cast<float*>(bars + 16);   // [2 slots][2 halves][128 rows]
+  float* sum_buf = max_buf + 4 * TILE_Q;                  // [2 slots][2 halves][128 rows]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -142,9 +153,9 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     ptx::mbar_init(v_full, 1);  ptx::mbar_init(v_empty, 1);
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
-      ptx::mbar_init(&s_full[i], 1);  ptx::mbar_init(&p_full[i], 4);
+      ptx::mbar_init(&s_full[i], 1);  ptx::mbar_init(&p_full[i], SOFTMAX_WARPS);
     }
-    ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, 4);
+    ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, SOFTMAX_WARPS);
     ptx::fence_mbar_init();
   }
   if (warp == 1) {
@@ -238,23 +249,21 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
   } else {
     // ------------------------------------------------------------------ softmax + output warps
-    const int quarter = warp & 3;
+    const int quarter = warp & 3;          // TMEM lane quarter this warp may access
+    const int half = (warp - 2) >> 2;      // which half of the keys / of the output columns
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int row_in_tile = quarter * 32 + lane;
-    const int groups = p.LP >> 4;  // 16-key groups (13 for L = 197)
-    float inv_sum_prev = 0.f;
+    const int groups = p.LP >> 4;          // 16-key groups (13 for L = 197)
+    const int g_split = (groups + 1) >> 1;
+    const int g_begin = half == 0 ? 0 : g_split;
+    const int g_count = half == 0 ? g_split : groups - g_split;
 
-    auto write_output = [&](int J, float inv_sum) {  // O_J / rowsum -> global split rows
+    auto write_output = [&](int J) {  // O_J / rowsum -> global split rows (32 of the 64 dims)
       ptx::mbar_wait(o_full, J & 1);
       ptx::tc_fence_after();
-      uint32_t o[64];
-      {
-        uint32_t (&lo32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[0]);
-        uint32_t (&hi32)[32] = *reinterpret_cast<uint32_t (*)[32]>(&o[32]);
-        ptx::tmem_ld_32x32(tmem_base + O_COL + lane_off, lo32);
-        ptx::tmem_ld_32x32(tmem_base + O_COL + 32 + lane_off, hi32);
-        ptx::tmem_ld_wait();
-      }
+      uint32_t o[32];
+      ptx::tmem_ld_32x32(tmem_base + O_COL + 32 * half + lane_off, o);
+      ptx::tmem_ld_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(o_empty);
@@ -262,20 +271,17 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       const int item = blockIdx.x + it * gridDim.x;
       const int b = item / p.heads, h = item - b * p.heads;
       const int r = q * TILE_Q + row_in_tile;
+      const float* sb = sum_buf + (J & 1) * 2 * TILE_Q;
+      const float inv_sum = 1.0f / (sb[row_in_tile] + sb[TILE_Q + row_in_tile]);
       if (r < p.L) {
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.L + r) * p.ld_out + h * HD;
+        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.L + r) * p.ld_out + h * HD + 32 * half;
 #pragma unroll
-        for (int c = 0; c < 8; ++c) {
+        for (int c = 0; c < 4; ++c) {
           uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = __uint_as_float(o[8 * c + 2 * j]) * inv_sum;
-            const float bb = __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum;
-            const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(bb);
-            hi[j] = pack2(h0, h1);
-            lo[j] = pack2(__float2bfloat16_rn(a - __bfloat162float(h0)),
-                          __float2bfloat16_rn(bb - __bfloat162float(h1)));
-          }
+          for (int j = 0; j < 4; ++j)
+            split_pack2(__uint_as_float(o[8 * c + 2 * j]) * inv_sum,
+                        __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum, hi[j], lo[j]);
           *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
           *reinterpret_cast<uint4*>(dst + 8 * c + p.out_plane_stride) =
               make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -288,43 +294,56 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       const uint32_t s_addr = tmem_base + slot * S_STRIDE + lane_off;
       ptx::mbar_wait(&s_full[slot], (J >> 1) & 1);
       ptx::tc_fence_after();
-      // pass 1: row maximum over the L real keys
+      // this thread's half of the score row -> registers (all loads in flight, one wait)
+      uint32_t v[HALF_GROUPS][16];
+#pragma unroll
+      for (int gi = 0; gi < HALF_GROUPS; ++gi)
+        if (gi < g_count) tmem_ld_x16(s_addr + 16 * (g_begin + gi), v[gi]);
+      ptx::tmem_ld_wait();
       float mx = -INFINITY;
-      for (int g = 0; g < groups; ++g) {
-        uint32_t raw[16];
-        tmem_ld_x16(s_addr + 16 * g, raw);
-        ptx::tmem_ld_wait();
 #pragma unroll
-        for (int j = 0; j < 16; ++j)
-          if (16 * g + j < p.L) mx = fmaxf(mx, __uint_as_float(raw[j]));
-      }
-      const float mb = mx * p.sl2;
-      // pass 2: probabilities; hi plane overwrites the scores already consumed, lo plane is kept
-      // in registers until every score column has been read
-      float sum = 0.f;
-      uint32_t lo_keep[MAX_LP / 2];
+      for (int gi = 0; gi < HALF_GROUPS; ++gi)
+        if (gi < g_count) {
+          const int key0 = 16 * (g_begin + gi);
+          if (key0 + 16 <= p.L) {  // warp-uniform: only the last group straddles L
 #pragma unroll
-      for (int g = 0; g < MAX_LP / 16; ++g) {
-        if (g < groups) {
-          uint32_t raw[16], hi[8];
-          tmem_ld_x16(s_addr + 16 * g, raw);
-          ptx::tmem_ld_wait();
-          softmax_group(raw, 16 * g, p.L, p.sl2, mb, sum, hi, &lo_keep[8 * g]);
-          tmem_st_x8(s_addr + 8 * g, hi);
+            for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[gi][j]));
+          } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j)
+              if (key0 + j < p.L) mx = fmaxf(mx, __uint_as_float(v[gi][j]));
+          }
         }
-      }
+      // exchange the partial maxima of the two halves; after this barrier every score of the
+      // tile has been read, so the probabilities may overwrite the score buffer
+      float* mxb = max_buf + slot * 2 * TILE_Q;
+      mxb[half * TILE_Q + row_in_tile] = mx;
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      mx = fmaxf(mx, mxb[(half ^ 1) * TILE_Q + row_in_tile]);
+      const float mb = mx * p.sl2;
+      float sum = 0.f;
 #pragma unroll
-      for (int g = 0; g < MAX_LP / 16; ++g)
-        if (g < groups) tmem_st_x8(s_addr + PLO_OFF + 8 * g, &lo_keep[8 * g]);
+      for (int gi = 0; gi < HALF_GROUPS; ++gi)
+        if (gi < g_count) {
+          const int g = g_begin + gi;
+          sum += (16 * g + 16 <= p.L) ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
+                                      : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+          tmem_st_x8(s_addr + 8 * g, &v[gi][0]);             // hi plane, packed
+          tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
+        }
+      sum_buf[slot * 2 * TILE_Q + half * TILE_Q + row_in_tile] = sum;
       tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
       if (lane == 0) ptx::mbar_arrive(&p_full[slot]);
-      // the previous tile's output is ready by now: normalise and store it
-      if (J > 0) write_output(J - 1, inv_sum_prev);
-      inv_sum_prev = 1.0f / sum;
+      // the previous tile's output is ready by now: normalise and store it.  (Its row sums were
+      // written before the barrier above by both halves.)
+      if (J > 0) write_output(J - 1);
     }
-    if (my_tiles > 0) write_output(my_tiles - 1, inv_sum_prev);
+    if (my_tiles > 0) {
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      write_output(my_tiles - 1);
+    }
   }
 
   ptx::tc_fence_before();
@@ -395,12 +414,12 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   p.out_plane_stride = out_plane_stride;
   p.ld_out = ld_out;
   p.width = heads * HD;
-  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 256 + 1024;
+  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 1024;
   static bool configured = false;
   if (!configured) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 256 + 1024));
+                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 1024));
     configured = true;
   }
   int ctas = sm_count();

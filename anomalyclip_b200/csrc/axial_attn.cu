@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "split.cuh"
 
 namespace aclip {
 
@@ -103,14 +104,7 @@ axial_attention_kernel(const float* __restrict__ qkv, int E, int heads, int L, l
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int t = 0; t < 4; ++t) {
-      const float a = o[d + 2 * t], b = o[d + 2 * t + 1];
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(a), h1 = __float2bfloat16_rn(b);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-      hi[t] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-      lo[t] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+      split_pack2(o[d + 2 * t], o[d + 2 * t + 1], hi[t], lo[t]);
     }
     *reinterpret_cast<uint4*>(dst + d) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst + d + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);

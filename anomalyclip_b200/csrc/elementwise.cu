@@ -3,19 +3,13 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "split.cuh"
 #include "rowmap.cuh"
 
 namespace aclip {
 
 __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t& lo) {
-  const __nv_bfloat16 h0 = __float2bfloat16_rn(a);
-  const __nv_bfloat16 h1 = __float2bfloat16_rn(b);
-  const __nv_bfloat16 l0 = __float2bfloat16_rn(a - __bfloat162float(h0));
-  const __nv_bfloat16 l1 = __float2bfloat16_rn(b - __bfloat162float(h1));
-  hi = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-       (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-  lo = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-       (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
+  split_pack2(a, b, hi, lo);
 }
 
 // ------------------------------------------------------------------------------ split

@@ -25,6 +25,7 @@
 #include <cuda_bf16.h>
 
 #include "ptx.cuh"
+#include "split.cuh"
 
 namespace aclip {
 
@@ -124,16 +125,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
   if (p.out_split != nullptr) {
     uint32_t hi[16], lo[16];
 #pragma unroll
-    for (int j = 0; j < 16; ++j) {
-      const __nv_bfloat16 h0 = __float2bfloat16_rn(v[2 * j]);
-      const __nv_bfloat16 h1 = __float2bfloat16_rn(v[2 * j + 1]);
-      const __nv_bfloat16 l0 = __float2bfloat16_rn(v[2 * j] - __bfloat162float(h0));
-      const __nv_bfloat16 l1 = __float2bfloat16_rn(v[2 * j + 1] - __bfloat162float(h1));
-      hi[j] = static_cast<uint32_t>(__bfloat16_as_ushort(h0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(h1)) << 16);
-      lo[j] = static_cast<uint32_t>(__bfloat16_as_ushort(l0)) |
-              (static_cast<uint32_t>(__bfloat16_as_ushort(l1)) << 16);
-    }
+    for (int j = 0; j < 16; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
     uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ld_split + n);
     uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
                                          out_row * p.ld_split + n);

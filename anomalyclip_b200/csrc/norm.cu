@@ -6,6 +6,7 @@
 
 #include "common.h"
 #include "rowmap.cuh"
+#include "split.cuh"
 
 namespace aclip {
 
@@ -79,16 +80,12 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
       y.w = v[i].w * rstd * g.w + b.w;
       if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * ld_f32)[c] = y;
       if (out_split != nullptr) {
-        const __nv_bfloat16 h0 = __float2bfloat16_rn(y.x), h1 = __float2bfloat16_rn(y.y);
-        const __nv_bfloat16 h2 = __float2bfloat16_rn(y.z), h3 = __float2bfloat16_rn(y.w);
-        const __nv_bfloat16 l0 = __float2bfloat16_rn(y.x - __bfloat162float(h0));
-        const __nv_bfloat16 l1 = __float2bfloat16_rn(y.y - __bfloat162float(h1));
-        const __nv_bfloat16 l2 = __float2bfloat16_rn(y.z - __bfloat162float(h2));
-        const __nv_bfloat16 l3 = __float2bfloat16_rn(y.w - __bfloat162float(h3));
+        uint32_t h01, l01, h23, l23;
+        split_pack2(y.x, y.y, h01, l01);
+        split_pack2(y.z, y.w, h23, l23);
         __nv_bfloat16* dst = out_split + row * ld_split + 4 * c;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(pack_bf16(h0, h1), pack_bf16(h2, h3));
-        *reinterpret_cast<uint2*>(dst + plane_stride) =
-            make_uint2(pack_bf16(l0, l1), pack_bf16(l2, l3));
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+        *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(l01, l23);
       }
     }
   }
