@@ -149,7 +149,7 @@ def run_reference(args) -> None:
     value = statistics.median(vals)
     sample_txt = (f"per step: oracle ViT-B/16 on {sample} frames (scaled to {FRAMES_PER_STEP}) + "
                   f"selector/temporal/head on one {FRAMES_PER_STEP}-row unit; median of {args.steps} steps")
-    print(json.dumps({
+    _emit({
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
@@ -158,7 +158,7 @@ def run_reference(args) -> None:
                          "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
-    }))
+    })
 
 
 # ------------------------------------------------------------------------------------------
@@ -315,7 +315,7 @@ def run_b200(args) -> None:
 
     if rank == 0:
         flops_per_frame = VIT_GFLOP_PER_FRAME * 1e9 + TEMPORAL_MFLOP_PER_FRAME * 1e6
-        print(json.dumps({
+        _emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
@@ -328,9 +328,27 @@ def run_b200(args) -> None:
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "algorithmic_tflops_whole_path": value * flops_per_frame / 1e12 / n_gpus,
             "kernels": breakdown,
-        }))
+        })
     if world > 1:
         dist.destroy_process_group()
+
+
+_REAL_STDOUT = None
+
+
+def _quiet_stdout() -> None:
+    """Everything except the final JSON line goes to stderr -- including C-level prints of the
+    libraries (NCCL writes its version banner to stdout)."""
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
+
+def _emit(obj: dict) -> None:
+    out = _REAL_STDOUT if _REAL_STDOUT is not None else sys.stdout
+    out.write(json.dumps(obj) + "\n")
+    out.flush()
 
 
 def main() -> None:
@@ -343,6 +361,7 @@ def main() -> None:
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: 1 warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
+    _quiet_stdout()
     if args.impl == "reference":
         run_reference(args)
     else:

@@ -266,3 +266,31 @@ def padded_length(num_frames: int, num_segments: int, seg_length: int, stride: i
     """Test mode pads the frame count up to a multiple of num_segments*seg_length*stride."""
     unit = num_segments * seg_length * stride
     return int(math.ceil(num_frames / unit) * unit)
+
+
+def test_mode_frame_indices(num_frames: int, num_segments: int, seg_length: int, stride: int = 1):
+    """The reference's own loops (feature_dataset.py:252-259,359-366): list of source-frame
+    indices in append order, and segment_size (:373)."""
+    end_frame = padded_length(num_frames, num_segments, seg_length, stride)
+    n_starts = int(end_frame / (seg_length * stride))
+    start_indices = [k * (seg_length * stride) for k in range(n_starts)]
+    out = []
+    for start_index in start_indices:
+        for i in range(seg_length):
+            out.append((int(start_index) + i * stride) % num_frames)
+    return out, len(start_indices) // num_segments
+
+
+test_mode_frame_indices.__test__ = False
+
+
+def frame_labels(num_frames: int, start_frame: int, label: int, normal_id: int, intervals):
+    """feature_dataset.py:336-349."""
+    labels = []
+    for i in range(num_frames):
+        lab = normal_id
+        for s, e in zip(intervals[::2], intervals[1::2]):
+            if int(s) <= i + start_frame <= int(e):
+                lab = label
+        labels.append(lab)
+    return labels

@@ -10,6 +10,8 @@ What is pinned
                   a 2-layer / width-128 / 2-head instance on 32x32 frames, seeded weights.
   selector.npz    reference `SelectorModel.forward(test_mode=True)` (selector_model.py:32-69).
   head.npz        reference `ClassificationHead.forward` (classification_head.py:11-15).
+  text.npz        reference `TextEncoder.forward` (text_encoder.py:14-25) on a small reference CLIP
+                  text transformer with PromptLearner-style prompts (coop.py:82-90).
   temporal.npz    reference `TemporalModel.forward(test_mode=True)` (temporal_model.py:42-77) run
                   over a STAND-IN for the un-vendored `axial_attention` package: the stand-in is
                   this script's nn.Module restatement of axial-attention 0.6.1, so this vector pins
@@ -286,7 +288,49 @@ def make_temporal():
     print("temporal", tuple(out.shape), sorted(tm.state_dict().keys())[:6])
 
 
+def make_text():
+    """Reference TextEncoder (text_encoder.py:5-25) over a small reference CLIP text transformer
+    (clip/model.py:293-431), fed with PromptLearner-style prompts [SOS][ctx][class .][EOT][pad]."""
+    sys.path.insert(0, str(REF))
+    clip_model_mod = _load_by_path("ref_clip_model_t", REF / "src/models/components/clip/model.py")
+    from src.models.components.text_encoder import TextEncoder
+
+    torch.manual_seed(5)
+    n_cls, n_ctx, ctx_len, vocab, width = 5, 4, 20, 64, 64
+    clip_model = clip_model_mod.CLIP(embed_dim=32, image_resolution=32, vision_layers=1, vision_width=64,
+                                     vision_patch_size=16, context_length=ctx_len, vocab_size=vocab,
+                                     transformer_width=width, transformer_heads=2,
+                                     transformer_layers=2).float().eval()
+    gen = torch.Generator().manual_seed(23)
+    with torch.no_grad():
+        for name, p_ in clip_model.transformer.named_parameters():
+            if name.endswith("bias"):
+                p_.copy_(0.1 * torch.randn(p_.shape, generator=gen))
+        clip_model.ln_final.weight.copy_(1 + 0.2 * torch.randn(width, generator=gen))
+        clip_model.ln_final.bias.copy_(0.1 * torch.randn(width, generator=gen))
+    enc = TextEncoder(clip_model).eval()
+    tokens = torch.zeros(n_cls, ctx_len, dtype=torch.long)
+    for i in range(n_cls):   # SOS, ctx placeholders, name tokens, '.', EOT (= highest id), padding 0
+        seq = [vocab - 2] + [7] * n_ctx + [10 + j for j in range(1 + i % 3)] + [9, vocab - 1]
+        tokens[i, : len(seq)] = torch.tensor(seq)
+    with torch.no_grad():
+        emb = clip_model.token_embedding(tokens)
+        ctx = 0.02 * torch.randn(n_cls, n_ctx, width, generator=gen)
+        prompts = torch.cat([emb[:, :1], ctx, emb[:, 1 + n_ctx:]], dim=1)   # coop.py:82-90
+        out = enc(prompts, tokens)
+    sd = {"text_encoder." + k: v for k, v in enc.state_dict().items()}
+    sd["token_embedding.weight"] = clip_model.token_embedding.weight
+    sd["prompt_learner.ctx"] = ctx
+    sd["prompt_learner.token_prefix"] = emb[:, :1]
+    sd["prompt_learner.token_suffix"] = emb[:, 1 + n_ctx:]
+    np.savez(OUT / "text.npz", out=out.numpy(), tokens=tokens.numpy(),
+             cfg=np.array([n_cls, n_ctx, ctx_len, vocab, width, 2, 2, 32], dtype=np.int64),
+             **{"w." + k: v for k, v in _np(sd).items()})
+    print("text", tuple(out.shape), sorted(sd)[:4])
+
+
 if __name__ == "__main__":
+    make_text()
     make_vit()
     make_selector()
     make_head()

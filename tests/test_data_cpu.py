@@ -1,0 +1,43 @@
+"""Frame-batch assembly (test mode) against the oracle's restatement of the reference loops."""
+import numpy as np
+import pytest
+import torch
+
+from anomalyclip_b200 import data
+from oracle import anomalyclip_oracle as oracle
+
+
+@pytest.mark.parametrize("frames", [1, 15, 16, 511, 512, 513, 1000, 1536, 4097])
+@pytest.mark.parametrize("stride", [1, 2])
+def test_index_plan_matches_reference_loops(frames, stride):
+    idx, seg = data.test_mode_indices(frames, 32, 16, stride)
+    ref, seg_ref = oracle.test_mode_frame_indices(frames, 32, 16, stride)
+    assert idx.tolist() == ref and seg == seg_ref
+    assert len(idx) * stride == data.padded_length(frames, 32, 16, stride)
+    assert idx.max() < frames
+
+
+def test_labels_and_dataset_tuple(tmp_path):
+    rng = np.random.default_rng(0)
+    frames, ncrops = 700, 1
+    feats = rng.standard_normal((frames * ncrops, 512)).astype(np.float32)
+    np.save(tmp_path / "Abuse001_x264.npy", feats)
+    (tmp_path / "test.txt").write_text("Abuse001_x264.npy 0 699 3\n")
+    ds = data.FeatureVideoDataset.from_annotation_file(
+        str(tmp_path / "test.txt"), str(tmp_path), num_segments=32, seg_length=16, stride=1,
+        ncrops=ncrops, normal_id=7, annotations={"Abuse001_x264": [100, 200, 650, 10_000]})
+    x, labels, label, segment_size, path = ds[0]
+    assert x.shape == (1, 1024, 512) and segment_size == 2 and label == 3
+    assert labels.tolist() == oracle.frame_labels(frames, 0, 3, 7, [100, 200, 650, 10_000])
+    ref_idx, _ = oracle.test_mode_frame_indices(frames, 32, 16, 1)
+    assert torch.equal(x[0], torch.from_numpy(feats)[ref_idx])
+    # default collate with batch_size_test = 1 gives the shape test_step expects
+    batch = torch.utils.data.default_collate([ds[0]])
+    assert batch[0].shape == (1, 1, 1024, 512) and int(batch[3][0]) == 2
+
+
+def test_gather_raw_frames_wraps_around():
+    frames = torch.arange(600, dtype=torch.uint8).view(600, 1, 1, 1).expand(600, 3, 2, 2)
+    batch, seg = data.gather_test_frames(frames, 32, 16)
+    assert batch.shape == (1024, 3, 2, 2) and seg == 2
+    assert batch[:, 0, 0, 0].tolist() == [(i % 600) % 256 for i in range(1024)]

@@ -155,3 +155,23 @@ def test_target_paths_of_the_reference_configs_resolve():
                    "src.models.components.classification_head.ClassificationHead"):
         mod, name = target.rsplit(".", 1)
         assert hasattr(importlib.import_module(mod), name), target
+
+
+def test_text_tower_matches_reference_text_encoder():
+    """The stock-PyTorch text tower of the mirror (evaluated once per checkpoint) against the
+    reference TextEncoder's own output, with the EOT positions recovered without the tokenizer."""
+    import numpy as np
+    from anomalyclip_b200.models import PromptLearner, TextEncoder, eot_positions
+    z = np.load(ROOT / "tests" / "golden" / "text.npz")
+    w = {k[2:]: torch.from_numpy(z[k]) for k in z.files if k.startswith("w.")}
+    n_cls, n_ctx, ctx_len, vocab, width, heads, layers, embed = (int(v) for v in z["cfg"])
+    enc = TextEncoder(width, layers, heads, ctx_len, embed)
+    missing, unexpected = enc.load_state_dict(
+        {k[len("text_encoder."):]: v for k, v in w.items() if k.startswith("text_encoder.")}, strict=True)
+    pl = PromptLearner(n_cls, n_ctx, width, ctx_len, shared_context=False)
+    pl.load_state_dict({k[len("prompt_learner."):]: v for k, v in w.items() if k.startswith("prompt_learner.")})
+    eot = eot_positions(pl.token_suffix, w["token_embedding.weight"][0], n_ctx)
+    assert eot.tolist() == torch.from_numpy(z["tokens"]).argmax(-1).tolist()
+    with torch.no_grad():
+        out = enc(pl(), eot)
+    torch.testing.assert_close(out, torch.from_numpy(z["out"]), rtol=1e-4, atol=1e-5)
