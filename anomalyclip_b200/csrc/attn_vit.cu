@@ -286,6 +286,9 @@ namespace aclip {
 int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                   int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
                   cudaStream_t stream) {
+  if (kernel >= 16)  // profiling experiments: kernel = 16 + debug mask
+    return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                            out_plane_stride, ld_out, stream, kernel - 16);
   ACLIP_REQUIRE(kernel >= 0 && kernel <= 2, "vit_attention: kernel must be 0, 1 or 2");
   if (kernel == 1)
     return vit_attention_mma(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,

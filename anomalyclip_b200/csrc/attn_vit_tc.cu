@@ -47,6 +47,7 @@ struct AttnTcParams {
   long long out_plane_stride;
   int ld_out;
   int width;                // heads * 64: column offset of K (and 2x for V) inside a qkv row
+  int debug;                // profiling experiments only (0 in production)
 };
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -118,7 +119,14 @@ __device__ __forceinline__ float softmax_group(uint32_t (&v)[16], int key0, int 
       if (k + 1 >= L) p1 = 0.f;
     }
     sum += p0 + p1;
-    split_pack2(p0, p1, hi[j], lo[j]);
+    // hi plane by truncation (one byte-permute for two keys instead of a conversion on the
+    // 16-lane pipe, which is this kernel's bottleneck next to ex2); lo = bf16(p - hi) still
+    // rounds to nearest, so hi + lo carries p to 2^-16 relative.
+    const uint32_t b0 = __float_as_uint(p0), b1 = __float_as_uint(p1);
+    hi[j] = __byte_perm(b0, b1, 0x7632);
+    const __nv_bfloat162 l = __floats2bfloat162_rn(p0 - __uint_as_float(b0 & 0xffff0000u),
+                                                   p1 - __uint_as_float(b1 & 0xffff0000u));
+    lo[j] = *reinterpret_cast<const uint32_t*>(&l);
   }
 #pragma unroll
   for (int j = 0; j < 8; ++j) { v[j] = hi[j]; v[8 + j] = lo[j]; }
@@ -144,6 +152,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
   float* max_buf = reinterpret_cast<float*>(bars + 16);   // [2 slots][2 halves][128 rows]
   float* sum_buf = max_buf + 4 * TILE_Q;                  // [2 slots][2 halves][128 rows]
+  uint8_t* out_stage = reinterpret_cast<uint8_t*>(sum_buf + 4 * TILE_Q);  // [4 quarters][2 planes][32][128 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp == 0 && lane == 0) {
@@ -270,21 +279,38 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       const int it = J >> 1, q = J & 1;
       const int item = blockIdx.x + it * gridDim.x;
       const int b = item / p.heads, h = item - b * p.heads;
-      const int r = q * TILE_Q + row_in_tile;
       const float* sb = sum_buf + (J & 1) * 2 * TILE_Q;
       const float inv_sum = 1.0f / (sb[row_in_tile] + sb[TILE_Q + row_in_tile]);
-      if (r < p.L) {
-        __nv_bfloat16* dst = p.out + (static_cast<long long>(b) * p.L + r) * p.ld_out + h * HD + 32 * half;
+      // Stage this warp's 32 rows x 32 dims (hi and lo) in shared memory next to the other half's
+      // 32 dims, then write whole 128-byte rows: 4 rows per store instruction instead of 32
+      // scattered 16-byte pieces.  16-byte chunks are XOR-swizzled by the row to avoid conflicts.
+      uint8_t* stage = out_stage + quarter * (2 * 32 * 128);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t hi[4], lo[4];
+      for (int c = 0; c < 4; ++c) {
+        uint32_t hi[4], lo[4];
 #pragma unroll
-          for (int j = 0; j < 4; ++j)
-            split_pack2(__uint_as_float(o[8 * c + 2 * j]) * inv_sum,
-                        __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum, hi[j], lo[j]);
-          *reinterpret_cast<uint4*>(dst + 8 * c) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-          *reinterpret_cast<uint4*>(dst + 8 * c + p.out_plane_stride) =
-              make_uint4(lo[0], lo[1], lo[2], lo[3]);
+        for (int j = 0; j < 4; ++j)
+          split_pack2(__uint_as_float(o[8 * c + 2 * j]) * inv_sum,
+                      __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum, hi[j], lo[j]);
+        const int chunk = (half * 4 + c) ^ (lane & 7);
+        *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+        *reinterpret_cast<uint4*>(stage + 4096 + lane * 128 + chunk * 16) =
+            make_uint4(lo[0], lo[1], lo[2], lo[3]);
+      }
+      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+      if (!(p.debug & 2)) {
+        const int row_base = q * TILE_Q + quarter * 32;
+        __nv_bfloat16* out_rows = p.out + (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = half * 16 + i * 4 + (lane >> 3);   // this warp stores 16 of the 32 rows
+          const int chunk = lane & 7;
+          if (row_base + row < p.L) {
+            const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
+            __nv_bfloat16* dst = out_rows + static_cast<long long>(row) * p.ld_out + chunk * 8;
+            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+            *reinterpret_cast<uint4*>(dst + p.out_plane_stride) = *reinterpret_cast<const uint4*>(src + 4096);
+          }
         }
       }
     };
@@ -326,10 +352,13 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       for (int gi = 0; gi < HALF_GROUPS; ++gi)
         if (gi < g_count) {
           const int g = g_begin + gi;
-          sum += (16 * g + 16 <= p.L) ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
-                                      : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
-          tmem_st_x8(s_addr + 8 * g, &v[gi][0]);             // hi plane, packed
-          tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
+          if (!(p.debug & 1))
+            sum += (16 * g + 16 <= p.L) ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
+                                        : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+          if (!(p.debug & 4)) {
+            tmem_st_x8(s_addr + 8 * g, &v[gi][0]);             // hi plane, packed
+            tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
+          }
         }
       sum_buf[slot * 2 * TILE_Q + half * TILE_Q + row_in_tile] = sum;
       tmem_st_wait();
@@ -376,7 +405,7 @@ EncodeTiledFn encode_fn() {
 
 int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                      int heads, void* out_split, long long out_plane_stride, int ld_out,
-                     cudaStream_t stream) {
+                     cudaStream_t stream, int debug) {
   ACLIP_REQUIRE(qkv_split != nullptr && out_split != nullptr, "vit_attention: null pointer");
   ACLIP_REQUIRE(B > 0 && heads > 0 && L > 0, "vit_attention: empty problem");
   const int LP = (L + 15) / 16 * 16;
@@ -414,12 +443,13 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   p.out_plane_stride = out_plane_stride;
   p.ld_out = ld_out;
   p.width = heads * HD;
-  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 1024;
+  p.debug = debug;
+  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
   static bool configured = false;
   if (!configured) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 1024));
+                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024));
     configured = true;
   }
   int ctas = sm_count();

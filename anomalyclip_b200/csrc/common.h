@@ -38,7 +38,7 @@ int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, i
                   cudaStream_t stream);
 int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                      int heads, void* out_split, long long out_plane_stride, int ld_out,
-                     cudaStream_t stream);
+                     cudaStream_t stream, int debug = 0);
 int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E, int heads,
                     int axis, void* out_split, long long plane_stride, cudaStream_t stream);
 
