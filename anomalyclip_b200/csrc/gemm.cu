@@ -183,8 +183,9 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.split_plane_stride = g.split_plane_stride;
   p.ldc = g.ldc;
   p.ld_split = g.ld_split > 0 ? g.ld_split : g.ldc;
-  p.row_group = g.row_group > 0 ? g.row_group : 0x7fffffff;
-  p.row_group_stride = g.row_group > 0 ? g.row_group_stride : 0;
+  p.row_group = g.row_group > 0 ? g.row_group : 1;
+  p.row_group_stride = g.row_group > 0 ? g.row_group_stride : 0;  // 0 = no remap
+  ACLIP_REQUIRE(g.row_group <= 0 || g.row_group_stride > 0, "gemm: row_group_stride must be > 0 with a row remap");
   p.row_offset = g.row_offset;
 
   CUtensorMap tmA, tmB;

@@ -69,7 +69,9 @@ struct GemmCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int TMEM_COLS = 2 * BLOCK_N;  // double-buffered fp32 accumulator
   static constexpr int BAR_BYTES = 256;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + BAR_BYTES + 1024;  // +1024 align slack
+  static constexpr int EPI_WARPS = 4;
+  static constexpr int SMEM_BYTES =
+      STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * 32 * 128 + 1024;  // +1024 align slack
   static constexpr int THREADS = 192;
   static_assert(STAGES >= 2, "need at least a double buffer");
   static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
@@ -85,14 +87,23 @@ __device__ __forceinline__ float apply_act(float x, int act) {
   return x;
 }
 
-// Epilogue of one 32-column chunk of one accumulator row per thread: TMEM -> registers ->
-// bias -> activation -> residual -> fp32 and/or split-bf16 global stores.
+// Epilogue of one 32-row x 32-column chunk per warp.  The accumulator comes out of TMEM with one
+// row per lane; bias and activation are applied in that layout, then the chunk is transposed through
+// a 4 KB per-warp staging buffer (16-byte pieces XOR-swizzled by the row) so that every global
+// access is row-contiguous: a load/store instruction touches 4 rows x 128 B instead of 32 rows x
+// 16 B.  In the transposed layout lane = (row & 3 within a group of 4 rows, 16-byte piece 0..7).
+constexpr int EPI_STAGE_BYTES = 32 * 128;
+
+struct EpiRows {      // rows of this warp's 32-row block
+  int m_base;         // first logical row
+};
+
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
-                                               bool row_ok, long long out_row, long long res_row) {
+                                               int m_base, int lane, uint8_t* stage) {
   uint32_t raw[32];
   ptx::tmem_ld_32x32(taddr, raw);
   ptx::tmem_ld_wait();
-  if (!row_ok) return;
+  if (m_base >= p.M) return;  // warp-uniform: the whole block is padding
   float v[32];
 #pragma unroll
   for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
@@ -108,43 +119,53 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
 #pragma unroll
     for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
   }
-  if (p.residual != nullptr) {
-    const float4* r4 = reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + n);
+  __syncwarp();  // the previous chunk's readers are done with the staging buffer
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 r = r4[j];
-      v[4 * j + 0] += r.x; v[4 * j + 1] += r.y; v[4 * j + 2] += r.z; v[4 * j + 3] += r.w;
+  for (int j = 0; j < 8; ++j)
+    *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+        make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  __syncwarp();
+  const int piece = lane & 7;
+  const int col = n + piece * 4;
+  // phase 1: all residual loads in flight before anything is stored (out_f32 may alias residual)
+  float4 val[8];
+  long long out_rows[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    const int m = m_base + row;
+    out_rows[i] = -1;
+    if (m < p.M) {
+      long long out_row = m;
+      if (p.row_group_stride != 0)
+        out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride + (m % p.row_group);
+      out_row += p.row_offset;
+      out_rows[i] = out_row;
+      val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (p.residual != nullptr) {
+        const long long res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
+        val[i] = *reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + col);
+      }
     }
   }
-  if (p.out_f32 != nullptr) {
-    float4* o4 = reinterpret_cast<float4*>(p.out_f32 + out_row * p.ldc + n);
+  // phase 2: add the staged accumulator values and store row-contiguously
 #pragma unroll
-    for (int j = 0; j < 8; ++j)
-      o4[j] = make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
-  }
-  if (p.out_split != nullptr) {
-    uint32_t hi[16], lo[16];
-#pragma unroll
-    for (int j = 0; j < 16; ++j) split_pack2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
-    uint4* oh = reinterpret_cast<uint4*>(p.out_split + out_row * p.ld_split + n);
-    uint4* ol = reinterpret_cast<uint4*>(p.out_split + p.split_plane_stride +
-                                         out_row * p.ld_split + n);
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      oh[j] = make_uint4(hi[4 * j], hi[4 * j + 1], hi[4 * j + 2], hi[4 * j + 3]);
-      ol[j] = make_uint4(lo[4 * j], lo[4 * j + 1], lo[4 * j + 2], lo[4 * j + 3]);
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    if (out_rows[i] >= 0) {
+      const float4 a = *reinterpret_cast<const float4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
+      const float4 v4 = make_float4(a.x + val[i].x, a.y + val[i].y, a.z + val[i].z, a.w + val[i].w);
+      if (p.out_f32 != nullptr)
+        *reinterpret_cast<float4*>(p.out_f32 + out_rows[i] * p.ldc + col) = v4;
+      if (p.out_split != nullptr) {
+        uint32_t h0, l0, h1, l1;
+        split_pack2(v4.x, v4.y, h0, l0);
+        split_pack2(v4.z, v4.w, h1, l1);
+        __nv_bfloat16* dst = p.out_split + out_rows[i] * p.ld_split + col;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(dst + p.split_plane_stride) = make_uint2(l0, l1);
+      }
     }
-  }
-}
-
-__device__ __forceinline__ void epilogue_rows(const GemmParams& p, int m, bool& row_ok,
-                                              long long& out_row, long long& res_row) {
-  row_ok = m < p.M;
-  out_row = 0; res_row = 0;
-  if (row_ok) {
-    out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride + (m % p.row_group) +
-              p.row_offset;
-    res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
   }
 }
 
@@ -264,18 +285,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else {
     // ------------------------------------------------------------ epilogue (warps 2..5)
     const int quarter = warp & 3;  // TMEM lane quarter this warp may read
+    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + Cfg::BAR_BYTES + (warp - 2) * EPI_STAGE_BYTES;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n0 = (t % n_tiles) * BLOCK_N;
-      const int m0 = (t / n_tiles) * Cfg::BLOCK_M;
-      const int m = m0 + quarter * 32 + lane;
-      const bool row_ok = m < p.M;
-      long long out_row = 0, res_row = 0;
-      if (row_ok) {
-        out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride +
-                  (m % p.row_group) + p.row_offset;
-        res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
-      }
+      const int m_base = (t / n_tiles) * Cfg::BLOCK_M + quarter * 32;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -283,7 +297,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int c = 0; c < BLOCK_N / 32; ++c) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;  // warp-uniform
-        epilogue_chunk(p, t_row + c * 32, n, row_ok, out_row, res_row);
+        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
       }
       // hand the accumulator buffer back to the MMA warp
       ptx::tc_fence_before();
@@ -326,8 +340,8 @@ struct Gemm2Cfg {
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 512;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + 1024;
   static constexpr int EPI_WARPS = 8;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 256 + EPI_WARPS * 32 * 128 + 1024;
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
 };
 
@@ -451,14 +465,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // ------------------------------------------------------------ epilogue (warps 2..9)
     const int quarter = warp & 3;            // TMEM lane quarter this warp may read
     const int col_half = (warp - 2) >> 2;    // which 128 of the 256 columns
+    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
     uint32_t acc = 0, acc_phase = 0;
     for (int t = cluster_id; t < total_tiles; t += num_clusters) {
       const int n0 = (t % n_tiles) * Cfg::BLOCK_N + col_half * 128;
-      const int m0 = (t / n_tiles) * Cfg::BLOCK_M + static_cast<int>(rank) * Cfg::CTA_M;
-      const int m = m0 + quarter * 32 + lane;
-      bool row_ok;
-      long long out_row, res_row;
-      epilogue_rows(p, m, row_ok, out_row, res_row);
+      const int m_base = (t / n_tiles) * Cfg::BLOCK_M + static_cast<int>(rank) * Cfg::CTA_M + quarter * 32;
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
@@ -467,7 +478,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       for (int c = 0; c < 4; ++c) {
         const int n = n0 + c * 32;
         if (n >= p.N) break;  // warp-uniform
-        epilogue_chunk(p, t_row + c * 32, n, row_ok, out_row, res_row);
+        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -75,3 +75,15 @@ def test_weights_changed_after_first_call_are_repacked():
         concat_features=cfg.concat_features)
     assert not torch.allclose(a, b)
     assert_parity(b, ref, "scores after reloading weights")
+
+
+def test_device_prefetcher_preserves_batches():
+    from anomalyclip_b200.data import DevicePrefetcher
+    dev = torch.device("cuda")
+    host = [torch.full((4, 8), float(i)).pin_memory() for i in range(7)]
+    seen = []
+    for i, (x, tag) in enumerate(DevicePrefetcher(((h, i) for i, h in enumerate(host)), dev)):
+        assert x.is_cuda and tag == i
+        seen.append(float(x.sum().item()) / 32)      # consume before advancing
+    assert seen == [float(i) for i in range(7)]
+    assert list(DevicePrefetcher(iter(()), dev)) == []
