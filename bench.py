@@ -33,13 +33,13 @@ VIT_GFLOP_PER_FRAME = 35.127      # SURVEY 8d / BASELINE.md 2 (algorithmic, fp32
 TEMPORAL_MFLOP_PER_FRAME = 40.2   # ShanghaiTech configuration
 
 
-def _workload_config(n_gpus: int) -> dict:
+def _workload_config(n_gpus: int, micro_batch: int = 256) -> dict:
     return {
         "workload": ("configs[2]: ShanghaiTech-shaped raw frames 224x224 uint8, 512 frames/step/GPU "
                      "(2 ViT micro-batches of 256 = one 32x16 temporal unit), full ViT-B/16 + selector "
                      "+ temporal + score path"),
         "frames_per_step_per_gpu": FRAMES_PER_STEP,
-        "vit_micro_batch": 256,
+        "vit_micro_batch": micro_batch,
         "precision": "split-bf16 x3 tensor-core passes, fp32 accumulate (parity mode)",
         "l2": "inputs rotate over 4 frame buffers (308 MB) and activations are ~0.9 GB per micro-batch, both > 126 MB L2",
         "parallelism": f"dp{n_gpus} over sub-videos, one all-gather of score rows per step",
@@ -189,7 +189,7 @@ def run_b200(args) -> None:
                       num_segments=cfg.num_segments, seg_length=cfg.seg_length,
                       concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=cfg.stride,
                       load_from_features=False, ncrops=cfg.ncrops, build_text_tower=False,
-                      micro_batch=256, passes=3)
+                      micro_batch=args.micro_batch, passes=3)
     missing, unexpected = net.load_state_dict(syn.make_state_dict(cfg, with_vit=True), strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     net.set_text_features(syn.make_text_features(cfg))
@@ -325,7 +325,7 @@ def run_b200(args) -> None:
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split operands, f32 accumulate/residual", "data": "synthetic",
-            "config": _workload_config(n_gpus), "clocks": clocks,
+            "config": _workload_config(n_gpus, args.micro_batch), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 3 * 224 * 224,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * width * 4 * n_gpus},
@@ -363,6 +363,7 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: 1 warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
