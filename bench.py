@@ -290,7 +290,11 @@ def run_b200(args) -> None:
         "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tf_sustained"],
         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-        "traffic": None,
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT-block GEMM
+        # launches (in_proj 576 MB, out_proj 421 MB, c_fc 736 MB, c_proj 1002 MB) in the ncu --set full
+        # capture profiles/r1_ncu_full_block_v8.json; the algorithmic figure is next to it
+        "traffic": 684e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
+        "algorithmic_bytes_per_launch": gemm["bytes"] / max(gemm["launches"], 1),
         "passes": 3, "tensor_pipe_issued_tflops": 3 * achieved,
         "tensor_pipe_issued_frac": 3 * achieved / peaks["tf_sustained"],
         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
