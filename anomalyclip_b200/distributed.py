@@ -79,3 +79,16 @@ def run_sharded(num_units: int, unit_rows: int, compute: Callable[[int, int], to
     if local.shape[0] != cnt * unit_rows:
         raise ValueError("run_sharded: compute returned the wrong number of rows")
     return gather_rows(local, [c * unit_rows for _, c in blocks], group)
+
+
+def sharded_mean(local_sum: torch.Tensor, local_count: int,
+                 group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """Mean over all ranks of row sums accumulated per rank: ONE all-reduce of (sum[D], count).
+    Used for `ncentroid` (mean feature of the normal training videos,
+    src/models/anomaly_clip_module.py:419-445) when the normal set is sharded over the GPUs."""
+    packed = torch.cat((local_sum.to(torch.float64).reshape(-1),
+                        torch.tensor([float(local_count)], dtype=torch.float64,
+                                     device=local_sum.device)))
+    if dist.is_available() and dist.is_initialized():
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+    return (packed[:-1] / packed[-1].clamp_min(1.0)).to(torch.float32).reshape(local_sum.shape)

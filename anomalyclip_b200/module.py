@@ -59,7 +59,9 @@ class AnomalyCLIPModule(_Base):
 
     @torch.no_grad()
     def compute_ncentroid(self, loader, load_from_features: bool) -> torch.Tensor:
-        """Mean feature of the normal training videos, streamed in test mode (:419-441)."""
+        """Mean feature of the normal training videos, streamed in test mode (:419-441).  Under
+        torch.distributed each rank streams ITS shard of the loader and the (sum, count) pairs
+        are combined with one all-reduce."""
         dev = self._device
         total = torch.zeros(self.net.embedding_dim, dtype=torch.float64, device=dev)
         count = 0
@@ -73,7 +75,8 @@ class AnomalyCLIPModule(_Base):
                 feats = self.net.image_encoder(x.reshape(-1, c, h, w)[:n_real].to(dev))
             total += feats.double().sum(dim=0)
             count += feats.shape[0]
-        return (total / max(count, 1)).to(torch.float32)
+        from .distributed import sharded_mean
+        return sharded_mean(total, count)
 
     def on_test_start(self) -> None:
         if self.ncentroid is not None:
@@ -120,23 +123,13 @@ class AnomalyCLIPModule(_Base):
 
     # ---- metrics (anomaly_clip_module.py:501-619, the numeric part)
     def test_epoch_end(self, outputs: Any = None) -> Dict[str, float]:
-        from sklearn.metrics import average_precision_score, roc_auc_score
+        from .metrics import frame_metrics
 
-        labels = torch.cat(self.labels).numpy()
-        scores = torch.cat(self.abnormal_scores).numpy()
-        normal_id = self.net.normal_id
-        binary = (labels != normal_id).astype("int64")
-        metrics: Dict[str, float] = {}
-        if 0 < binary.sum() < binary.shape[0]:
-            metrics["test/AUC"] = float(roc_auc_score(binary, scores))
-            metrics["test/AP"] = float(average_precision_score(binary, scores))
+        labels = torch.cat(self.labels)
+        scores = torch.cat(self.abnormal_scores)
         probs = torch.cat(self.class_probs)
-        # class c >= normal_id sits in column c-1 (the normal row was dropped; :543-546)
-        pred = probs.argmax(dim=1)
-        pred = torch.where(pred >= normal_id, pred + 1, pred).numpy()
-        abn = labels != normal_id
-        if abn.any():
-            metrics["test/top1_abnormal"] = float((pred[abn] == labels[abn]).mean())
+        metrics = {f"test/{k}": v for k, v in
+                   frame_metrics(scores, probs, labels, self.net.normal_id).items()}
         if self.save_dir:
             Path(self.save_dir).mkdir(parents=True, exist_ok=True)
             with open(Path(self.save_dir) / "metrics.json", "w") as fp:

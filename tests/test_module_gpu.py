@@ -87,3 +87,38 @@ def test_device_prefetcher_preserves_batches():
         seen.append(float(x.sum().item()) / 32)      # consume before advancing
     assert seen == [float(i) for i in range(7)]
     assert list(DevicePrefetcher(iter(()), dev)) == []
+
+
+def test_eval_auc_within_1e3_of_reference_on_identical_features():
+    """north_star: eval AUC within 1e-3 of the reference on identical pre-extracted features."""
+    from anomalyclip_b200 import metrics
+    from anomalyclip_b200.module import AnomalyCLIPModule
+    cfg = PRESETS["ucfcrime"]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    net = _net(cfg)
+    net.load_state_dict(sd, strict=False)
+    net.set_text_features(text)
+    net.cuda().eval()
+    module = AnomalyCLIPModule(net, num_classes=cfg.num_classes)
+    module.ncentroid = m
+    g = torch.Generator().manual_seed(42)
+    ref_scores, ref_probs, all_labels = [], [], []
+    for vid, (frames, s) in enumerate([(500, 1), (900, 2), (1300, 3)]):
+        feats = make_features(cfg, s, seed=100 + vid)
+        labels = torch.where(torch.rand(frames, generator=g) < 0.3,
+                             torch.randint(0, cfg.num_classes, (frames,), generator=g),
+                             torch.full((frames,), cfg.normal_id))
+        module.test_step((feats, labels.unsqueeze(0), 0, s, f"v{vid}"), vid)
+        sim_ref, sc_ref = oracle.anomaly_clip_forward(
+            sd, feats, m, text, segment_size=s, normal_id=cfg.normal_id,
+            num_segments=cfg.num_segments, seg_length=cfg.seg_length, depth=cfg.depth,
+            heads=cfg.heads, concat_features=cfg.concat_features)
+        p_ref, s_ref = oracle.test_step_postprocess(sim_ref, sc_ref, frames)
+        ref_scores.append(s_ref), ref_probs.append(p_ref), all_labels.append(labels)
+    got = module.test_epoch_end()
+    ref = metrics.frame_metrics(torch.cat(ref_scores), torch.cat(ref_probs), torch.cat(all_labels),
+                                cfg.normal_id)
+    for k in ("AUC", "AP", "mAUC", "mAP"):
+        assert abs(got[f"test/{k}"] - ref[k]) < 1e-3, (k, got[f"test/{k}"], ref[k])
+    assert got["test/top1"] == ref["top1"] and got["test/top5"] == ref["top5"]
