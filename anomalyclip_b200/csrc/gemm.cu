@@ -161,13 +161,24 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.act >= 0 && g.act <= 2, "gemm: unknown activation %d", g.act);
   const int planes = g.passes == 1 ? 1 : 2;
   // 128-wide tiles when they waste fewer padded columns than 256-wide ones (e.g. N = 128, 384)
-  const bool narrow = ((g.N + 127) / 128) * 128 < ((g.N + 255) / 256) * 256;
   // CTA-pair kernel (256 x 256 tiles over two SMs) whenever N tiles evenly and there is enough
   // work to fill the machine; kernel = 1 / 2 forces the single-CTA / pair kernel (tests).
   ACLIP_REQUIRE(g.kernel >= 0 && g.kernel <= 2, "gemm: kernel must be 0 (auto), 1 or 2");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
   const bool pair = g.kernel == 2 || (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
-  const int block_n = pair ? 128 : (narrow ? 128 : 256);  // rows of W per TMA box
+  // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
+  // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
+  // more SMs share the K loop.  128 is also preferred when it wastes fewer padded columns.
+  int block_n = 128;  // rows of W per TMA box (the pair kernel loads 128 per CTA)
+  if (!pair) {
+    const int m_tiles = (g.M + 127) / 128;
+    const int want = sm_count() / 2;
+    auto tiles = [&](int bn) { return m_tiles * ((g.N + bn - 1) / bn); };
+    const bool narrow = ((g.N + 127) / 128) * 128 < ((g.N + 255) / 256) * 256;
+    if (!narrow && tiles(256) >= want) block_n = 256;
+    else if (tiles(128) >= want) block_n = 128;
+    else block_n = 64;
+  }
 
   GemmParams p{};
   p.M = g.M; p.N = g.N; p.K = g.K;
@@ -235,8 +246,11 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
                          : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);
   }
-  return g.passes == 3 ? launch<128, 3>(tmA, tmB, p, g.max_ctas, stream)
-                       : launch<128, 1>(tmA, tmB, p, g.max_ctas, stream);
+  if (block_n == 128)
+    return g.passes == 3 ? launch<128, 3>(tmA, tmB, p, g.max_ctas, stream)
+                         : launch<128, 1>(tmA, tmB, p, g.max_ctas, stream);
+  return g.passes == 3 ? launch<64, 3>(tmA, tmB, p, g.max_ctas, stream)
+                       : launch<64, 1>(tmA, tmB, p, g.max_ctas, stream);
 }
 
 }  // namespace aclip

@@ -74,7 +74,8 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * 32 * 128 + 1024;  // +1024 align slack
   static constexpr int THREADS = 192;
   static_assert(STAGES >= 2, "need at least a double buffer");
-  static_assert(TMEM_COLS == 256 || TMEM_COLS == 512, "TMEM columns must be a power of two");
+  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
+                "TMEM columns must be a power of two");
 };
 
 __device__ __forceinline__ float apply_act(float x, int act) {
