@@ -164,3 +164,23 @@ def test_gemm_cta_pair_split_output_rowmap_and_conv(ops):
     c1 = ops.gemm(xs, wk, bias=b, conv=(S, H, W, Cin), kernel=1)
     assert _rel(c2, cref) < 3e-5
     assert torch.equal(c1, c2)
+
+
+def test_gemm_random_shapes(ops):
+    """Ragged M, every legal N granule, K not a multiple of the 64-wide K block."""
+    import random
+    rnd = random.Random(1)
+    for _ in range(25):
+        M = rnd.choice([1, 2, 31, 127, 128, 129, 255, 257, 511, 700, 1023])
+        N = 32 * rnd.randint(1, 20)
+        K = 8 * rnd.randint(1, 90)
+        torch.manual_seed(M * 7 + N * 3 + K)
+        a = torch.randn(M, K, device="cuda")
+        w = torch.randn(N, K, device="cuda") * 0.05
+        bias = torch.randn(N, device="cuda")
+        res = torch.randn(M, N, device="cuda")
+        out = ops.gemm(ops.split(a), ops.split(w), bias=bias, residual=res)
+        s = ops.gemm(ops.split(a), ops.split(w), bias=bias, want_split=True)
+        ref = a.double() @ w.double().T + bias.double()
+        assert _rel(out, ref + res.double()) < 3e-5, (M, N, K)
+        assert _rel(_unsplit(s), ref) < 3e-5, (M, N, K)

@@ -1,4 +1,7 @@
 """The reference-facing API (AnomalyCLIP / AnomalyCLIPModule mirror) end to end on the GPU."""
+import os
+from pathlib import Path
+
 import pytest
 import torch
 
@@ -8,6 +11,7 @@ from tests.util_weights import (PRESETS, make_features, make_ncentroid, make_sta
                                 make_text_features)
 
 pytestmark = pytest.mark.gpu
+ROOT = Path(__file__).resolve().parent.parent
 
 
 def _net(cfg, load_from_features=True, **extra):
@@ -122,3 +126,60 @@ def test_eval_auc_within_1e3_of_reference_on_identical_features():
     for k in ("AUC", "AP", "mAUC", "mAP"):
         assert abs(got[f"test/{k}"] - ref[k]) < 1e-3, (k, got[f"test/{k}"], ref[k])
     assert got["test/top1"] == ref["top1"] and got["test/top5"] == ref["top5"]
+
+
+def test_ncrops_and_stride_follow_the_reference_layout():
+    """ncrops = 2 (each crop is its own temporal grid) and stride = 2 (repeat_interleave of the
+    outputs), anomaly_clip.py:132-134,149-152."""
+    import dataclasses
+    cfg = dataclasses.replace(PRESETS["xdviolence"], ncrops=2, stride=2)
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    net = _net(cfg)
+    net.load_state_dict(sd, strict=False)
+    net.set_text_features(text)
+    net.cuda().eval()
+    g = torch.Generator().manual_seed(8)
+    feats = torch.randn(1, 2, 2 * cfg.unit, 512, generator=g) * 0.5      # (b, ncrops, n*s*l, d), s = 2
+    sim_ref, sc_ref = oracle.anomaly_clip_forward(
+        sd, feats, m, text, segment_size=2, normal_id=cfg.normal_id, num_segments=cfg.num_segments,
+        seg_length=cfg.seg_length, depth=cfg.depth, heads=cfg.heads,
+        concat_features=cfg.concat_features, stride=2, ncrops=2)
+    sim, sc = net(feats.cuda(), None, m, 2, True)
+    assert sim.shape == (2 * 2 * cfg.unit * 2, cfg.num_classes - 1) and sc.shape == (sim.shape[0],)
+    assert_parity(sim, sim_ref, "ncrops/stride similarity")
+    assert_parity(sc, sc_ref, "ncrops/stride scores")
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_two_rank_nccl_sharding_matches_single_rank(tmp_path):
+    """configs[3] in miniature: sub-videos sharded over 2 ranks, ONE all-gather of the result rows."""
+    import subprocess
+    import sys
+    script = tmp_path / "worker.py"
+    script.write_text(
+        "import os, sys, torch, torch.distributed as dist\\n"
+        "sys.path.insert(0, os.environ['ACLIP_ROOT'])\\n"
+        "from anomalyclip_b200.distributed import run_sharded\\n"
+        "from anomalyclip_b200.engine import PackedTemporal, TemporalScorer\\n"
+        "from anomalyclip_b200 import synthetic as syn\\n"
+        "rank = int(os.environ['RANK']); torch.cuda.set_device(rank); dev = torch.device('cuda', rank)\\n"
+        "dist.init_process_group('nccl', device_id=dev)\\n"
+        "cfg = syn.PRESETS['xdviolence']\\n"
+        "p = PackedTemporal(syn.make_state_dict(cfg, with_vit=False), dev, num_classes=cfg.num_classes, normal_id=cfg.normal_id,\\n"
+        "    emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, num_segments=32, seg_length=16, concat_features=False)\\n"
+        "p.set_directions(syn.make_text_features(cfg), syn.make_ncentroid(cfg))\\n"
+        "sc = TemporalScorer(p)\\n"
+        "feats = syn.make_features(cfg, 5, seed=3).reshape(-1, 512).to(dev)\\n"
+        "def compute(start, count):\\n"
+        "    sim, s, pr = sc(feats[start * 512:(start + count) * 512], 1)\\n"
+        "    return torch.cat((s[:, None], pr), 1)\\n"
+        "rows = run_sharded(5, 512, compute)\\n"
+        "sim, s, pr = sc(feats, 1)\\n"
+        "assert torch.equal(rows, torch.cat((s[:, None], pr), 1)), 'sharded != single'\\n"
+        "dist.destroy_process_group(); print('rank', rank, 'ok')\\n")
+    env = dict(os.environ, ACLIP_ROOT=str(ROOT))
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+                         env=env, capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
