@@ -9,10 +9,14 @@
 // /root/reference/src/models/components/anomaly_clip.py:66-67).  PASSES == 1 is the plain
 // bf16 GEMM (hi plane only).
 //
-// Roles (192 threads, 1 CTA / SM):
+// Two kernels share the producer / issuer / epilogue code:
+//   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile            (192 threads)
+//   gemm2_tcgen05_kernel  a CTA pair (cta_group::2) per 256 x 256 tile   (320 threads per CTA)
+// Roles:
 //   warp 0  lane 0 : TMA producer   (A and W tiles, 128-byte swizzle, mbarrier complete_tx)
-//   warp 1  lane 0 : MMA issuer     (tcgen05.mma cta_group::1, M=128, N=BLOCK_N, K=16)
-//   warps 2..5     : epilogue       (tcgen05.ld -> bias / activation / residual -> global)
+//   warp 1  lane 0 : MMA issuer     (tcgen05.mma, K=16 per instruction)
+//   other warps    : epilogue       (tcgen05.ld -> bias / activation -> smem transpose ->
+//                                    residual -> row-contiguous fp32 / split-bf16 stores)
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a double-buffered TMEM accumulator
 // full/empty (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -94,10 +98,6 @@ __device__ __forceinline__ float apply_act(float x, int act) {
 // access is row-contiguous: a load/store instruction touches 4 rows x 128 B instead of 32 rows x
 // 16 B.  In the transposed layout lane = (row & 3 within a group of 4 rows, 16-byte piece 0..7).
 constexpr int EPI_STAGE_BYTES = 32 * 128;
-
-struct EpiRows {      // rows of this warp's 32-row block
-  int m_base;         // first logical row
-};
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
                                                int m_base, int lane, uint8_t* stage) {

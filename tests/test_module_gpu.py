@@ -152,32 +152,11 @@ def test_ncrops_and_stride_follow_the_reference_layout():
 
 
 @pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
-def test_two_rank_nccl_sharding_matches_single_rank(tmp_path):
+def test_two_rank_nccl_sharding_matches_single_rank():
     """configs[3] in miniature: sub-videos sharded over 2 ranks, ONE all-gather of the result rows."""
     import subprocess
     import sys
-    script = tmp_path / "worker.py"
-    script.write_text(
-        "import os, sys, torch, torch.distributed as dist\\n"
-        "sys.path.insert(0, os.environ['ACLIP_ROOT'])\\n"
-        "from anomalyclip_b200.distributed import run_sharded\\n"
-        "from anomalyclip_b200.engine import PackedTemporal, TemporalScorer\\n"
-        "from anomalyclip_b200 import synthetic as syn\\n"
-        "rank = int(os.environ['RANK']); torch.cuda.set_device(rank); dev = torch.device('cuda', rank)\\n"
-        "dist.init_process_group('nccl', device_id=dev)\\n"
-        "cfg = syn.PRESETS['xdviolence']\\n"
-        "p = PackedTemporal(syn.make_state_dict(cfg, with_vit=False), dev, num_classes=cfg.num_classes, normal_id=cfg.normal_id,\\n"
-        "    emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, num_segments=32, seg_length=16, concat_features=False)\\n"
-        "p.set_directions(syn.make_text_features(cfg), syn.make_ncentroid(cfg))\\n"
-        "sc = TemporalScorer(p)\\n"
-        "feats = syn.make_features(cfg, 5, seed=3).reshape(-1, 512).to(dev)\\n"
-        "def compute(start, count):\\n"
-        "    sim, s, pr = sc(feats[start * 512:(start + count) * 512], 1)\\n"
-        "    return torch.cat((s[:, None], pr), 1)\\n"
-        "rows = run_sharded(5, 512, compute)\\n"
-        "sim, s, pr = sc(feats, 1)\\n"
-        "assert torch.equal(rows, torch.cat((s[:, None], pr), 1)), 'sharded != single'\\n"
-        "dist.destroy_process_group(); print('rank', rank, 'ok')\\n")
+    script = ROOT / "tests" / "nccl_worker.py"
     env = dict(os.environ, ACLIP_ROOT=str(ROOT))
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
