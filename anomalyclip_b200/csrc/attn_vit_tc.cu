@@ -13,8 +13,8 @@
 // Every product is issued as hi*hi + lo*hi + hi*lo (Q, K, V arrive as hi/lo planes from the QKV
 // GEMM; P is split by the softmax threads).
 //
-// Roles: warp 0 = TMA producer (Q tiles double buffered, K, V), warp 1 = MMA issuer,
-// warps 2..9 = softmax + output (two warps per TMEM lane quarter, half of the keys each).  TMEM: S0 [0,224) S1 [224,448) O [448,512); the score
+// Roles: warps 0..7 = softmax + output (two warps per TMEM lane quarter, half of the keys each),
+// warp 10 = TMA producer (Q tiles double buffered, K, V), warp 11 = MMA issuer.  TMEM: S0 [0,224) S1 [224,448) O [448,512); the score
 // accumulator is double buffered so that the tensor pipe computes S of tile j+1 and O of tile j-1
 // while the softmax warps work on tile j.
 #include <cuda_bf16.h>
@@ -37,7 +37,10 @@ constexpr int PLO_OFF = S_STRIDE / 2;   // packed lo plane starts here inside a 
 constexpr int MAX_LP = 208 + 16;        // 224 keys at most
 constexpr int Q_PLANE = TILE_Q * 128;   // bytes of one bf16 plane of a Q tile
 constexpr int SOFTMAX_WARPS = 8;
-constexpr int ATT_THREADS = 64 + SOFTMAX_WARPS * 32;
+// warps 0..7 softmax, 8..9 idle (they keep the two single-thread roles off the schedulers of the
+// busiest softmax warps: warp w issues on scheduler w % 4), 10 = TMA producer, 11 = MMA issuer
+constexpr int PRODUCER_WARP = 10, MMA_WARP = 11;
+constexpr int ATT_THREADS = 12 * 32;
 constexpr int HALF_GROUPS = MAX_LP / 32;  // 16-key groups per softmax warp (7)
 
 struct AttnTcParams {
@@ -155,7 +158,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(sum_buf + 4 * TILE_Q);  // [4 quarters][2 planes][32][128 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp == 0 && lane == 0) {
+  if (warp == PRODUCER_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
     ptx::mbar_init(k_full, 1);  ptx::mbar_init(k_empty, 1);
@@ -167,7 +170,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, SOFTMAX_WARPS);
     ptx::fence_mbar_init();
   }
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     ptx::tmem_alloc(tmem_slot, 512);
     ptx::tmem_relinquish();
   }
@@ -180,7 +183,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                        static_cast<int>(gridDim.x);
   const int my_tiles = 2 * my_items;
 
-  if (warp == 0) {
+  if (warp == PRODUCER_WARP) {
     // ------------------------------------------------------------------ TMA producer
     if (lane == 0) {
       for (int it = 0; it < my_items; ++it) {
@@ -200,7 +203,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         ptx::tma_load_3d(sV, &tmKV, v_full, 2 * p.width + h * HD, row0, 0);
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
     if (lane == 0) {
       const uint32_t idesc_qk = ptx::make_idesc_bf16_f32(TILE_Q, p.LP);
@@ -256,10 +259,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         issue_pv(J);
       }
     }
-  } else {
+  } else if (warp < SOFTMAX_WARPS) {
     // ------------------------------------------------------------------ softmax + output warps
     const int quarter = warp & 3;          // TMEM lane quarter this warp may access
-    const int half = (warp - 2) >> 2;      // which half of the keys / of the output columns
+    const int half = warp >> 2;            // which half of the keys / of the output columns
     const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
     const int row_in_tile = quarter * 32 + lane;
     const int groups = p.LP >> 4;          // 16-key groups (13 for L = 197)
@@ -377,7 +380,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
 
   ptx::tc_fence_before();
   __syncthreads();
-  if (warp == 1) {
+  if (warp == MMA_WARP) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, 512);
   }
