@@ -67,6 +67,12 @@ class TemporalWeights(C.Structure):
                [("head_bias", C.c_float)]
 
 
+class PeerGather(C.Structure):
+    _fields_ = [("world", C.c_int), ("rank", C.c_int), ("rows_per_rank", C.c_longlong),
+                ("width", C.c_int), ("rows", vp * 8), ("flags", vp * 8), ("epoch", C.c_uint),
+                ("counter", vp)]
+
+
 class TimingRow(C.Structure):
     _fields_ = [("name", C.c_char * 32), ("launches", C.c_longlong), ("ms", C.c_double),
                 ("flops", C.c_double), ("bytes", C.c_double)]
@@ -98,6 +104,9 @@ SIGNATURES = {
     "aclip_temporal_workspace_bytes": (C.c_size_t, [C.POINTER(TemporalWeights), C.c_longlong]),
     "aclip_temporal_forward": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
                                          vp, vp, vp, C.c_size_t, C.c_int, vp]),
+    "aclip_temporal_forward_ex": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
+                                            vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PeerGather), vp]),
+    "aclip_peer_wait": (C.c_int, [vp, C.c_int, C.c_uint, vp]),
 }
 
 _lib = None

@@ -91,66 +91,115 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
   }
 }
 
+struct PeerDev {            // device-side copy of AclipPeerGather for one head launch
+  int world, rank, width, signal;
+  long long rows_per_rank;
+  float* rows[8];
+  unsigned int* flags[8];
+  unsigned int epoch;
+  unsigned int* counter;
+};
+
 // One warp per grid row (sub-video order).  E <= 256.
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 head_kernel(const float* __restrict__ x1, const float* __restrict__ x2, long long rows, int E,
             const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
             const float* __restrict__ w, float bias, const float* __restrict__ sim, int ld_sim,
             int ncls, RowMap map, float* __restrict__ scores, float* __restrict__ sim_out,
-            float* __restrict__ probs_out) {
+            float* __restrict__ probs_out, PeerDev pg) {
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int nvec = E >> 2;
-  float4 v[2];
-  float s = 0.f;
+  if (row < rows) {
+    const int nvec = E >> 2;
+    float4 v[2];
+    float s = 0.f;
 #pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      const float4 a = reinterpret_cast<const float4*>(x1 + row * E)[c];
-      const float4 b = reinterpret_cast<const float4*>(x2 + row * E)[c];
-      // torch.stack(x.chunk(2, dim=1)).mean(dim=0): (a + b) / 2
-      v[i] = make_float4((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f,
-                         (a.w + b.w) * 0.5f);
-      s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 a = reinterpret_cast<const float4*>(x1 + row * E)[c];
+        const float4 b = reinterpret_cast<const float4*>(x2 + row * E)[c];
+        // torch.stack(x.chunk(2, dim=1)).mean(dim=0): (a + b) / 2
+        v[i] = make_float4((a.x + b.x) * 0.5f, (a.y + b.y) * 0.5f, (a.z + b.z) * 0.5f,
+                           (a.w + b.w) * 0.5f);
+        s += (v[i].x + v[i].y) + (v[i].z + v[i].w);
+      }
+    }
+    const float mean = warp_sum(s) / static_cast<float>(E);
+    float q = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
+        q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+      }
+    }
+    const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(E) + eps);
+    float dot = 0.f;
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int c = lane + i * 32;
+      if (c < nvec) {
+        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
+        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
+        const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
+        dot += (v[i].x * rstd * g.x + b.x) * ww.x + (v[i].y * rstd * g.y + b.y) * ww.y +
+               (v[i].z * rstd * g.z + b.z) * ww.z + (v[i].w * rstd * g.w + b.w) * ww.w;
+      }
+    }
+    const float z = warp_sum(dot) + bias;
+    const float score = 1.0f / (1.0f + expf(-z));  // nn.Sigmoid (classification_head.py:14)
+    const long long orow = map.caller_row(row);
+    // softmax(similarity, dim=1) * score     (anomaly_clip_module.py:473-477)
+    const float sv = lane < ncls ? sim[row * ld_sim + lane] : -INFINITY;
+    const float mx = warp_max(sv);
+    const float e = lane < ncls ? expf(sv - mx) : 0.f;
+    const float den = warp_sum(e);
+    const float prob = (e / den) * score;
+    if (lane == 0) scores[orow] = score;
+    if (lane < ncls) {
+      if (sim_out != nullptr) sim_out[orow * ncls + lane] = sv;
+      if (probs_out != nullptr) probs_out[orow * ncls + lane] = prob;
+    }
+    if (pg.world > 0) {
+      // fused all-gather: row [score | class_probs] straight into every rank's gathered buffer
+      // (peer-mapped memory over NVLink; the local rank is just another entry of the table)
+      const float shifted = __shfl_up_sync(0xffffffffu, prob, 1);
+      const float val = lane == 0 ? score : shifted;
+      if (lane < pg.width) {
+        const long long dst = (pg.rank * pg.rows_per_rank + orow) * pg.width + lane;
+#pragma unroll 1
+        for (int r = 0; r < pg.world; ++r) pg.rows[r][dst] = val;
+      }
     }
   }
-  const float mean = warp_sum(s) / static_cast<float>(E);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      v[i].x -= mean; v[i].y -= mean; v[i].z -= mean; v[i].w -= mean;
-      q += (v[i].x * v[i].x + v[i].y * v[i].y) + (v[i].z * v[i].z + v[i].w * v[i].w);
+  if (pg.world > 0 && pg.signal) {
+    // publish: every CTA makes its peer stores visible system-wide, the last one raises the flags
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      const unsigned int done = atomicAdd(pg.counter, 1u);
+      if (done == gridDim.x - 1) {
+        *pg.counter = 0u;  // ready for the next launch
+        __threadfence_system();
+        for (int r = 0; r < pg.world; ++r)
+          asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pg.flags[r] + pg.rank), "r"(pg.epoch)
+                       : "memory");
+      }
     }
   }
-  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(E) + eps);
-  float dot = 0.f;
-#pragma unroll
-  for (int i = 0; i < 2; ++i) {
-    const int c = lane + i * 32;
-    if (c < nvec) {
-      const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + c);
-      const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + c);
-      const float4 ww = __ldg(reinterpret_cast<const float4*>(w) + c);
-      dot += (v[i].x * rstd * g.x + b.x) * ww.x + (v[i].y * rstd * g.y + b.y) * ww.y +
-             (v[i].z * rstd * g.z + b.z) * ww.z + (v[i].w * rstd * g.w + b.w) * ww.w;
-    }
-  }
-  const float z = warp_sum(dot) + bias;
-  const float score = 1.0f / (1.0f + expf(-z));  // nn.Sigmoid (classification_head.py:14)
-  const long long orow = map.caller_row(row);
-  // softmax(similarity, dim=1) * score     (anomaly_clip_module.py:473-477)
-  const float sv = lane < ncls ? sim[row * ld_sim + lane] : -INFINITY;
-  const float mx = warp_max(sv);
-  const float e = lane < ncls ? expf(sv - mx) : 0.f;
-  const float den = warp_sum(e);
-  if (lane == 0) scores[orow] = score;
-  if (lane < ncls) {
-    if (sim_out != nullptr) sim_out[orow * ncls + lane] = sv;
-    if (probs_out != nullptr) probs_out[orow * ncls + lane] = (e / den) * score;
+}
+
+// Stream-side wait of the fused gather: spin until every rank's flag has reached `epoch`.
+__global__ void peer_wait_kernel(const unsigned int* __restrict__ flags, int world, unsigned int epoch) {
+  const int r = threadIdx.x;
+  if (r < world) {
+    unsigned int v;
+    do {
+      asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
+      if (static_cast<int>(v - epoch) < 0) __nanosleep(200);
+    } while (static_cast<int>(v - epoch) < 0);
   }
 }
 
@@ -186,17 +235,40 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
 int score_head(const float* x1, const float* x2, long long rows, int E, const float* gamma,
                const float* beta, float eps, const float* w, float bias, const float* sim,
                int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
-               float* probs_out, cudaStream_t stream) {
+               float* probs_out, const AclipPeerGather* gather, int signal, cudaStream_t stream) {
   ACLIP_REQUIRE(x1 && x2 && gamma && beta && w && sim && scores, "score_head: null pointer");
   ACLIP_REQUIRE(E % 4 == 0 && E <= 256, "score_head: E=%d unsupported", E);
   ACLIP_REQUIRE(ncls >= 1 && ncls <= 32 && ld_sim >= ncls, "score_head: ncls=%d unsupported", ncls);
   if (rows <= 0) return ACLIP_OK;
+  PeerDev pg{};
+  if (gather != nullptr) {
+    ACLIP_REQUIRE(gather->world >= 1 && gather->world <= 8 && gather->rank >= 0 &&
+                      gather->rank < gather->world && gather->width == ncls + 1 && gather->width <= 32 &&
+                      gather->epoch > 0 && gather->counter != nullptr,
+                  "score_head: bad peer-gather descriptor");
+    pg.world = gather->world; pg.rank = gather->rank; pg.width = gather->width;
+    pg.signal = signal; pg.rows_per_rank = gather->rows_per_rank;
+    pg.epoch = gather->epoch; pg.counter = gather->counter;
+    for (int r = 0; r < gather->world; ++r) {
+      ACLIP_REQUIRE(gather->rows[r] && gather->flags[r], "score_head: null peer pointer %d", r);
+      pg.rows[r] = gather->rows[r];
+      pg.flags[r] = gather->flags[r];
+    }
+  }
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   timing_begin(KIND_SCORE_HEAD, stream);
   head_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(x1, x2, rows, E, gamma, beta, eps, w, bias,
                                                       sim, ld_sim, ncls, map, scores, sim_out,
-                                                      probs_out);
+                                                      probs_out, pg);
   timing_end(KIND_SCORE_HEAD, stream, 12.0 * rows * E, (double)rows * (8.0 * E + 4.0 * ld_sim + 4.0 + 8.0 * ncls));
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
+int peer_wait(const unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream) {
+  ACLIP_REQUIRE(local_flags != nullptr && world >= 1 && world <= 8 && epoch > 0, "peer_wait: bad arguments");
+  peer_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -210,4 +282,9 @@ extern "C" int aclip_layernorm(const float* x, long long rows, int D, long long 
                                long long ld_split, long long plane_stride, void* stream) {
   return aclip::layernorm(x, rows, D, ldx, gamma, beta, eps, mode, out_f32, ld_f32, out_split,
                           ld_split, plane_stride, aclip::as_stream(stream));
+}
+
+extern "C" int aclip_peer_wait(const unsigned int* local_flags, int world, unsigned int epoch,
+                               void* stream) {
+  return aclip::peer_wait(local_flags, world, epoch, aclip::as_stream(stream));
 }

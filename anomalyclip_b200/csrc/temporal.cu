@@ -92,6 +92,17 @@ extern "C" int aclip_temporal_forward(const AclipTemporalWeights* wp, const floa
                                       float* similarity_out, float* scores_out,
                                       float* class_probs_out, void* workspace,
                                       size_t workspace_bytes, int passes, void* stream_) {
+  return aclip_temporal_forward_ex(wp, features, sub_videos, segment_size, similarity_out,
+                                   scores_out, class_probs_out, workspace, workspace_bytes, passes,
+                                   nullptr, stream_);
+}
+
+extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const float* features,
+                                         long long sub_videos, int segment_size,
+                                         float* similarity_out, float* scores_out,
+                                         float* class_probs_out, void* workspace,
+                                         size_t workspace_bytes, int passes,
+                                         const AclipPeerGather* gather, void* stream_) {
   using namespace aclip;
   ACLIP_REQUIRE(wp != nullptr, "temporal_forward: weights are NULL");
   const AclipTemporalWeights& w = *wp;
@@ -102,6 +113,10 @@ extern "C" int aclip_temporal_forward(const AclipTemporalWeights* wp, const floa
                 sub_videos, segment_size);
   ACLIP_REQUIRE(passes == 1 || passes == 3, "temporal_forward: passes must be 1 or 3");
   if (sub_videos == 0) return ACLIP_OK;
+  ACLIP_REQUIRE(gather == nullptr ||
+                    gather->rows_per_rank == sub_videos * w.num_segments * w.seg_length,
+                "temporal_forward: peer gather expects %lld rows per rank",
+                gather ? gather->rows_per_rank : 0ll);
   ACLIP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) == 0,
                 "temporal_forward: workspace must be 1024-byte aligned");
   // largest chunk of sub-videos the workspace can hold
@@ -207,7 +222,7 @@ extern "C" int aclip_temporal_forward(const AclipTemporalWeights* wp, const floa
     }
     ACLIP_TRY(score_head(x1, P, rows, E, w.head_ln_g, w.head_ln_b, 1e-5f, w.head_w, w.head_bias,
                          SIM, 32, w.num_dirs, map, scores_out, similarity_out, class_probs_out,
-                         stream));
+                         gather, u0 + cs >= sub_videos ? 1 : 0, stream));
   }
   return ACLIP_OK;
 }

@@ -92,3 +92,63 @@ def sharded_mean(local_sum: torch.Tensor, local_count: int,
     if dist.is_available() and dist.is_initialized():
         dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
     return (packed[:-1] / packed[-1].clamp_min(1.0)).to(torch.float32).reshape(local_sum.shape)
+
+
+class PeerRowGather:
+    """Fused all-gather of the per-frame result rows over NVLink peer memory.
+
+    Every rank owns a symmetric buffer (torch.distributed._symmetric_memory: the allocation is
+    mapped into every peer of the group) holding two parity copies of the gathered rows
+    [world * rows_per_rank, width] and a flag word per rank.  `TemporalScorer(..., peer=self)`
+    makes the head kernel store each row it computes into ALL ranks' buffers and raise the flags
+    from its last CTA; `wait()` enqueues a one-warp kernel that holds the STREAM until every rank's
+    flag arrived, and returns the gathered rows -- no NCCL call, no host synchronisation.
+
+    Double buffering by call parity plus stream-ordered consumption keeps a fast rank from
+    overwriting rows a slow rank is still reading: a rank can be at most one call ahead, because
+    its next-but-one call needs this rank's flag of the call in between."""
+
+    def __init__(self, rows_per_rank: int, width: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None) -> None:
+        import torch.distributed._symmetric_memory as symm_mem
+
+        from . import _lib
+        self._lib = _lib
+        group = group if group is not None else dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise ValueError("PeerRowGather supports up to 8 ranks (one NVSwitch domain)")
+        self.rows_per_rank, self.width, self.device = rows_per_rank, width, device
+        self.block = self.world * rows_per_rank * width             # floats per parity copy
+        self.buf = symm_mem.empty(2 * self.block + 64, dtype=torch.float32, device=device)
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group.group_name)
+        self.counter = torch.zeros(1, dtype=torch.int32, device=device)
+        self.epoch = 0
+        torch.cuda.synchronize(device)
+        dist.barrier(group)                                          # all buffers zeroed and mapped
+
+    def descriptor(self, n_rows: int, width: int):
+        if n_rows != self.rows_per_rank or width != self.width:
+            raise ValueError("PeerRowGather: shape differs from the one it was built for")
+        self.epoch += 1
+        g = self._lib.PeerGather()
+        g.world, g.rank, g.rows_per_rank, g.width = self.world, self.rank, self.rows_per_rank, self.width
+        parity = self.epoch & 1
+        for r in range(self.world):
+            base = int(self.handle.buffer_ptrs[r])
+            g.rows[r] = base + 4 * parity * self.block
+            g.flags[r] = base + 4 * 2 * self.block
+        g.epoch = self.epoch
+        g.counter = self.counter.data_ptr()
+        return g
+
+    def wait(self) -> torch.Tensor:
+        """Gathered rows [world * rows_per_rank, width] of the latest call (a view of the local
+        symmetric buffer, valid until the call after next)."""
+        lib = self._lib.load()
+        self._lib.check(lib.aclip_peer_wait(self.buf.data_ptr() + 4 * 2 * self.block, self.world,
+                                            self.epoch, torch.cuda.current_stream(self.device).cuda_stream))
+        parity = self.epoch & 1
+        return self.buf[parity * self.block:(parity + 1) * self.block].view(
+            self.world * self.rows_per_rank, self.width)

@@ -261,7 +261,10 @@ class TemporalScorer:
         self.max_chunk = max_chunk_sub_videos
         self._ws = _Workspace()
 
-    def __call__(self, features: torch.Tensor, segment_size: int = 1, want_probs: bool = True):
+    def __call__(self, features: torch.Tensor, segment_size: int = 1, want_probs: bool = True,
+                 peer=None):
+        """peer: optional `distributed.PeerRowGather`; the head kernel then also stores the rows
+        [score | class_probs] into every rank's gathered buffer (fused all-gather over NVLink)."""
         p = self.packed
         if p.struct.selector_w is None:
             raise _lib.AclipError("TemporalScorer: set_directions() has not been called")
@@ -282,8 +285,10 @@ class TemporalScorer:
         chunk = max(1, min(sub_videos, self.max_chunk))
         nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), chunk)
         ws = self._ws.get(nbytes, dev)
-        _lib.check(lib.aclip_temporal_forward(
+        gather = peer.descriptor(n_rows, p.num_dirs + 1) if peer is not None else None
+        _lib.check(lib.aclip_temporal_forward_ex(
             C.byref(p.struct), feats.data_ptr(), sub_videos, segment_size, sim.data_ptr(),
             scores.data_ptr(), probs.data_ptr() if probs is not None else None, ws, nbytes,
-            self.passes, torch.cuda.current_stream().cuda_stream))
+            self.passes, C.byref(gather) if gather is not None else None,
+            torch.cuda.current_stream().cuda_stream))
         return sim, scores, probs

@@ -356,6 +356,9 @@ class AnomalyCLIP(nn.Module):
         self._scorer: Optional[engine.TemporalScorer] = None
         self._scorer_key = None
         self.class_probs: Optional[torch.Tensor] = None  # softmax(similarity)*score of the last call
+        # optional distributed.PeerRowGather: the head kernel then also all-gathers the rows
+        # [score | class_probs] of every rank over NVLink peer memory (read them with .wait())
+        self.peer_gather = None
 
     # ---- text directions: a per-checkpoint constant, computed once (the reference recomputes it
     # on every forward, anomaly_clip.py:136,217-221)
@@ -410,7 +413,7 @@ class AnomalyCLIP(nn.Module):
         if text.device != dev:  # keep the cached constant on the compute device
             text = self._text_features = text.to(dev)
         scorer.packed.set_directions(text, ncentroid.to(dev))
-        similarity, scores, probs = scorer(rows.to(torch.float32), segment_size)
+        similarity, scores, probs = scorer(rows.to(torch.float32), segment_size, peer=self.peer_gather)
         if self.stride != 1:                                                    # :149-150
             similarity = similarity.repeat_interleave(self.stride, dim=0)
             scores = scores.repeat_interleave(self.stride, dim=0)

@@ -42,7 +42,7 @@ def _workload_config(n_gpus: int, micro_batch: int = 256) -> dict:
         "vit_micro_batch": micro_batch,
         "precision": "split-bf16 x3 tensor-core passes, fp32 accumulate (parity mode)",
         "l2": "inputs rotate over 4 frame buffers (308 MB) and activations are ~0.9 GB per micro-batch, both > 126 MB L2",
-        "parallelism": f"dp{n_gpus} over sub-videos, one all-gather of score rows per step",
+        "parallelism": f"dp{n_gpus} over sub-videos, one exchange of score rows per step",
     }
 
 
@@ -197,14 +197,35 @@ def run_b200(args) -> None:
     module = AnomalyCLIPModule(net, num_classes=cfg.num_classes)
     module.ncentroid = syn.make_ncentroid(cfg).to(dev)
 
+    width = cfg.num_classes  # [score | class_probs(C-1)]
     n_buf = 4
     host = [syn.make_frames_u8(FRAMES_PER_STEP, seed=100 * rank + i).unsqueeze(0).pin_memory()
             for i in range(n_buf)]
     resident = [h.to(dev) for h in host]
     labels = torch.zeros(1, FRAMES_PER_STEP, dtype=torch.long)
-    width = cfg.num_classes  # [score | class_probs(C-1)]
+
+    # N > 1: the per-frame rows [score | class_probs] of all ranks are exchanged once per step.
+    # Preferred transport: the head kernel stores them straight into every rank's buffer over
+    # NVLink peer memory (fused all-gather, PeerRowGather); if symmetric memory cannot be set up
+    # on this box the same rows go through one NCCL all-gather instead.
+    peer, transport = None, "none (1 GPU)"
+    if world > 1:
+        try:
+            from anomalyclip_b200.distributed import PeerRowGather
+            peer = PeerRowGather(FRAMES_PER_STEP, width, dev)
+            net.peer_gather = peer
+            transport = "fused into the head kernel over NVLink peer memory (symmetric memory)"
+        except Exception as exc:  # noqa: BLE001
+            print(f"bench.py: peer gather unavailable ({exc!r}); using NCCL all-gather", file=sys.stderr)
+            peer, transport = None, "NCCL all-gather"
+        ok = torch.tensor([1 if peer is not None else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)          # all ranks must agree on the transport
+        if int(ok.item()) == 0:
+            peer, net.peer_gather, transport = None, None, "NCCL all-gather"
 
     def exchange(scores, probs):
+        if peer is not None:
+            return peer.wait()
         rows = torch.cat((scores.unsqueeze(1), probs), dim=1)
         if world > 1:
             rows = gather_rows(rows, [FRAMES_PER_STEP] * world)
@@ -329,7 +350,7 @@ def run_b200(args) -> None:
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16x3-split operands, f32 accumulate/residual", "data": "synthetic",
-            "config": _workload_config(n_gpus, args.micro_batch), "clocks": clocks,
+            "config": dict(_workload_config(n_gpus, args.micro_batch), exchange=transport), "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 3 * 224 * 224,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * width * 4 * n_gpus},

@@ -204,6 +204,26 @@ typedef struct AclipTemporalWeights { /* SelectorModel (test branch) + TemporalM
 
 size_t aclip_temporal_workspace_bytes(const AclipTemporalWeights* w, long long sub_videos);
 
+/* Optional fused all-gather of the result rows over NVLink peer memory (one process per GPU).
+ * Every rank owns a buffer rows[world * rows_per_rank][width] (width = 1 + num_dirs: score, then
+ * the class probabilities) and a flag array flags[world], both mapped into every peer (e.g. with
+ * torch.distributed._symmetric_memory).  The head kernel of aclip_temporal_forward_ex stores each
+ * of its rows into ALL peers' buffers at row (rank * rows_per_rank + r) while it computes them,
+ * and its last CTA publishes flags[rank] = epoch on every peer (system-scope release).
+ * aclip_peer_wait then blocks the STREAM (not the host) until all `world` flags of the local array
+ * have reached `epoch`.  This replaces the NCCL all-gather of per-frame scores. */
+typedef struct AclipPeerGather {
+  int world, rank;
+  long long rows_per_rank;
+  int width;
+  float* rows[8];            /* peer-mapped base of each rank's gathered buffer (index = peer rank) */
+  unsigned int* flags[8];    /* peer-mapped flag arrays [world] */
+  unsigned int epoch;        /* > 0, increasing by one per call on every rank */
+  unsigned int* counter;     /* LOCAL zero-initialised device word (CTA completion counter) */
+} AclipPeerGather;
+
+int aclip_peer_wait(const unsigned int* local_flags, int world, unsigned int epoch, void* stream);
+
 /* AnomalyCLIP.forward(test_mode=True) after the image encoder (anomaly_clip.py:132-154) fused with
  * test_step's softmax(similarity) * score (anomaly_clip_module.py:473-477).
  * features: fp32 [N][feature_dim], rows in the caller's "(b n s l)" order, N = sub_videos*n*l with
@@ -214,6 +234,12 @@ int aclip_temporal_forward(const AclipTemporalWeights* w, const float* features,
                            long long sub_videos, int segment_size, float* similarity_out,
                            float* scores_out, float* class_probs_out, void* workspace,
                            size_t workspace_bytes, int passes, void* stream);
+/* Same, with the fused peer all-gather (gather may be NULL). */
+int aclip_temporal_forward_ex(const AclipTemporalWeights* w, const float* features,
+                              long long sub_videos, int segment_size, float* similarity_out,
+                              float* scores_out, float* class_probs_out, void* workspace,
+                              size_t workspace_bytes, int passes, const AclipPeerGather* gather,
+                              void* stream);
 
 #ifdef __cplusplus
 }

@@ -33,6 +33,19 @@ def main():
     rows = run_sharded(units, cfg.unit, compute)
     sim, s, pr = scorer(feats, 1)
     assert torch.equal(rows, torch.cat((s[:, None], pr), 1)), "sharded result differs from single-rank"
+
+    # fused all-gather over NVLink peer memory: the head kernel stores the rows into every rank's
+    # buffer; compare with the NCCL all-gather of the same rows over several calls (both parities)
+    from anomalyclip_b200.distributed import PeerRowGather, gather_rows
+    world = dist.get_world_size()
+    per_rank = 2 * cfg.unit
+    peer = PeerRowGather(per_rank, cfg.num_classes, dev)
+    for it in range(5):
+        mine = syn.make_features(cfg, 2, seed=50 + 10 * it + rank).reshape(-1, 512).to(dev)
+        sim, s, pr = scorer(mine, 1, peer=peer)
+        fused = peer.wait().clone()
+        ref = gather_rows(torch.cat((s[:, None], pr), 1), [per_rank] * world)
+        assert torch.equal(fused, ref), f"fused peer gather differs from NCCL at call {it}"
     dist.destroy_process_group()
     print("rank", rank, "ok")
 
