@@ -89,6 +89,43 @@ __device__ __forceinline__ void mma_bf16_ts(uint32_t d_tmem, uint32_t a_tmem, ui
       "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a CONVERGED issuing warp: every lane runs the (warp-uniform) control flow
+// and address arithmetic, so the compiler keeps descriptors in uniform registers; only the lane
+// with `issue` set executes the instruction.
+__device__ __forceinline__ void mma_ss_if(bool issue, uint32_t d_tmem, uint64_t a_desc,
+                                          uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
+__device__ __forceinline__ void mma_ts_if(bool issue, uint32_t d_tmem, uint32_t a_tmem,
+                                          uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], [%1], %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "r"(a_tmem), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
+__device__ __forceinline__ void commit_if(bool issue, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(ptx::smem_u32(bar)),
+      "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
 // MN-major operand stored as rows of 128 bytes (64 bf16 along MN) with the 128-byte swizzle:
 // K advances by one row (128 B), groups of 8 K rows are SBO = 1024 B apart.
 __device__ __forceinline__ uint64_t make_mnmajor_sw128_desc(uint32_t smem_addr) {
@@ -205,11 +242,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     }
   } else if (warp == MMA_WARP) {
     // ------------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The whole warp stays converged; one elected lane issues (see mma_ss_if).
+    {
+      const bool leader = ptx::elect_one();
       const uint32_t idesc_qk = ptx::make_idesc_bf16_f32(TILE_Q, p.LP);
       const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(TILE_Q, HD) | (1u << 16);  // B is MN-major
       const uint32_t k_base = ptx::smem_u32(sK), v_base = ptx::smem_u32(sV);
       const int ksteps = p.LP >> 4;
+      // descriptors advance by a constant in their low word: +2 (32 bytes >> 4) per 16-wide K step
+      // of a K-major operand, +128 (2048 bytes >> 4) per 16 keys of the MN-major V operand
+      const uint64_t kd_hi = ptx::make_kmajor_sw128_desc(k_base);
+      const uint64_t kd_lo = ptx::make_kmajor_sw128_desc(k_base + kv_plane);
+      const uint64_t vd_hi = make_mnmajor_sw128_desc(v_base);
+      const uint64_t vd_lo = make_mnmajor_sw128_desc(v_base + kv_plane);
 
       auto issue_qk = [&](int J) {  // S[J % 2] = Q_J K^T
         const int it = J >> 1, q = J & 1;
@@ -218,20 +263,17 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + q * S_STRIDE;
         const uint32_t q_base = ptx::smem_u32(sQ + q * 2 * Q_PLANE);
+        const uint64_t qd_hi = ptx::make_kmajor_sw128_desc(q_base);
+        const uint64_t qd_lo = ptx::make_kmajor_sw128_desc(q_base + Q_PLANE);
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
-          const uint32_t koff = k * 32;
-          const uint64_t a_hi = ptx::make_kmajor_sw128_desc(q_base + koff);
-          const uint64_t a_lo = ptx::make_kmajor_sw128_desc(q_base + Q_PLANE + koff);
-          const uint64_t b_hi = ptx::make_kmajor_sw128_desc(k_base + koff);
-          const uint64_t b_lo = ptx::make_kmajor_sw128_desc(k_base + kv_plane + koff);
-          ptx::mma_bf16_ss(d, a_hi, b_hi, idesc_qk, k != 0 ? 1u : 0u);
-          ptx::mma_bf16_ss(d, a_lo, b_hi, idesc_qk, 1u);
-          ptx::mma_bf16_ss(d, a_hi, b_lo, idesc_qk, 1u);
+          mma_ss_if(leader, d, qd_hi + 2 * k, kd_hi + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
+          mma_ss_if(leader, d, qd_lo + 2 * k, kd_hi + 2 * k, idesc_qk, 1u);
+          mma_ss_if(leader, d, qd_hi + 2 * k, kd_lo + 2 * k, idesc_qk, 1u);
         }
-        ptx::mma_commit(&s_full[q]);
-        ptx::mma_commit(&q_empty[q]);
-        if (q == 1) ptx::mma_commit(k_empty);
+        commit_if(leader, &s_full[q]);
+        commit_if(leader, &q_empty[q]);
+        if (q == 1) commit_if(leader, k_empty);
       };
       auto issue_pv = [&](int J) {  // O = P_J V
         const int it = J >> 1, q = J & 1;
@@ -242,15 +284,14 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         const uint32_t d = tmem_base + O_COL;
         const uint32_t a_hi0 = tmem_base + q * S_STRIDE;
         const uint32_t a_lo0 = a_hi0 + PLO_OFF;
+#pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
-          const uint64_t b_hi = make_mnmajor_sw128_desc(v_base + k * 2048);
-          const uint64_t b_lo = make_mnmajor_sw128_desc(v_base + kv_plane + k * 2048);
-          mma_bf16_ts(d, a_hi0 + 8 * k, b_hi, idesc_pv, k != 0 ? 1u : 0u);
-          mma_bf16_ts(d, a_lo0 + 8 * k, b_hi, idesc_pv, 1u);
-          mma_bf16_ts(d, a_hi0 + 8 * k, b_lo, idesc_pv, 1u);
+          mma_ts_if(leader, d, a_hi0 + 8 * k, vd_hi + 128 * k, idesc_pv, k != 0 ? 1u : 0u);
+          mma_ts_if(leader, d, a_lo0 + 8 * k, vd_hi + 128 * k, idesc_pv, 1u);
+          mma_ts_if(leader, d, a_hi0 + 8 * k, vd_lo + 128 * k, idesc_pv, 1u);
         }
-        ptx::mma_commit(o_full);
-        if (q == 1) ptx::mma_commit(v_empty);
+        commit_if(leader, o_full);
+        if (q == 1) commit_if(leader, v_empty);
       };
 
       if (my_tiles > 0) issue_qk(0);
