@@ -428,8 +428,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer (leader CTA only)
-    if (rank == 0 && lane == 0) {
+    // The warp stays converged; one elected lane issues (descriptors in uniform registers).
+    if (rank == 0) {
+      const bool leader = ptx::elect_one();
       constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
+      const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -439,25 +442,22 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          // descriptor low word counts 16-byte units: stage / plane / K-step offsets are adds
+          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-            const uint32_t koff = k * Cfg::UMMA_K * 2;
-            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a_base + koff);
-            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b_base + koff);
-            ptx::mma_bf16_ss_pair(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
+            ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (PASSES == 3) {
-              const uint64_t a_lo = ptx::make_kmajor_sw128_desc(a_base + Cfg::A_PLANE_BYTES + koff);
-              const uint64_t b_lo = ptx::make_kmajor_sw128_desc(b_base + Cfg::B_PLANE_BYTES + koff);
-              ptx::mma_bf16_ss_pair(d_tmem, a_lo, b_hi, idesc, 1u);
-              ptx::mma_bf16_ss_pair(d_tmem, a_hi, b_lo, idesc, 1u);
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
             }
           }
-          ptx::mma_commit_pair(&empty_bar[stage], 0x3);  // frees the slot in both CTAs
+          ptx::mma_commit_pair_if(leader, &empty_bar[stage], 0x3);  // frees the slot in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit_pair(&tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
+        ptx::mma_commit_pair_if(leader, &tfull_bar[acc], 0x3);  // accumulator complete -> both epilogues
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -217,6 +217,32 @@ __device__ __forceinline__ void mma_bf16_ss_pair(uint32_t d_tmem, uint64_t a_des
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a converged issuing warp (all lanes run the warp-uniform control flow, the
+// lane with `issue` set executes the instruction; descriptors then live in uniform registers).
+__device__ __forceinline__ void mma_bf16_ss_pair_if(bool issue, uint32_t d_tmem, uint64_t a_desc,
+                                                    uint64_t b_desc, uint32_t idesc,
+                                                    uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_pair_if(bool issue, uint64_t* bar, uint16_t cta_mask) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+      " [%0], %1;\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "h"(cta_mask), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
 // Arrive (once every previously issued MMA of this thread has retired) on the barrier at this
 // offset in every CTA of `cta_mask`.
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar, uint16_t cta_mask) {
