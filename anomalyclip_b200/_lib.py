@@ -90,6 +90,8 @@ SIGNATURES = {
                                        C.c_int, C.c_longlong, vp]),
     "aclip_patchify": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
                                  C.POINTER(C.c_float), vp, C.c_longlong, vp]),
+    "aclip_resize_crop_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
+                                       C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "aclip_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "aclip_layernorm": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_longlong, vp, vp, C.c_float,
                                   C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp]),

@@ -11,7 +11,7 @@ namespace {
 
 const char* const kKindNames[KIND_COUNT] = {"gemm_tcgen05", "vit_attention", "layernorm", "patchify",
                                             "cls_rows", "center_regroup", "axial_attention",
-                                            "score_head", "split"};
+                                            "score_head", "split", "resize_crop"};
 struct Sample { int kind; cudaEvent_t a, b; double flops, bytes; };
 std::atomic<int> g_timing_on{0};
 std::mutex g_timing_mu;

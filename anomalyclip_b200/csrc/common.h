@@ -74,7 +74,7 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
 // for the roofline numbers.  Off by default; when off the cost is one relaxed atomic load.
 enum KernelKind : int {
   KIND_GEMM = 0, KIND_VIT_ATTENTION, KIND_LAYERNORM, KIND_PATCHIFY, KIND_CLS_ROWS,
-  KIND_CENTER_REGROUP, KIND_AXIAL_ATTENTION, KIND_SCORE_HEAD, KIND_SPLIT, KIND_COUNT
+  KIND_CENTER_REGROUP, KIND_AXIAL_ATTENTION, KIND_SCORE_HEAD, KIND_SPLIT, KIND_RESIZE, KIND_COUNT
 };
 void timing_begin(int kind, cudaStream_t stream);
 void timing_end(int kind, cudaStream_t stream, double flops, double bytes);

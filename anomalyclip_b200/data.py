@@ -159,3 +159,128 @@ class DevicePrefetcher:
             done = torch.cuda.Event()      # everything the consumer enqueued on batch cur_k
             done.record(compute)
             self._consumed[cur_k] = done
+
+
+# --------------------------------------------------------------------------------------------
+# GPU-side frame ingest: PIL-exact bicubic resize + centre crop plan
+# --------------------------------------------------------------------------------------------
+_PRECISION_BITS = 32 - 8 - 2   # Pillow, libImaging/Resample.c (8 bits per channel)
+
+
+def _bicubic(x: float) -> float:
+    a = -0.5
+    if x < 0.0:
+        x = -x
+    if x < 1.0:
+        return ((a + 2.0) * x - (a + 3.0)) * x * x + 1
+    if x < 2.0:
+        return (((x - 5) * x + 8) * x - 4) * a
+    return 0.0
+
+
+def pil_resample_plan(in_size: int, out_size: int, first: int = 0, count: Optional[int] = None):
+    """Pillow's `precompute_coeffs` + `normalize_coeffs_8bpc` for the bicubic filter over the full
+    input extent: for output samples [first, first+count) the first input index, the tap count
+    and the fixed-point (22-bit) taps.  Returns (bounds int32 [count, 2], coeffs int32 [count, ksize])."""
+    count = out_size - first if count is None else count
+    scale = filterscale = in_size / out_size
+    if filterscale < 1.0:
+        filterscale = 1.0
+    support = 2.0 * filterscale
+    ksize = int(math.ceil(support)) * 2 + 1
+    bounds = np.zeros((count, 2), dtype=np.int32)
+    coeffs = np.zeros((count, ksize), dtype=np.int32)
+    ss = 1.0 / filterscale
+    for i in range(count):
+        xx = first + i
+        center = (xx + 0.5) * scale
+        xmin = int(center - support + 0.5)
+        if xmin < 0:
+            xmin = 0
+        xmax = int(center + support + 0.5)
+        if xmax > in_size:
+            xmax = in_size
+        xmax -= xmin
+        k = [_bicubic((x + xmin - center + 0.5) * ss) for x in range(xmax)]
+        ww = 0.0
+        for w in k:
+            ww += w
+        if ww != 0.0:
+            k = [w / ww for w in k]
+        for x, w in enumerate(k):
+            coeffs[i, x] = int(-0.5 + w * (1 << _PRECISION_BITS)) if w < 0 else int(0.5 + w * (1 << _PRECISION_BITS))
+        bounds[i] = (xmin, xmax)
+    return bounds, coeffs
+
+
+@dataclass
+class ResizeCropPlan:
+    """Everything `aclip_resize_crop_u8` needs for frames of one source size: the reference's
+    GroupScale(size, BICUBIC) + GroupCenterCrop(size) (src/utils/augmentations.py:25-29) restricted
+    to the pixels the crop keeps."""
+    in_h: int
+    in_w: int
+    size: int
+    row0: int                 # first source row the vertical pass reads
+    rows: int                 # number of source rows it reads (height of the intermediate image)
+    hbounds: np.ndarray
+    hcoeffs: np.ndarray
+    vbounds: np.ndarray       # relative to row0
+    vcoeffs: np.ndarray
+
+
+def resize_crop_plan(in_h: int, in_w: int, size: int = 224) -> ResizeCropPlan:
+    # torchvision.transforms.Resize(int): the smaller edge becomes `size`
+    if in_w <= in_h:
+        out_w, out_h = size, int(size * in_h / in_w)
+    else:
+        out_h, out_w = size, int(size * in_w / in_h)
+    # torchvision center_crop
+    top = int(round((out_h - size) / 2.0))
+    left = int(round((out_w - size) / 2.0))
+    hb, hc = pil_resample_plan(in_w, out_w, left, size)
+    vb, vc = pil_resample_plan(in_h, out_h, top, size)
+    row0 = int(vb[:, 0].min())
+    rows = int((vb[:, 0] + vb[:, 1]).max()) - row0
+    vb = vb.copy()
+    vb[:, 0] -= row0
+    return ResizeCropPlan(in_h, in_w, size, row0, rows, hb, hc, vb, vc)
+
+
+class GpuFrameIngest:
+    """Decoded uint8 frames (F, H, W, 3) on the device -> (F, 3, size, size) uint8, bit-exact with
+    the reference's PIL resize + centre crop; feed the result to the image encoder (which
+    normalises uint8 frames on the fly).  One plan per source resolution."""
+
+    def __init__(self, in_h: int, in_w: int, device: torch.device, size: int = 224) -> None:
+        from . import _lib
+        self._lib = _lib
+        if device.type != "cuda":
+            raise _lib.AclipError("GpuFrameIngest runs only on a CUDA device (no CPU fallback)")
+        self.plan, self.device = resize_crop_plan(in_h, in_w, size), device
+        up = lambda a: torch.from_numpy(np.ascontiguousarray(a)).to(device)  # noqa: E731
+        self._hb, self._hc = up(self.plan.hbounds), up(self.plan.hcoeffs)
+        self._vb, self._vc = up(self.plan.vbounds), up(self.plan.vcoeffs)
+        self._tmp = None
+
+    def __call__(self, frames_hwc: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+        p = self.plan
+        if not frames_hwc.is_cuda or frames_hwc.dtype != torch.uint8 or \
+                tuple(frames_hwc.shape[1:]) != (p.in_h, p.in_w, 3):
+            raise ValueError(f"GpuFrameIngest: expected CUDA uint8 (F,{p.in_h},{p.in_w},3) frames")
+        frames_hwc = frames_hwc.contiguous()
+        n = frames_hwc.shape[0]
+        if out is None:
+            out = torch.empty((n, 3, p.size, p.size), dtype=torch.uint8, device=self.device)
+        if n == 0:
+            return out
+        need = n * p.rows * p.size * 3
+        if self._tmp is None or self._tmp.numel() < need:
+            self._tmp = torch.empty(need, dtype=torch.uint8, device=self.device)
+        lib = self._lib.load()
+        self._lib.check(lib.aclip_resize_crop_u8(
+            frames_hwc.data_ptr(), n, p.in_h, p.in_w, p.row0, p.rows, p.size, self._hb.data_ptr(),
+            self._hc.data_ptr(), p.hcoeffs.shape[1], self._vb.data_ptr(), self._vc.data_ptr(),
+            p.vcoeffs.shape[1], self._tmp.data_ptr(), out.data_ptr(),
+            torch.cuda.current_stream(self.device).cuda_stream))
+        return out

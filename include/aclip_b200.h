@@ -82,6 +82,17 @@ int aclip_patchify(const void* frames, int frames_are_u8, int B, int R, int P,
                    const float* mean3_host, const float* std3_host, void* out_split,
                    long long plane_stride, void* stream);
 
+/* Pillow-exact bicubic resize + centre crop of decoded frames (H x W x 3 uint8) to planar
+ * (3, size, size) uint8: the reference's GroupScale(224, BICUBIC) + GroupCenterCrop(224)
+ * (src/utils/augmentations.py:25-29) without the per-frame PIL calls.  The tap tables (device
+ * int32: bounds [size][2] = first source index, tap count; coeffs [size][k] 22-bit fixed point)
+ * come from the host plan (anomalyclip_b200/data.py:resize_crop_plan); vertical bounds are relative
+ * to row0.  tmp: [num_frames][rows][size][3] scratch.  Bit-exact with Pillow. */
+int aclip_resize_crop_u8(const uint8_t* frames_hwc, int num_frames, int H, int W, int row0, int rows,
+                         int size, const int* hbounds, const int* hcoeffs, int hk,
+                         const int* vbounds, const int* vcoeffs, int vk, uint8_t* tmp,
+                         uint8_t* out_chw, void* stream);
+
 typedef struct AclipGemmArgs {
   /* operands (bf16 split planes) */
   const void* a;  /* linear: [planes][M][lda]; conv3x3: [planes][S][H][W][C]            */

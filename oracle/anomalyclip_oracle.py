@@ -294,3 +294,25 @@ def frame_labels(num_frames: int, start_frame: int, label: int, normal_id: int, 
                 lab = label
         labels.append(lab)
     return labels
+
+
+def resize_center_crop_u8(frame_hwc, plan):
+    """Integer restatement of Pillow's two-pass 8-bit resample (horizontal, then vertical;
+    libImaging/Resample.c ImagingResampleHorizontal_8bpc / Vertical_8bpc) driven by a
+    `ResizeCropPlan`; what GroupScale(224, BICUBIC) + GroupCenterCrop(224) produce
+    (src/utils/augmentations.py:25-29).  frame_hwc: uint8 numpy (H, W, 3) -> uint8 (3, size, size).
+    Pinned against Pillow itself in tests/test_data_cpu.py."""
+    import numpy as np
+    half = 1 << (22 - 1)
+    src = frame_hwc[plan.row0:plan.row0 + plan.rows].astype(np.int64)
+    tmp = np.zeros((plan.rows, plan.size, 3), dtype=np.int64)
+    for x in range(plan.size):
+        x0, n = plan.hbounds[x]
+        acc = half + (src[:, x0:x0 + n, :] * plan.hcoeffs[x, :n].astype(np.int64)[None, :, None]).sum(1)
+        tmp[:, x, :] = np.clip(acc >> 22, 0, 255)
+    out = np.zeros((plan.size, plan.size, 3), dtype=np.int64)
+    for y in range(plan.size):
+        y0, n = plan.vbounds[y]
+        acc = half + (tmp[y0:y0 + n] * plan.vcoeffs[y, :n].astype(np.int64)[:, None, None]).sum(0)
+        out[y] = np.clip(acc >> 22, 0, 255)
+    return out.astype(np.uint8).transpose(2, 0, 1)

@@ -41,3 +41,20 @@ def test_gather_raw_frames_wraps_around():
     batch, seg = data.gather_test_frames(frames, 32, 16)
     assert batch.shape == (1024, 3, 2, 2) and seg == 2
     assert batch[:, 0, 0, 0].tolist() == [(i % 600) % 256 for i in range(1024)]
+
+
+@pytest.mark.parametrize("h,w", [(240, 320), (360, 640), (480, 856), (224, 224), (120, 160), (300, 225), (225, 400)])
+def test_resize_crop_plan_is_bit_exact_with_pillow(h, w):
+    """The oracle's integer restatement of Pillow's bicubic resample + torchvision's centre crop
+    against Pillow/torchvision themselves (what the reference's dataset runs)."""
+    import torchvision.transforms as T
+    from PIL import Image
+    rng = np.random.default_rng(h * 1000 + w)
+    frame = rng.integers(0, 256, (h, w, 3), dtype=np.uint8)
+    ref = T.Compose([T.Resize(224, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224)])(
+        Image.fromarray(frame))
+    ref = np.asarray(ref).transpose(2, 0, 1)
+    plan = data.resize_crop_plan(h, w, 224)
+    got = oracle.resize_center_crop_u8(frame, plan)
+    assert got.shape == (3, 224, 224)
+    assert np.array_equal(got, ref)
