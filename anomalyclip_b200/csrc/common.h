@@ -26,7 +26,7 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
                const float* beta, float eps, const float* w, float bias, const float* sim,
                int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
                float* probs_out, const AclipPeerGather* gather, int signal, cudaStream_t stream);
-int peer_wait(const unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream);
+int peer_wait(unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream);
 int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
              const float* std3, void* out_split, long long plane_stride, cudaStream_t stream);
 int cls_rows(float* x, int B, int tokens, int width, const float* cls, const float* pos,

@@ -192,14 +192,19 @@ head_kernel(const float* __restrict__ x1, const float* __restrict__ x2, long lon
 }
 
 // Stream-side wait of the fused gather: spin until every rank's flag has reached `epoch`.
-__global__ void peer_wait_kernel(const unsigned int* __restrict__ flags, int world, unsigned int epoch) {
+// Bounded: after ~5 s of GPU clocks without progress (a peer died) the kernel gives up and records
+// the missing rank in flags[world + r] = 1 instead of hanging the device.
+__global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, unsigned int epoch) {
   const int r = threadIdx.x;
   if (r < world) {
+    const long long t0 = clock64();
     unsigned int v;
-    do {
+    for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
-      if (static_cast<int>(v - epoch) < 0) __nanosleep(200);
-    } while (static_cast<int>(v - epoch) < 0);
+      if (static_cast<int>(v - epoch) >= 0) break;
+      if (clock64() - t0 > 10000000000ll) { flags[world + r] = 1u; break; }
+      __nanosleep(200);
+    }
   }
 }
 
@@ -266,7 +271,7 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
   return ACLIP_OK;
 }
 
-int peer_wait(const unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream) {
+int peer_wait(unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream) {
   ACLIP_REQUIRE(local_flags != nullptr && world >= 1 && world <= 8 && epoch > 0, "peer_wait: bad arguments");
   peer_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch);
   ACLIP_CHECK_LAUNCH();
@@ -284,7 +289,7 @@ extern "C" int aclip_layernorm(const float* x, long long rows, int D, long long 
                           ld_split, plane_stride, aclip::as_stream(stream));
 }
 
-extern "C" int aclip_peer_wait(const unsigned int* local_flags, int world, unsigned int epoch,
+extern "C" int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch,
                                void* stream) {
   return aclip::peer_wait(local_flags, world, epoch, aclip::as_stream(stream));
 }

@@ -152,3 +152,8 @@ class PeerRowGather:
         parity = self.epoch & 1
         return self.buf[parity * self.block:(parity + 1) * self.block].view(
             self.world * self.rows_per_rank, self.width)
+
+    def timed_out(self) -> List[int]:
+        """Ranks whose rows did not arrive within the wait kernel's bound (synchronises)."""
+        marks = self.buf[2 * self.block + self.world: 2 * self.block + 2 * self.world]
+        return [r for r, v in enumerate(marks.view(torch.int32).tolist()) if v != 0]

@@ -233,7 +233,9 @@ typedef struct AclipPeerGather {
   unsigned int* counter;     /* LOCAL zero-initialised device word (CTA completion counter) */
 } AclipPeerGather;
 
-int aclip_peer_wait(const unsigned int* local_flags, int world, unsigned int epoch, void* stream);
+/* local_flags: [2 * world] words: arrival flags, then timeout markers (set to 1 for a rank whose
+ * flag did not arrive within ~5 s; the wait never hangs the device). */
+int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch, void* stream);
 
 /* AnomalyCLIP.forward(test_mode=True) after the image encoder (anomaly_clip.py:132-154) fused with
  * test_step's softmax(similarity) * score (anomaly_clip_module.py:473-477).
