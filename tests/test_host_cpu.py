@@ -175,3 +175,20 @@ def test_text_tower_matches_reference_text_encoder():
     with torch.no_grad():
         out = enc(pl(), eot)
     torch.testing.assert_close(out, torch.from_numpy(z["out"]), rtol=1e-4, atol=1e-5)
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs) emits exactly one JSON line with
+    the contract's keys; everything else goes to stderr."""
+    import json
+    import subprocess
+    import sys
+    res = subprocess.run([sys.executable, str(ROOT / "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "1"], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stderr[-2000:]
+    lines = [ln for ln in res.stdout.splitlines() if ln.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
+    assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
+    assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
