@@ -313,7 +313,7 @@ def run_b200(args) -> None:
         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT-block GEMM
         # launches (in_proj 576 MB, out_proj 421 MB, c_fc 736 MB, c_proj 1002 MB) in the ncu --set full
-        # capture profiles/r1_ncu_full_block_v8.json; the algorithmic figure is next to it
+        # capture profiles/r1_ncu_full_block_final.json; the algorithmic figure is next to it
         "traffic": 684e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(gemm["launches"], 1),
         "passes": 3, "tensor_pipe_issued_tflops": 3 * achieved,
