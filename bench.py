@@ -129,6 +129,46 @@ def _cpu_state(sample_frames: int):
     return cfg, sd, vit_sd, syn.make_text_features(cfg), syn.make_ncentroid(cfg), frames, feats
 
 
+def _torch_gpu_baseline(dev) -> dict:
+    """The reference arithmetic (oracle port: the same torch ops the reference modules call) run by
+    stock PyTorch on the GPU for one 512-frame step, fp32 and with TF32 allowed.  A reported
+    baseline only: nothing of it is on the product path."""
+    from oracle import anomalyclip_oracle as oracle
+    cfg, sd, vit_sd, text, m, _, _ = _cpu_state(1)
+    from anomalyclip_b200 import synthetic as syn
+    sd = {k: v.to(dev) for k, v in sd.items()}
+    vit_sd = {k: v.to(dev) for k, v in vit_sd.items()}
+    text, m = text.to(dev), m.to(dev)
+    frames = syn.normalise_frames(syn.make_frames_u8(FRAMES_PER_STEP, seed=0)).to(dev)
+
+    def step():
+        with torch.no_grad():
+            feats = torch.cat([oracle.vit_forward(vit_sd, frames[i:i + 256]) for i in range(0, FRAMES_PER_STEP, 256)])
+            return oracle.anomaly_clip_forward(sd, feats.reshape(1, 1, FRAMES_PER_STEP, -1), m, text,
+                                               segment_size=1, normal_id=cfg.normal_id,
+                                               num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                                               depth=cfg.depth, heads=cfg.heads,
+                                               concat_features=cfg.concat_features)
+
+    out = {}
+    for name, tf32 in (("fp32", False), ("tf32_allowed", True)):
+        torch.backends.cuda.matmul.allow_tf32 = tf32
+        torch.backends.cudnn.allow_tf32 = tf32
+        for _ in range(2):
+            step()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(3):
+            step()
+        e1.record()
+        torch.cuda.synchronize()
+        out[name] = {"frames_per_s": FRAMES_PER_STEP * 3 / (e0.elapsed_time(e1) * 1e-3)}
+    torch.backends.cuda.matmul.allow_tf32 = False
+    out["what"] = "oracle torch ops on cuda:0, 512 frames/step in 2 ViT batches of 256, 2 warm-ups + 3 steps"
+    return out
+
+
 def run_reference(args) -> None:
     """--impl reference: the reference's CPU arithmetic for the same workload, on the host cores.
     The reference is pure Python over PyTorch CPU ops; what is timed is the oracle port of its
@@ -343,6 +383,10 @@ def run_b200(args) -> None:
                                   f"selector/temporal/head on one {FRAMES_PER_STEP}-row unit, fp32, "
                                   "1 warm-up + median of 3"}
 
+    torch_gpu = None
+    if rank == 0 and world == 1 and args.torch_gpu_baseline:
+        torch_gpu = _torch_gpu_baseline(dev)
+
     if rank == 0:
         flops_per_frame = VIT_GFLOP_PER_FRAME * 1e9 + TEMPORAL_MFLOP_PER_FRAME * 1e6
         _emit({
@@ -357,6 +401,7 @@ def run_b200(args) -> None:
             "gpu_launches": launches,
             "roofline": roofline, "cpu_baseline": cpu_baseline,
             "algorithmic_tflops_whole_path": value * flops_per_frame / 1e12 / n_gpus,
+            "torch_gpu_baseline": torch_gpu,
             "kernels": breakdown,
         })
     if world > 1:
@@ -389,6 +434,9 @@ def main() -> None:
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
+    ap.add_argument("--torch-gpu-baseline", action="store_true",
+                    help="also time the reference arithmetic as stock PyTorch ops ON THE GPU (fp32 and "
+                         "TF32-allowed): the bar a hand-written path has to beat (SURVEY 8d)")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: 1 warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
