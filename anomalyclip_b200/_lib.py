@@ -108,6 +108,8 @@ SIGNATURES = {
                                          vp, vp, vp, C.c_size_t, C.c_int, vp]),
     "aclip_temporal_forward_ex": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
                                             vp, vp, vp, C.c_size_t, C.c_int, C.POINTER(PeerGather), vp]),
+    "aclip_temporal_core_forward": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
+                                              vp, C.c_size_t, C.c_int, vp]),
     "aclip_peer_wait": (C.c_int, [vp, C.c_int, C.c_uint, vp]),
 }
 

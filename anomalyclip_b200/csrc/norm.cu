@@ -241,9 +241,9 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
                const float* beta, float eps, const float* w, float bias, const float* sim,
                int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
                float* probs_out, const AclipPeerGather* gather, int signal, cudaStream_t stream) {
-  ACLIP_REQUIRE(x1 && x2 && gamma && beta && w && sim && scores, "score_head: null pointer");
+  ACLIP_REQUIRE(x1 && x2 && gamma && beta && w && scores && (sim || ncls == 0), "score_head: null pointer");
   ACLIP_REQUIRE(E % 4 == 0 && E <= 256, "score_head: E=%d unsupported", E);
-  ACLIP_REQUIRE(ncls >= 1 && ncls <= 32 && ld_sim >= ncls, "score_head: ncls=%d unsupported", ncls);
+  ACLIP_REQUIRE(ncls >= 0 && ncls <= 32 && ld_sim >= ncls, "score_head: ncls=%d unsupported", ncls);
   if (rows <= 0) return ACLIP_OK;
   PeerDev pg{};
   if (gather != nullptr) {

@@ -78,6 +78,69 @@ int check_weights(const AclipTemporalWeights& w) {
   return ACLIP_OK;
 }
 
+
+// The reversible axial transformer + head on projected rows P (fp32 [rows][E], sub-video order;
+// overwritten).  sim may be NULL (no class probabilities: TemporalModel.forward on its own).
+int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, void* H, long long hp,
+             float* QKV, void* MID, long long mp, const float* SIM, const RowMap& map,
+             float* scores_out, float* similarity_out, float* class_probs_out,
+             const AclipPeerGather* gather, int signal, int passes, cudaStream_t stream) {
+  const int n = w.num_segments, l = w.seg_length, E = w.emb;
+  const long long rows = cs * n * l;
+  const float* x1 = P;  // both reversible streams start as the same tensor
+  for (int d = 0; d < w.depth; ++d) {
+    for (int axis = 0; axis < 2; ++axis) {  // y1 = x1 + Attn_n(LN(x2)); y2 = x2 + Attn_l(LN(y1))
+      const AclipAxialAttnWeights& a = w.attn[2 * d + axis];
+      ACLIP_REQUIRE(a.norm_g && a.norm_b && a.qkv_w && a.out_w && a.out_b,
+                    "temporal_forward: attention %d/%d has a null weight", d, axis);
+      const float* src = axis == 0 ? P : A1;
+      ACLIP_TRY(layernorm(src, rows, E, E, a.norm_g, a.norm_b, 1e-5f, 0, nullptr, 0, H, E, hp, stream));
+      {
+        AclipGemmArgs g = linear(H, hp, rows, E, E, a.qkv_w, 3 * E, passes);
+        g.out_f32 = QKV; g.ldc = 3 * E;
+        ACLIP_TRY(gemm(g, stream));
+      }
+      ACLIP_TRY(axial_attention(QKV, cs, n, l, E, w.heads, axis, H, hp, stream));
+      {
+        AclipGemmArgs g = linear(H, hp, rows, E, E, a.out_w, E, passes);
+        g.bias = a.out_b;
+        g.residual = axis == 0 ? x1 : P; g.ldr = E;
+        g.out_f32 = axis == 0 ? A1 : P; g.ldc = E;
+        ACLIP_TRY(gemm(g, stream));
+      }
+    }
+    x1 = A1;
+    for (int fg = 0; fg < 2; ++fg) {  // y1 = x1 + FF_f(x2); y2 = x2 + FF_g(y1)
+      const AclipConvFFWeights& c = w.ff[2 * d + fg];
+      ACLIP_REQUIRE(c.g && c.b && c.conv1_w && c.conv1_b && c.conv2_w && c.conv2_b,
+                    "temporal_forward: feed-forward %d/%d has a null weight", d, fg);
+      const float* src = fg == 0 ? P : A1;
+      float* dst = fg == 0 ? A1 : P;
+      ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, stream));
+      {
+        AclipGemmArgs g = linear(H, hp, rows, 9 * E, E, c.conv1_w, 4 * E, passes);
+        g.a_mode = 1; g.conv_c = E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
+        g.bias = c.conv1_b;
+        g.act = ACLIP_ACT_LEAKYRELU;
+        g.out_split = MID; g.split_plane_stride = mp; g.ld_split = 4 * E;
+        ACLIP_TRY(gemm(g, stream));
+      }
+      {
+        AclipGemmArgs g = linear(MID, mp, rows, 36 * E, 4 * E, c.conv2_w, E, passes);
+        g.a_mode = 1; g.conv_c = 4 * E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
+        g.bias = c.conv2_b;
+        g.residual = dst; g.ldr = E;
+        g.out_f32 = dst; g.ldc = E;
+        ACLIP_TRY(gemm(g, stream));
+      }
+    }
+  }
+  ACLIP_TRY(score_head(x1, P, rows, E, w.head_ln_g, w.head_ln_b, 1e-5f, w.head_w, w.head_bias,
+                       SIM, 32, SIM != nullptr ? w.num_dirs : 0, map, scores_out, similarity_out, class_probs_out,
+                       gather, signal, stream));
+  return ACLIP_OK;
+}
+
 }  // namespace
 
 }  // namespace aclip
@@ -172,57 +235,39 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
       ACLIP_TRY(gemm(g, stream));
     }
 
-    const float* x1 = P;  // both reversible streams start as the same tensor
-    for (int d = 0; d < w.depth; ++d) {
-      for (int axis = 0; axis < 2; ++axis) {  // y1 = x1 + Attn_n(LN(x2)); y2 = x2 + Attn_l(LN(y1))
-        const AclipAxialAttnWeights& a = w.attn[2 * d + axis];
-        ACLIP_REQUIRE(a.norm_g && a.norm_b && a.qkv_w && a.out_w && a.out_b,
-                      "temporal_forward: attention %d/%d has a null weight", d, axis);
-        const float* src = axis == 0 ? P : A1;
-        ACLIP_TRY(layernorm(src, rows, E, E, a.norm_g, a.norm_b, 1e-5f, 0, nullptr, 0, H, E, hp, stream));
-        {
-          AclipGemmArgs g = linear(H, hp, rows, E, E, a.qkv_w, 3 * E, passes);
-          g.out_f32 = QKV; g.ldc = 3 * E;
-          ACLIP_TRY(gemm(g, stream));
-        }
-        ACLIP_TRY(axial_attention(QKV, cs, n, l, E, w.heads, axis, H, hp, stream));
-        {
-          AclipGemmArgs g = linear(H, hp, rows, E, E, a.out_w, E, passes);
-          g.bias = a.out_b;
-          g.residual = axis == 0 ? x1 : P; g.ldr = E;
-          g.out_f32 = axis == 0 ? A1 : P; g.ldc = E;
-          ACLIP_TRY(gemm(g, stream));
-        }
-      }
-      x1 = A1;
-      for (int fg = 0; fg < 2; ++fg) {  // y1 = x1 + FF_f(x2); y2 = x2 + FF_g(y1)
-        const AclipConvFFWeights& c = w.ff[2 * d + fg];
-        ACLIP_REQUIRE(c.g && c.b && c.conv1_w && c.conv1_b && c.conv2_w && c.conv2_b,
-                      "temporal_forward: feed-forward %d/%d has a null weight", d, fg);
-        const float* src = fg == 0 ? P : A1;
-        float* dst = fg == 0 ? A1 : P;
-        ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, stream));
-        {
-          AclipGemmArgs g = linear(H, hp, rows, 9 * E, E, c.conv1_w, 4 * E, passes);
-          g.a_mode = 1; g.conv_c = E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
-          g.bias = c.conv1_b;
-          g.act = ACLIP_ACT_LEAKYRELU;
-          g.out_split = MID; g.split_plane_stride = mp; g.ld_split = 4 * E;
-          ACLIP_TRY(gemm(g, stream));
-        }
-        {
-          AclipGemmArgs g = linear(MID, mp, rows, 36 * E, 4 * E, c.conv2_w, E, passes);
-          g.a_mode = 1; g.conv_c = 4 * E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
-          g.bias = c.conv2_b;
-          g.residual = dst; g.ldr = E;
-          g.out_f32 = dst; g.ldc = E;
-          ACLIP_TRY(gemm(g, stream));
-        }
-      }
-    }
-    ACLIP_TRY(score_head(x1, P, rows, E, w.head_ln_g, w.head_ln_b, 1e-5f, w.head_w, w.head_bias,
-                         SIM, 32, w.num_dirs, map, scores_out, similarity_out, class_probs_out,
-                         gather, u0 + cs >= sub_videos ? 1 : 0, stream));
+    ACLIP_TRY(run_core(w, cs, P, A1, H, hp, QKV, MID, mp, SIM, map, scores_out, similarity_out,
+                       class_probs_out, gather, u0 + cs >= sub_videos ? 1 : 0, passes, stream));
   }
   return ACLIP_OK;
+}
+
+extern "C" int aclip_temporal_core_forward(const AclipTemporalWeights* wp, float* projected,
+                                           long long sub_videos, int segment_size,
+                                           float* scores_out, void* workspace,
+                                           size_t workspace_bytes, int passes, void* stream_) {
+  using namespace aclip;
+  ACLIP_REQUIRE(wp != nullptr && projected != nullptr && scores_out != nullptr,
+                "temporal_core_forward: null argument");
+  const AclipTemporalWeights& w = *wp;
+  ACLIP_REQUIRE(w.emb % 64 == 0 && w.emb <= 256 && w.depth >= 0 && w.heads > 0 &&
+                    w.seg_length > 0 && 128 % w.seg_length == 0 &&
+                    (w.num_segments * w.seg_length) % 128 == 0 && w.head_ln_g && w.head_ln_b &&
+                    w.head_w && (w.depth == 0 || (w.attn && w.ff)),
+                "temporal_core_forward: unsupported configuration or null weight");
+  ACLIP_REQUIRE(sub_videos >= 0 && segment_size >= 1 && sub_videos % segment_size == 0,
+                "temporal_core_forward: sub_videos must be a multiple of segment_size");
+  ACLIP_REQUIRE(passes == 1 || passes == 3, "temporal_core_forward: passes must be 1 or 3");
+  if (sub_videos == 0) return ACLIP_OK;
+  ACLIP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) == 0,
+                "temporal_core_forward: workspace must be 1024-byte aligned");
+  const TemporalPlan pl = plan_temporal(w, sub_videos);
+  if (workspace_bytes < pl.total)
+    return fail(ACLIP_ERR_WORKSPACE, "temporal_core_forward: workspace %zu < %zu bytes",
+                workspace_bytes, pl.total);
+  auto* base = static_cast<uint8_t*>(workspace);
+  const RowMap map{w.num_segments, segment_size, w.seg_length, 0};
+  return run_core(w, sub_videos, projected, reinterpret_cast<float*>(base + pl.off_a1), base + pl.off_h,
+                  static_cast<long long>(pl.h_plane), reinterpret_cast<float*>(base + pl.off_qkv),
+                  base + pl.off_mid, static_cast<long long>(pl.mid_plane), nullptr, map, scores_out,
+                  nullptr, nullptr, nullptr, 0, passes, as_stream(stream_));
 }

@@ -186,8 +186,10 @@ class PackedTemporal:
             return s.data_ptr()
 
         pre = "temporal_model."
-        self.bn_mean = _dev_f32(sd["selector_model.bn_layer.running_mean"], device)
-        self.bn_var = _dev_f32(sd["selector_model.bn_layer.running_var"], device)
+        self.has_selector = "selector_model.bn_layer.running_mean" in sd
+        if self.has_selector:
+            self.bn_mean = _dev_f32(sd["selector_model.bn_layer.running_mean"], device)
+            self.bn_var = _dev_f32(sd["selector_model.bn_layer.running_var"], device)
         w = self.struct = _lib.TemporalWeights()
         w.feature_dim, w.num_dirs, w.emb, w.depth, w.heads = feature_dim, self.num_dirs, E, depth, heads
         w.num_segments, w.seg_length, w.concat = num_segments, seg_length, int(concat_features)
@@ -201,10 +203,18 @@ class PackedTemporal:
             pw = torch.cat((pw[:, self.num_dirs:], pw[:, : self.num_dirs],
                             pw.new_zeros(E, 32 - self.num_dirs)), dim=1)
         w.proj_w, w.proj_b = spl(pw), f32t(sd[pre + "projection.bias"])
+        # the projection in the reference's own column order, K padded to a multiple of 8
+        # (TemporalModel.forward on its own)
+        pw0 = sd[pre + "projection.weight"].detach().to(torch.float32)
+        self.in_dim, self.in_pad = in_dim, (in_dim + 7) // 8 * 8
+        self.proj_plain = _split_weight(torch.nn.functional.pad(pw0, (0, self.in_pad - in_dim)), device)
+        self.proj_bias = _dev_f32(sd[pre + "projection.bias"], device)
+        self.pos = None
         p0 = sd[pre + "axial_attn.pos_emb.param_0"].to(torch.float32)  # (1,E,n,1)
         p1 = sd[pre + "axial_attn.pos_emb.param_1"].to(torch.float32)  # (1,E,1,l)
         pos = (p0 + p1)[0].permute(1, 2, 0).reshape(num_segments * seg_length, E)
         w.pos = f32t(pos)
+        self.pos = keep[-1]
 
         self.attn = (_lib.AxialAttnWeights * max(2 * depth, 1))()
         self.ff = (_lib.ConvFFWeights * max(2 * depth, 1))()
@@ -292,3 +302,38 @@ class TemporalScorer:
             self.passes, C.byref(gather) if gather is not None else None,
             torch.cuda.current_stream().cuda_stream))
         return sim, scores, probs
+
+
+class TemporalCore:
+    """`TemporalModel.forward(features, segment_size, test_mode=True)` on its own
+    (temporal_model.py:42-77): projection GEMM (+ positional embedding) on the regrouped rows,
+    then `aclip_temporal_core_forward` (axial transformer + classifier)."""
+
+    def __init__(self, packed: PackedTemporal, passes: int = 3) -> None:
+        self.packed, self.passes = packed, passes
+        self._ws = _Workspace()
+        self._zeros = torch.zeros(packed.in_pad, dtype=torch.float32, device=packed.device)
+
+    def __call__(self, features: torch.Tensor, segment_size: int = 1) -> torch.Tensor:
+        p = self.packed
+        if not features.is_cuda:
+            raise _lib.AclipError("TemporalCore: features must be on the CUDA device")
+        x = features.reshape(-1, features.shape[-1]).to(torch.float32)
+        n, l, E = p.struct.num_segments, p.struct.seg_length, p.struct.emb
+        unit = n * l
+        if x.shape[1] != p.in_dim or x.shape[0] % (unit * segment_size) != 0:
+            raise ValueError(f"TemporalCore: expected (k*{unit * segment_size}, {p.in_dim}) rows, got {tuple(x.shape)}")
+        if p.in_pad != p.in_dim:
+            x = torch.nn.functional.pad(x, (0, p.in_pad - p.in_dim))
+        rows = x.shape[0]
+        sub_videos = rows // unit
+        xs = ops.center(x.contiguous(), self._zeros, regroup=(n, segment_size, l))   # regroup + split
+        proj = ops.gemm(xs, p.proj_plain, bias=p.proj_bias, residual=p.pos, res_mod=unit)
+        scores = torch.empty(rows, dtype=torch.float32, device=x.device)
+        lib = _lib.load()
+        nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), sub_videos)
+        ws = self._ws.get(nbytes, x.device)
+        _lib.check(lib.aclip_temporal_core_forward(
+            C.byref(p.struct), proj.data_ptr(), sub_videos, segment_size, scores.data_ptr(), ws, nbytes,
+            self.passes, torch.cuda.current_stream().cuda_stream))
+        return scores.unsqueeze(1)

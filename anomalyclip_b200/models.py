@@ -180,9 +180,23 @@ class TemporalModel(nn.Module):
                                                 axial_pos_emb_shape=(num_segments, seg_length))
         self.classifier = ClassificationHead(emb_size, output_size)
 
+    @torch.no_grad()
     def forward(self, features, segment_size, test_mode):
-        raise AclipError("TemporalModel runs fused with the selector and the head inside "
-                         "AnomalyCLIP.forward (aclip_temporal_forward); call that instead")
+        """Stand-alone scores (N, 1).  Inside AnomalyCLIP.forward this module is NOT called: it
+        runs fused with the selector and the head (aclip_temporal_forward)."""
+        if not test_mode:
+            raise NotImplementedError("TemporalModel: the training regrouping is out of scope")
+        key = _versions(self)
+        if getattr(self, "_core", None) is None or key != self._core_key:
+            dev = self.projection.weight.device
+            sd = {"temporal_model." + k: v for k, v in self.state_dict().items()}
+            concat = self.input_size != 512
+            packed = engine.PackedTemporal(
+                sd, dev, num_classes=self.input_size - 512 + 1 if concat else 2, normal_id=0,
+                emb_size=self.emb_size, depth=self.depth, heads=self.heads,
+                num_segments=self.num_segments, seg_length=self.seg_length, concat_features=concat)
+            self._core, self._core_key = engine.TemporalCore(packed), key
+        return self._core(features, int(segment_size))
 
 
 class SelectorModel(nn.Module):

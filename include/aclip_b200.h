@@ -247,7 +247,14 @@ int aclip_temporal_forward(const AclipTemporalWeights* w, const float* features,
                            long long sub_videos, int segment_size, float* similarity_out,
                            float* scores_out, float* class_probs_out, void* workspace,
                            size_t workspace_bytes, int passes, void* stream);
-/* Same, with the fused peer all-gather (gather may be NULL). */
+/* TemporalModel.forward on its own (temporal_model.py:42-77) after the projection: `projected` is
+ * fp32 [sub_videos*n*l][emb] = projection(features) + axial positional embedding, rows in sub-video
+ * order (overwritten); scores_out [N] comes back in the caller's "(b n s l)" order.  Only the
+ * transformer / classifier fields of `w` are read.  Workspace as aclip_temporal_workspace_bytes. */
+int aclip_temporal_core_forward(const AclipTemporalWeights* w, float* projected, long long sub_videos,
+                                int segment_size, float* scores_out, void* workspace,
+                                size_t workspace_bytes, int passes, void* stream);
+/* Same as aclip_temporal_forward, with the fused peer all-gather (gather may be NULL). */
 int aclip_temporal_forward_ex(const AclipTemporalWeights* w, const float* features,
                               long long sub_videos, int segment_size, float* similarity_out,
                               float* scores_out, float* class_probs_out, void* workspace,

@@ -58,6 +58,13 @@ def test_forward_and_test_step_on_features(name):
     # the selector on its own (SelectorModel.forward, test branch)
     sel = net.selector_model(feats.cuda(), text.cuda(), None, m.cuda(), True)
     assert_parity(sel, sim_ref, f"{name} SelectorModel.forward")
+    # ... and the temporal model on its own (TemporalModel.forward, test branch)
+    xc = (feats.reshape(-1, 512) - m)
+    tin = torch.cat((sim_ref, xc), dim=-1) if cfg.concat_features else xc
+    t_ref = oracle.temporal_forward(tin, sd, 2, cfg.num_segments, cfg.seg_length, cfg.depth, cfg.heads)
+    t_out = net.temporal_model(tin.cuda(), 2, True)
+    assert t_out.shape == (tin.shape[0], 1)
+    assert_parity(t_out, t_ref, f"{name} TemporalModel.forward")
 
 
 def test_weights_changed_after_first_call_are_repacked():
