@@ -192,3 +192,34 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["impl"] == "reference" and d["unit"] == "frames/s" and d["value"] > 0
     assert d["higher_is_better"] is True and d["cpu_baseline"]["kind"] == "port"
     assert d["e2e"]["h2d_bytes_per_step"] == 0 and "workload" in d["config"]
+
+
+def test_text_features_are_computed_once_from_checkpoint_buffers():
+    """AnomalyCLIP.get_text_features: prompts from prompt_learner buffers, EOT positions recovered
+    from token_suffix, result cached until the text-side parameters change (the reference
+    recomputes it on every forward, anomaly_clip.py:136)."""
+    from anomalyclip_b200.models import AnomalyCLIP
+    torch.manual_seed(0)
+    C = 7
+    net = AnomalyCLIP(arch="ViT-B/16", classnames=[f"c{i}" for i in range(C)], emb_size=128, depth=1,
+                      heads=8, dim_heads=None, num_segments=32, seg_length=16, concat_features=False,
+                      normal_id=4, stride=1, load_from_features=True, ncrops=1, n_ctx=8).eval()
+    emb = net.token_embedding.weight.detach()
+    tokens = torch.zeros(C, 77, dtype=torch.long)
+    for i in range(C):   # SOS X*8 <name tokens> . EOT pad...
+        seq = [49406] + [343] * 8 + [1000 + i + j for j in range(1 + i % 3)] + [269, 49407]
+        tokens[i, : len(seq)] = torch.tensor(seq)
+    full = emb[tokens]
+    with torch.no_grad():
+        net.prompt_learner.token_prefix.copy_(full[:, :1])
+        net.prompt_learner.token_suffix.copy_(full[:, 9:])
+    a = net.get_text_features()
+    assert a.shape == (C, 512) and torch.isfinite(a).all()
+    with torch.no_grad():
+        ref = net.text_encoder(net.prompt_learner(), tokens.argmax(-1))
+    torch.testing.assert_close(a, ref)
+    assert net.get_text_features() is a                      # cached
+    with torch.no_grad():
+        net.prompt_learner.ctx.add_(0.01)
+    b = net.get_text_features()
+    assert b is not a and not torch.allclose(a, b)           # recomputed after the context changed
