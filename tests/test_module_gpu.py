@@ -169,3 +169,27 @@ def test_two_rank_nccl_sharding_matches_single_rank():
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          env=env, capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-2000:]
+
+
+def test_mirror_net_on_raw_frames_matches_oracle():
+    """configs[2] through the reference-facing class: AnomalyCLIP(load_from_features=False) on one
+    512-frame unit of uint8 frames (ViT-B/16, 12 layers) against the CPU oracle."""
+    from tests.util_weights import make_frames_u8, normalise_frames
+    cfg = PRESETS["shanghaitech"]
+    sd = make_state_dict(cfg, with_vit=True)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    net = _net(cfg, load_from_features=False)
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    net.set_text_features(text)
+    net.cuda().eval()
+    u8 = make_frames_u8(cfg.unit, seed=4)
+    sim_ref, sc_ref = oracle.anomaly_clip_forward(
+        sd, normalise_frames(u8).unsqueeze(0), m, text, segment_size=1, normal_id=cfg.normal_id,
+        num_segments=cfg.num_segments, seg_length=cfg.seg_length, depth=cfg.depth, heads=cfg.heads,
+        concat_features=cfg.concat_features, load_from_features=False)
+    sim, sc = net(u8.unsqueeze(0).cuda(), None, m, 1, True)
+    assert_parity(sim, sim_ref, "mirror net, raw frames: similarity")
+    assert_parity(sc, sc_ref, "mirror net, raw frames: scores")
+    probs_ref, _ = oracle.test_step_postprocess(sim_ref, sc_ref)
+    assert torch.equal(net.class_probs.argmax(1).cpu(), probs_ref.argmax(1))
