@@ -10,6 +10,8 @@
 // ldmatrix is conflict free; scores never leave registers (online softmax over 64-key chunks).
 #include <cuda_bf16.h>
 
+#include <cstdlib>
+
 #include "common.h"
 #include "split.cuh"
 
@@ -286,9 +288,15 @@ namespace aclip {
 int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                   int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
                   cudaStream_t stream) {
-  if (kernel >= 16)  // profiling experiments: kernel = 16 + debug mask
+  if (kernel >= 16) {
+    // profiling experiments (kernel = 16 + mask: skip softmax math / output stores / TMEM stores;
+    // results are WRONG by construction) -- only with ACLIP_PROFILING_EXPERIMENTS=1 in the environment
+    const char* allow = getenv("ACLIP_PROFILING_EXPERIMENTS");
+    ACLIP_REQUIRE(allow != nullptr && allow[0] == '1',
+                  "vit_attention: kernel must be 0, 1 or 2 (got %d)", kernel);
     return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
                             out_plane_stride, ld_out, stream, kernel - 16);
+  }
   ACLIP_REQUIRE(kernel >= 0 && kernel <= 2, "vit_attention: kernel must be 0, 1 or 2");
   if (kernel == 1)
     return vit_attention_mma(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
