@@ -261,12 +261,13 @@ int vit_attention_mma(const void* qkv_split, long long in_plane_stride, int ld_i
   ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(qkv_split) & 15) == 0,
                 "vit_attention: qkv must be 16-byte aligned");
   const int smem = 4 * LP * ROW_BYTES;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int once_dev;
+  if (once.need(once_dev)) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        4 * ATT_WARPS * 32 * ROW_BYTES));
-    configured = true;
+    once.mark(once_dev);
   }
   const float sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
   dim3 grid(2, heads, B);

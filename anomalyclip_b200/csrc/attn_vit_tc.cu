@@ -489,12 +489,13 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   p.width = heads * HD;
   p.debug = debug;
   const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int once_dev;
+  if (once.need(once_dev)) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024));
-    configured = true;
+    once.mark(once_dev);
   }
   int ctas = sm_count();
   if (ctas > p.items) ctas = p.items;

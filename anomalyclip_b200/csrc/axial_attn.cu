@@ -135,11 +135,12 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
   auto* o = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_AXIAL_ATTENTION, stream);
   if (eh == 32) {
-    static bool configured = false;
-    if (!configured) {
+    static PerDeviceOnce once;
+    int once_dev;
+    if (once.need(once_dev)) {
       ACLIP_CUDA_OK(cudaFuncSetAttribute(axial_attention_kernel<32>,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * MAX_L * 32 * 4));
-      configured = true;
+      once.mark(once_dev);
     }
     axial_attention_kernel<32><<<static_cast<unsigned>(seqs), heads * 32, smem, stream>>>(
         qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride);

@@ -79,6 +79,21 @@ enum KernelKind : int {
 void timing_begin(int kind, cudaStream_t stream);
 void timing_end(int kind, cudaStream_t stream, double flops, double bytes);
 
+// "Do this once per device" latch for cudaFuncSetAttribute (the attribute is per device; a process
+// may drive several GPUs, and several host threads may launch concurrently).
+struct PerDeviceOnce {
+  std::atomic<unsigned long long> done{0};
+  // true if the caller must (re)apply the setting for the current device; call mark() afterwards
+  bool need(int& dev) {
+    dev = 0;
+    cudaGetDevice(&dev);
+    return dev < 0 || dev >= 64 || ((done.load(std::memory_order_acquire) >> dev) & 1ull) == 0;
+  }
+  void mark(int dev) {
+    if (dev >= 0 && dev < 64) done.fetch_or(1ull << dev, std::memory_order_release);
+  }
+};
+
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 }  // namespace aclip

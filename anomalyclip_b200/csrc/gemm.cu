@@ -25,16 +25,16 @@ int fail(int code, const char* fmt, ...) {
 }
 
 int sm_count() {
-  static int cached = 0;
-  if (cached == 0) {
-    int dev = 0, n = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess &&
-        cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && n > 0)
-      cached = n;
-    else
+  static std::atomic<int> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
+  int n = cached[dev].load(std::memory_order_relaxed);
+  if (n == 0) {
+    if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess || n <= 0)
       return 148;
+    cached[dev].store(n, std::memory_order_relaxed);
   }
-  return cached;
+  return n;
 }
 
 std::atomic<long long> g_launches{0};
@@ -80,11 +80,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
                   int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, PASSES>;
   auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int once_dev;
+  if (once.need(once_dev)) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    configured = true;
+    once.mark(once_dev);
   }
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -111,11 +112,12 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
                        int max_ctas, cudaStream_t stream) {
   using Cfg = Gemm2Cfg<PASSES>;
   auto kernel = gemm2_tcgen05_kernel<PASSES>;
-  static bool configured = false;
-  if (!configured) {
+  static PerDeviceOnce once;
+  int once_dev;
+  if (once.need(once_dev)) {
     ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        Cfg::SMEM_BYTES));
-    configured = true;
+    once.mark(once_dev);
   }
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
