@@ -91,81 +91,6 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
   }
 }
 
-// Same arithmetic, 8 elements per lane and iteration (two adjacent float4 in, one 16-byte store per
-// plane out): used when D is a multiple of 8.  Fewer, wider memory instructions per row.
-template <int MODE>
-__global__ void __launch_bounds__(kWarpsPerCta * 32)
-layernorm8_kernel(const float* __restrict__ x, long long rows, int D, long long ldx,
-                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                  float* __restrict__ out_f32, long long ld_f32,
-                  __nv_bfloat16* __restrict__ out_split, long long ld_split,
-                  long long plane_stride) {
-  constexpr int kMaxOct = kMaxVec / 2;
-  const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-  if (row >= rows) return;
-  const int noct = D >> 3;
-  const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
-  float4 v[kMaxOct][2];
-  float s = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxOct; ++i) {
-    const int c = lane + i * 32;
-    if (c < noct) {
-      v[i][0] = xr[2 * c];
-      v[i][1] = xr[2 * c + 1];
-      s += ((v[i][0].x + v[i][0].y) + (v[i][0].z + v[i][0].w)) +
-           ((v[i][1].x + v[i][1].y) + (v[i][1].z + v[i][1].w));
-    }
-  }
-  const float mean = warp_sum(s) / static_cast<float>(D);
-  float q = 0.f;
-#pragma unroll
-  for (int i = 0; i < kMaxOct; ++i) {
-    const int c = lane + i * 32;
-    if (c < noct) {
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        v[i][h].x -= mean; v[i][h].y -= mean; v[i][h].z -= mean; v[i][h].w -= mean;
-        q += (v[i][h].x * v[i][h].x + v[i][h].y * v[i][h].y) +
-             (v[i][h].z * v[i][h].z + v[i][h].w * v[i][h].w);
-      }
-    }
-  }
-  const float var = warp_sum(q) / static_cast<float>(D);
-  const float rstd = MODE == 0 ? rsqrtf(var + eps) : 1.0f / (sqrtf(var) + eps);
-#pragma unroll
-  for (int i = 0; i < kMaxOct; ++i) {
-    const int c = lane + i * 32;
-    if (c < noct) {
-      float4 y[2];
-#pragma unroll
-      for (int h = 0; h < 2; ++h) {
-        const float4 g = __ldg(reinterpret_cast<const float4*>(gamma) + 2 * c + h);
-        const float4 b = __ldg(reinterpret_cast<const float4*>(beta) + 2 * c + h);
-        y[h].x = v[i][h].x * rstd * g.x + b.x;
-        y[h].y = v[i][h].y * rstd * g.y + b.y;
-        y[h].z = v[i][h].z * rstd * g.z + b.z;
-        y[h].w = v[i][h].w * rstd * g.w + b.w;
-      }
-      if (out_f32 != nullptr) {
-        float4* o = reinterpret_cast<float4*>(out_f32 + row * ld_f32) + 2 * c;
-        o[0] = y[0]; o[1] = y[1];
-      }
-      if (out_split != nullptr) {
-        uint32_t h[4], l[4];
-        split_pack2(y[0].x, y[0].y, h[0], l[0]);
-        split_pack2(y[0].z, y[0].w, h[1], l[1]);
-        split_pack2(y[1].x, y[1].y, h[2], l[2]);
-        split_pack2(y[1].z, y[1].w, h[3], l[3]);
-        __nv_bfloat16* dst = out_split + row * ld_split + 8 * c;
-        *reinterpret_cast<uint4*>(dst) = make_uint4(h[0], h[1], h[2], h[3]);
-        *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(l[0], l[1], l[2], l[3]);
-      }
-    }
-  }
-}
-
 struct PeerDev {            // device-side copy of AclipPeerGather for one head launch
   int world, rank, width, signal;
   long long rows_per_rank;
@@ -299,17 +224,7 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   auto* os = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_LAYERNORM, stream);
-  const bool wide = D % 8 == 0 && ldx % 8 == 0 && (out_f32 == nullptr || ld_f32 % 8 == 0) &&
-                    (out_split == nullptr || (ld_split % 8 == 0 && plane_stride % 8 == 0)) &&
-                    (reinterpret_cast<uintptr_t>(x) & 31) == 0 &&
-                    (reinterpret_cast<uintptr_t>(out_split) & 15) == 0;
-  if (wide && mode == 0)
-    layernorm8_kernel<0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
-  else if (wide)
-    layernorm8_kernel<1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
-  else if (mode == 0)
+  if (mode == 0)
     layernorm_kernel<0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   else
