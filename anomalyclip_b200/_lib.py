@@ -34,12 +34,14 @@ class GemmArgs(C.Structure):
         ("split_plane_stride", C.c_longlong), ("ldc", C.c_int), ("ld_split", C.c_int),
         ("row_group", C.c_int), ("row_group_stride", C.c_int), ("row_offset", C.c_int),
         ("max_ctas", C.c_int), ("kernel", C.c_int),
+        ("out_scale", C.c_float), ("out_enc", C.c_int),
     ]
 
 
 class VitBlock(C.Structure):
     _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w",
-                                  "out_b", "fc_w", "fc_b", "proj_w", "proj_b")]
+                                  "out_b", "fc_w", "fc_b", "proj_w", "proj_b")] + \
+               [(n, C.c_float) for n in ("qkv_s", "out_s", "fc_s", "proj_s")]
 
 
 class VitWeights(C.Structure):
@@ -47,7 +49,7 @@ class VitWeights(C.Structure):
                                        "output_dim")] + \
                [(n, vp) for n in ("conv1_w", "class_embedding", "positional_embedding", "ln_pre_g",
                                   "ln_pre_b", "ln_post_g", "ln_post_b", "proj_w")] + \
-               [("blocks", C.POINTER(VitBlock))]
+               [("blocks", C.POINTER(VitBlock)), ("conv1_s", C.c_float), ("proj_s", C.c_float)]
 
 
 class AxialAttnWeights(C.Structure):
@@ -86,17 +88,20 @@ SIGNATURES = {
     "aclip_timing_enable": (C.c_int, [C.c_int]),
     "aclip_timing_collect": (C.c_int, [C.POINTER(TimingRow), C.c_int]),
     "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),
+    "aclip_encode_f16f8": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong,
+                                     C.c_int, C.c_int, C.c_int, vp]),
     "aclip_center_regroup": (C.c_int, [vp, C.c_longlong, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp,
                                        C.c_int, C.c_longlong, vp]),
     "aclip_patchify": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),
-                                 C.POINTER(C.c_float), vp, C.c_longlong, vp]),
+                                 C.POINTER(C.c_float), vp, C.c_longlong, C.c_int, vp]),
     "aclip_resize_crop_u8": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, vp, vp,
                                        C.c_int, vp, vp, C.c_int, vp, vp, vp]),
     "aclip_gemm": (C.c_int, [C.POINTER(GemmArgs), vp]),
     "aclip_layernorm": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_longlong, vp, vp, C.c_float,
-                                  C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, vp]),
+                                  C.c_int, vp, C.c_longlong, vp, C.c_longlong, C.c_longlong, C.c_int,
+                                  vp]),
     "aclip_vit_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int, vp,
-                                      C.c_longlong, C.c_int, C.c_int, vp]),
+                                      C.c_longlong, C.c_int, C.c_int, C.c_int, vp]),
     "aclip_axial_attention": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, C.c_int, C.c_int,
                                         C.c_int, vp, C.c_longlong, vp]),
     "aclip_vit_workspace_bytes": (C.c_size_t, [C.POINTER(VitWeights), C.c_int]),

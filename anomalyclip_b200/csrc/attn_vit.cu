@@ -288,7 +288,9 @@ namespace aclip {
 // kernel: 0 = default (tcgen05), 1 = warp-level mma.sync kernel, 2 = tcgen05 kernel
 int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                   int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
-                  cudaStream_t stream) {
+                  int out_enc, cudaStream_t stream) {
+  ACLIP_REQUIRE(out_enc == 0 || kernel == 0 || kernel == 2,
+                "vit_attention: only the tcgen05 kernel writes f16f8 output");
   if (kernel >= 16) {
     // profiling experiments (kernel = 16 + mask: skip softmax math / output stores / TMEM stores;
     // results are WRONG by construction) -- only with ACLIP_PROFILING_EXPERIMENTS=1 in the environment
@@ -303,14 +305,14 @@ int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, i
     return vit_attention_mma(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
                              out_plane_stride, ld_out, stream);
   return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
-                          out_plane_stride, ld_out, stream);
+                          out_plane_stride, ld_out, stream, 0, out_enc);
 }
 }  // namespace aclip
 
 extern "C" int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in,
                                    int B, int L, int heads, void* out_split,
                                    long long out_plane_stride, int ld_out, int kernel,
-                                   void* stream) {
+                                   int out_enc, void* stream) {
   return aclip::vit_attention(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
-                              out_plane_stride, ld_out, kernel, aclip::as_stream(stream));
+                              out_plane_stride, ld_out, kernel, out_enc, aclip::as_stream(stream));
 }

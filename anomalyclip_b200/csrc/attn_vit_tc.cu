@@ -51,6 +51,7 @@ struct AttnTcParams {
   int ld_out;
   int width;                // heads * 64: column offset of K (and 2x for V) inside a qkv row
   int debug;                // profiling experiments only (0 in production)
+  int out_enc;              // 0 = bf16 hi/lo output planes, 1 = f16f8 activation planes (split.cuh)
 };
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -173,6 +174,7 @@ __device__ __forceinline__ float softmax_group(uint32_t (&v)[16], int key0, int 
   return sum;
 }
 
+template <int ENC>  // output encoding: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                         const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p) {
@@ -329,6 +331,44 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       // 32 dims, then write whole 128-byte rows: 4 rows per store instruction instead of 32
       // scattered 16-byte pieces.  16-byte chunks are XOR-swizzled by the row to avoid conflicts.
       uint8_t* stage = out_stage + quarter * (2 * 32 * 128);
+      if (ENC == 1) {
+        // f16f8: buffer 0 holds the fp16 rows (128 B), buffer 1 the e4m3 rows [L 64 B | C 64 B]
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint2 h0, h1;
+          uint32_t l0, l1, c0, c1;
+          f16f8_pack4(__uint_as_float(o[8 * c + 0]) * inv_sum, __uint_as_float(o[8 * c + 1]) * inv_sum,
+                      __uint_as_float(o[8 * c + 2]) * inv_sum, __uint_as_float(o[8 * c + 3]) * inv_sum,
+                      kActScaleMain, kActScaleRes, kActScaleCoarse, h0, l0, c0);
+          f16f8_pack4(__uint_as_float(o[8 * c + 4]) * inv_sum, __uint_as_float(o[8 * c + 5]) * inv_sum,
+                      __uint_as_float(o[8 * c + 6]) * inv_sum, __uint_as_float(o[8 * c + 7]) * inv_sum,
+                      kActScaleMain, kActScaleRes, kActScaleCoarse, h1, l1, c1);
+          const int chunk = (half * 4 + c) ^ (lane & 7);
+          *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+          const int lchunk = (half * 2 + (c >> 1)) ^ (lane & 7);   // 8 dims = 8 bytes of L and of C
+          const int cchunk = (4 + half * 2 + (c >> 1)) ^ (lane & 7);
+          *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + lchunk * 16 + (c & 1) * 8) = make_uint2(l0, l1);
+          *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + cchunk * 16 + (c & 1) * 8) = make_uint2(c0, c1);
+        }
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        const int row_base = q * TILE_Q + quarter * 32;
+        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
+        const long long off0 = (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = half * 16 + i * 4 + (lane >> 3);
+          const int chunk = lane & 7;
+          if (row_base + row < p.L) {
+            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
+            const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
+            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) = *reinterpret_cast<const uint4*>(src);
+            // chunks 0..3 of buffer 1 -> L plane, chunks 4..7 -> C plane (16 values each)
+            uint8_t* dst8 = ob + (chunk < 4 ? 2 : 3) * p.out_plane_stride + off + (chunk & 3) * 16;
+            *reinterpret_cast<uint4*>(dst8) = *reinterpret_cast<const uint4*>(src + 4096);
+          }
+        }
+        return;
+      }
 #pragma unroll
       for (int c = 0; c < 4; ++c) {
         uint32_t hi[4], lo[4];
@@ -449,8 +489,10 @@ EncodeTiledFn encode_fn() {
 
 int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                      int heads, void* out_split, long long out_plane_stride, int ld_out,
-                     cudaStream_t stream, int debug) {
+                     cudaStream_t stream, int debug, int out_enc) {
   ACLIP_REQUIRE(qkv_split != nullptr && out_split != nullptr, "vit_attention: null pointer");
+  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && ld_out % 16 == 0 && out_plane_stride % 16 == 0),
+                "vit_attention: out_enc=%d unsupported (f16f8 needs 16-element pitches)", out_enc);
   ACLIP_REQUIRE(B > 0 && heads > 0 && L > 0, "vit_attention: empty problem");
   const int LP = (L + 15) / 16 * 16;
   ACLIP_REQUIRE(LP <= MAX_LP, "vit_attention: L=%d exceeds the %d-token limit", L, MAX_LP);
@@ -488,19 +530,25 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   p.ld_out = ld_out;
   p.width = heads * HD;
   p.debug = debug;
+  p.out_enc = out_enc;
   const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
   static PerDeviceOnce once;
   int once_dev;
   if (once.need(once_dev)) {
-    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel,
-                                       cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024));
+    constexpr int kMaxSmem = 4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<0>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<1>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     once.mark(once_dev);
   }
   int ctas = sm_count();
   if (ctas > p.items) ctas = p.items;
   timing_begin(KIND_VIT_ATTENTION, stream);
-  vit_attention_tc_kernel<<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  if (out_enc == 1)
+    vit_attention_tc_kernel<1><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  else
+    vit_attention_tc_kernel<0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
   timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
              (double)B * L * heads * HD * (3 * 4.0 + 4.0));
   ACLIP_CHECK_LAUNCH();

@@ -19,16 +19,20 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream);
 struct RowMap;
 int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
               long long plane_stride, cudaStream_t stream);
+int encode_f16f8(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
+                 long long plane_stride, int e_main, int e_res, int e_coarse, cudaStream_t stream);
 int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
               const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
-              void* out_split, long long ld_split, long long plane_stride, cudaStream_t stream);
+              void* out_split, long long ld_split, long long plane_stride, int out_enc,
+              cudaStream_t stream);
 int score_head(const float* x1, const float* x2, long long rows, int E, const float* gamma,
                const float* beta, float eps, const float* w, float bias, const float* sim,
                int ld_sim, int ncls, const RowMap& map, float* scores, float* sim_out,
                float* probs_out, const AclipPeerGather* gather, int signal, cudaStream_t stream);
 int peer_wait(unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream);
 int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
-             const float* std3, void* out_split, long long plane_stride, cudaStream_t stream);
+             const float* std3, void* out_split, long long plane_stride, int out_enc,
+             cudaStream_t stream);
 int cls_rows(float* x, int B, int tokens, int width, const float* cls, const float* pos,
              cudaStream_t stream);
 int center_regroup(const float* feats, long long rows, int D, const float* centroid,
@@ -36,10 +40,10 @@ int center_regroup(const float* feats, long long rows, int D, const float* centr
                    cudaStream_t stream);
 int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                   int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
-                  cudaStream_t stream);
+                  int out_enc, cudaStream_t stream);
 int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                      int heads, void* out_split, long long out_plane_stride, int ld_out,
-                     cudaStream_t stream, int debug = 0);
+                     cudaStream_t stream, int debug = 0, int out_enc = 0);
 int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E, int heads,
                     int axis, void* out_split, long long plane_stride, cudaStream_t stream);
 

@@ -72,6 +72,65 @@ int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, i
 }
 
 
+// ------------------------------------------------------------------------------ f16f8 encode
+// fp32 [rows][cols] -> f16f8 planes (split.cuh): used to pack weights (per-tensor exponent) and, in
+// tests, activations.  Columns cols..ld_out-1 are zero-filled.
+__global__ void __launch_bounds__(256)
+encode_f16f8_kernel(const float* __restrict__ in, long long rows, int cols, int ld_in,
+                    uint8_t* __restrict__ out, int ld_out, long long plane_stride, float s_main,
+                    float s_res, float s_coarse, bool vec_ok) {
+  const int groups_per_row = ld_out >> 3;
+  const long long total = rows * groups_per_row;
+  for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / groups_per_row;
+    const int c = static_cast<int>(i - r * groups_per_row) << 3;
+    float v[8];
+    const float* src = in + r * ld_in + c;
+    if (vec_ok && c + 8 <= cols) {
+      const float4 a = *reinterpret_cast<const float4*>(src);
+      const float4 b = *reinterpret_cast<const float4*>(src + 4);
+      v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
+      v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) v[j] = (c + j < cols) ? src[j] : 0.0f;
+    }
+    uint2 h0, h1;
+    uint32_t l0, l1, c0, c1;
+    f16f8_pack4(v[0], v[1], v[2], v[3], s_main, s_res, s_coarse, h0, l0, c0);
+    f16f8_pack4(v[4], v[5], v[6], v[7], s_main, s_res, s_coarse, h1, l1, c1);
+    const long long off = r * ld_out + c;
+    *reinterpret_cast<uint4*>(out + 2 * off) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+    *reinterpret_cast<uint2*>(out + 2 * plane_stride + off) = make_uint2(l0, l1);
+    *reinterpret_cast<uint2*>(out + 3 * plane_stride + off) = make_uint2(c0, c1);
+  }
+}
+
+int encode_f16f8(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
+                 long long plane_stride, int e_main, int e_res, int e_coarse, cudaStream_t stream) {
+  ACLIP_REQUIRE(in != nullptr && out != nullptr, "encode_f16f8: null pointer");
+  ACLIP_REQUIRE(rows >= 0 && cols > 0 && ld_in >= cols, "encode_f16f8: bad shape");
+  ACLIP_REQUIRE(ld_out % 16 == 0 && ld_out >= cols,
+                "encode_f16f8: ld_out=%d must be a multiple of 16 >= cols", ld_out);
+  ACLIP_REQUIRE(plane_stride % 16 == 0 && plane_stride >= rows * ld_out,
+                "encode_f16f8: plane_stride too small or unaligned");
+  ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(out) & 15) == 0, "encode_f16f8: output must be 16-byte aligned");
+  ACLIP_REQUIRE(e_main >= -30 && e_main <= 30 && e_res >= 0 && e_res <= 12 && e_coarse >= -40 && e_coarse <= 40,
+                "encode_f16f8: exponents out of range");
+  if (rows == 0) return ACLIP_OK;
+  const bool vec_ok = (ld_in % 4 == 0) && ((reinterpret_cast<uintptr_t>(in) & 15) == 0);
+  const long long total = rows * (ld_out >> 3);
+  timing_begin(KIND_SPLIT, stream);
+  encode_f16f8_kernel<<<grid_for(total, 256), 256, 0, stream>>>(
+      in, rows, cols, ld_in, static_cast<uint8_t*>(out), ld_out, plane_stride, exp2f((float)e_main),
+      exp2f((float)e_res), exp2f((float)e_coarse), vec_ok);
+  timing_end(KIND_SPLIT, stream, 0.0, (double)rows * (4.0 * cols + 4.0 * ld_out));
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
 // ------------------------------------------------------------------------------ patchify
 // Frames (B,3,R,R) -> im2col rows for the patch-embedding GEMM (clip/model.py:246-252,267):
 // row = b*G*G + gy*G + gx, column k = c*P*P + py*P + px (the order of conv1.weight.reshape(width,-1)).
@@ -79,7 +138,7 @@ int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, i
 // (src/utils/augmentations.py:21-34): ((v / 255) - mean) / std in fp32.
 struct Norm3 { float mean[3]; float std[3]; };
 
-template <bool U8>
+template <bool U8, int ENC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
                 __nv_bfloat16* __restrict__ out, long long plane_stride) {
@@ -113,6 +172,11 @@ patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
       v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
     }
+    if (ENC == 1) {
+      f16f8_store4_act(out, plane_stride, row * K + k, v[0], v[1], v[2], v[3]);
+      f16f8_store4_act(out, plane_stride, row * K + k + 4, v[4], v[5], v[6], v[7]);
+      continue;
+    }
     uint32_t hi[4], lo[4];
 #pragma unroll
     for (int j = 0; j < 4; ++j) split2(v[2 * j], v[2 * j + 1], hi[j], lo[j]);
@@ -123,8 +187,11 @@ patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
 }
 
 int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
-             const float* std3, void* out_split, long long plane_stride, cudaStream_t stream) {
+             const float* std3, void* out_split, long long plane_stride, int out_enc,
+             cudaStream_t stream) {
   ACLIP_REQUIRE(frames != nullptr && out_split != nullptr, "patchify: null pointer");
+  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && plane_stride % 16 == 0 && (3 * P * P) % 16 == 0),
+                "patchify: out_enc=%d unsupported", out_enc);
   ACLIP_REQUIRE(B > 0 && P % 8 == 0 && R % P == 0, "patchify: B=%d R=%d P=%d unsupported", B, R, P);
   ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 15) == 0, "patchify: frames must be 16-byte aligned");
   Norm3 nrm{{0.f, 0.f, 0.f}, {1.f, 1.f, 1.f}};
@@ -136,10 +203,15 @@ int patchify(const void* frames, int is_u8, int B, int R, int P, const float* me
   const long long total = static_cast<long long>(B) * G * G * (3 * P * P / 8);
   auto* o = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_PATCHIFY, stream);
-  if (is_u8)
-    patchify_kernel<true><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  const int grid = grid_for(total, 256);
+  if (is_u8 && out_enc == 1)
+    patchify_kernel<true, 1><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  else if (is_u8)
+    patchify_kernel<true, 0><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+  else if (out_enc == 1)
+    patchify_kernel<false, 1><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
   else
-    patchify_kernel<false><<<grid_for(total, 256), 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
+    patchify_kernel<false, 0><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
   timing_end(KIND_PATCHIFY, stream, 0.0, (double)B * 3 * R * R * ((is_u8 ? 1.0 : 4.0) + 4.0));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -223,6 +295,13 @@ extern "C" int aclip_split_f32(const float* in, long long rows, int cols, int ld
                           aclip::as_stream(stream));
 }
 
+extern "C" int aclip_encode_f16f8(const float* in, long long rows, int cols, int ld_in, void* out,
+                                  int ld_out, long long plane_stride, int e_main, int e_res,
+                                  int e_coarse, void* stream) {
+  return aclip::encode_f16f8(in, rows, cols, ld_in, out, ld_out, plane_stride, e_main, e_res,
+                             e_coarse, aclip::as_stream(stream));
+}
+
 extern "C" int aclip_center_regroup(const float* feats, long long rows, int D,
                                     const float* centroid, int num_segments, int segment_size,
                                     int seg_length, void* out_split, int ld_out,
@@ -236,7 +315,7 @@ extern "C" int aclip_center_regroup(const float* feats, long long rows, int D,
 
 extern "C" int aclip_patchify(const void* frames, int frames_are_u8, int B, int R, int P,
                               const float* mean3_host, const float* std3_host, void* out_split,
-                              long long plane_stride, void* stream) {
+                              long long plane_stride, int out_enc, void* stream) {
   return aclip::patchify(frames, frames_are_u8, B, R, P, mean3_host, std3_host, out_split,
-                         plane_stride, aclip::as_stream(stream));
+                         plane_stride, out_enc, aclip::as_stream(stream));
 }

@@ -62,13 +62,15 @@ static EncodeTiledFn encode_tiled_fn() {
 // bf16 tensor map with the 128-byte swizzle; dims/strides innermost first, strides in bytes for
 // dims 1..rank-1.
 static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                     const cuuint64_t* strides_bytes, const cuuint32_t* box) {
+                     const cuuint64_t* strides_bytes, const cuuint32_t* box,
+                     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
-  CUresult r = fn(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, static_cast<cuuint32_t>(rank),
+  CUresult r = fn(map, dtype, static_cast<cuuint32_t>(rank),
                   const_cast<void*>(base), dims, strides_bytes, box, elem_strides,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, swizzle,
                   CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS)
     return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
@@ -108,8 +110,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
 }
 
 template <int PASSES>
-static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
-                       int max_ctas, cudaStream_t stream) {
+static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA8,
+                       const CUtensorMap& tmB8, const GemmParams& p, int max_ctas,
+                       cudaStream_t stream) {
   using Cfg = Gemm2Cfg<PASSES>;
   auto kernel = gemm2_tcgen05_kernel<PASSES>;
   static PerDeviceOnce once;
@@ -125,7 +128,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
   if (clusters > m_tiles * n_tiles) clusters = m_tiles * n_tiles;
   if (clusters < 1) clusters = 1;
   timing_begin(KIND_GEMM, stream);
-  kernel<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  kernel<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA8, tmB8, p);
   {
     const double planes = PASSES == 1 ? 1.0 : 2.0;
     const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
@@ -141,7 +144,17 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const Gem
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  ACLIP_REQUIRE(g.passes == 1 || g.passes == 3, "gemm: passes must be 1 or 3 (got %d)", g.passes);
+  ACLIP_REQUIRE(g.passes >= 1 && g.passes <= 3, "gemm: passes must be 1, 2 or 3 (got %d)", g.passes);
+  ACLIP_REQUIRE(g.out_enc == 0 || g.out_enc == 1, "gemm: out_enc must be 0 (bf16 hi/lo) or 1 (f16f8)");
+  if (g.passes == 2) {
+    // f16f8 operands (split.cuh): CTA-pair kernel, linear A only
+    ACLIP_REQUIRE(g.a_mode == 0 && g.N % 256 == 0 && g.kernel != 1,
+                  "gemm: passes=2 (f16f8 operands) needs a linear A operand and N %% 256 == 0 (N=%d)", g.N);
+    ACLIP_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.a_plane_stride % 16 == 0 &&
+                      g.w_plane_stride % 16 == 0,
+                  "gemm: passes=2 needs pitches and plane strides that are multiples of 16");
+    ACLIP_REQUIRE(g.out_scale > 0.0f, "gemm: passes=2 needs out_scale = 2^-(e_act + e_weight)");
+  }
   ACLIP_REQUIRE(g.N % 32 == 0, "gemm: N=%d must be a multiple of 32", g.N);
   ACLIP_REQUIRE(g.ldw % 8 == 0 && g.K % 8 == 0, "gemm: K=%d / ldw=%d must be multiples of 8", g.K,
                 g.ldw);
@@ -167,7 +180,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   // work to fill the machine; kernel = 1 / 2 forces the single-CTA / pair kernel (tests).
   ACLIP_REQUIRE(g.kernel >= 0 && g.kernel <= 2, "gemm: kernel must be 0 (auto), 1 or 2");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
-  const bool pair = g.kernel == 2 || (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
+  const bool pair = g.kernel == 2 || g.passes == 2 || (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
   // more SMs share the K loop.  128 is also preferred when it wastes fewer padded columns.
@@ -200,8 +213,35 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.row_group_stride = g.row_group > 0 ? g.row_group_stride : 0;  // 0 = no remap
   ACLIP_REQUIRE(g.row_group <= 0 || g.row_group_stride > 0, "gemm: row_group_stride must be > 0 with a row remap");
   p.row_offset = g.row_offset;
+  p.out_scale = g.out_scale > 0.0f ? g.out_scale : 1.0f;
+  p.out_enc = g.out_enc;
+  ACLIP_REQUIRE(g.out_enc == 0 || g.out_split == nullptr ||
+                    (p.ld_split % 16 == 0 && g.split_plane_stride % 16 == 0),
+                "gemm: an f16f8 output needs a pitch and plane stride that are multiples of 16");
 
-  CUtensorMap tmA, tmB;
+  CUtensorMap tmA, tmB, tmA8, tmB8;
+  if (g.passes == 2) {
+    // fp16 plane: [1][rows][ld] (128-byte swizzle rows of 64 values); e4m3 planes L, C: one
+    // [2][rows][ld] byte tensor starting 2 * plane_stride bytes in (64-byte swizzle rows)
+    for (int op = 0; op < 2; ++op) {
+      const void* base = op == 0 ? g.a : g.w;
+      const cuuint64_t rows = op == 0 ? g.M : g.N, ld = op == 0 ? g.lda : g.ldw;
+      const cuuint64_t ps = op == 0 ? g.a_plane_stride : g.w_plane_stride;
+      ACLIP_REQUIRE(ps >= rows * ld, "gemm: plane stride smaller than the operand");
+      cuuint64_t dims_h[3] = {(cuuint64_t)g.K, rows, 1};
+      cuuint64_t str_h[2] = {ld * 2, ld * 2 * rows};
+      cuuint32_t box_h[3] = {64, 128, 1};
+      ACLIP_TRY(make_tmap(op == 0 ? &tmA : &tmB, base, 3, dims_h, str_h, box_h,
+                          CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
+      cuuint64_t dims_8[3] = {(cuuint64_t)g.K, rows, 2};
+      cuuint64_t str_8[2] = {ld, ps};
+      cuuint32_t box_8[3] = {64, 128, 2};
+      ACLIP_TRY(make_tmap(op == 0 ? &tmA8 : &tmB8, static_cast<const uint8_t*>(base) + 2 * ps, 3,
+                          dims_8, str_8, box_8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
+                          CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+    return launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
+  }
   if (g.a_mode == 0) {
     ACLIP_REQUIRE(g.lda % 8 == 0 && g.lda >= g.K, "gemm: lda=%d invalid for K=%d", g.lda, g.K);
     cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, (cuuint64_t)planes};
@@ -242,8 +282,8 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   }
 
   if (pair)
-    return g.passes == 3 ? launch_pair<3>(tmA, tmB, p, g.max_ctas, stream)
-                         : launch_pair<1>(tmA, tmB, p, g.max_ctas, stream);
+    return g.passes == 3 ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+                         : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
   if (block_n == 256) {
     return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
                          : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);

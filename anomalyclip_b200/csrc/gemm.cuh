@@ -55,6 +55,8 @@ struct GemmParams {
   int ld_split;  // pitch of out_split (elements)
   // output row remap: out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset
   int row_group, row_group_stride, row_offset;
+  float out_scale;  // multiplies the accumulator before bias (f16f8 operands: 2^-(ex + ew)), else 1
+  int out_enc;      // encoding of out_split: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes
 };
 
 template <int BLOCK_N_, int PASSES_>
@@ -107,7 +109,7 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
   if (m_base >= p.M) return;  // warp-uniform: the whole block is padding
   float v[32];
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]);
+  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.out_scale;
   if (p.bias != nullptr) {
     const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
 #pragma unroll
@@ -159,12 +161,17 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
       if (p.out_f32 != nullptr)
         *reinterpret_cast<float4*>(p.out_f32 + out_rows[i] * p.ldc + col) = v4;
       if (p.out_split != nullptr) {
-        uint32_t h0, l0, h1, l1;
-        split_pack2(v4.x, v4.y, h0, l0);
-        split_pack2(v4.z, v4.w, h1, l1);
-        __nv_bfloat16* dst = p.out_split + out_rows[i] * p.ld_split + col;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-        *reinterpret_cast<uint2*>(dst + p.split_plane_stride) = make_uint2(l0, l1);
+        if (p.out_enc == 0) {
+          uint32_t h0, l0, h1, l1;
+          split_pack2(v4.x, v4.y, h0, l0);
+          split_pack2(v4.z, v4.w, h1, l1);
+          __nv_bfloat16* dst = p.out_split + out_rows[i] * p.ld_split + col;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+          *reinterpret_cast<uint2*>(dst + p.split_plane_stride) = make_uint2(l0, l1);
+        } else {
+          f16f8_store4_act(p.out_split, p.split_plane_stride, out_rows[i] * p.ld_split + col, v4.x,
+                           v4.y, v4.z, v4.w);
+        }
       }
     }
   }
@@ -349,7 +356,9 @@ struct Gemm2Cfg {
 template <int PASSES>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
+                     const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmA8,
+                     const __grid_constant__ CUtensorMap tmB8, const GemmParams p) {
   using Cfg = Gemm2Cfg<PASSES>;
   constexpr int STAGES = Cfg::STAGES;
 
@@ -371,6 +380,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
+    if (PASSES == 2) {
+      ptx::prefetch_tmap(&tmA8);
+      ptx::prefetch_tmap(&tmB8);
+    }
     for (int s = 0; s < STAGES; ++s) {
       ptx::mbar_init(&full_bar[s], 1);   // leader's producer (arrive.expect_tx for both CTAs)
       ptx::mbar_init(&empty_bar[s], 1);  // multicast tcgen05.commit
@@ -413,6 +426,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
           uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (PASSES == 2) {
+            // f16f8 operands: fp16 plane (128 B rows, SWIZZLE_128B) + the two e4m3 planes in one
+            // box (64 B rows, SWIZZLE_64B); same bytes per stage as two bf16 planes
+            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+            ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (p.a_mode == 0) {
             ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
           } else {
@@ -431,8 +454,11 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // The warp stays converged; one elected lane issues (descriptors in uniform registers).
     if (rank == 0) {
       const bool leader = ptx::elect_one();
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
+      // kind::f16 with fp16 operands and kind::f8f6f4 with e4m3 operands both encode format 0
+      constexpr uint32_t idesc = PASSES == 2 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
+                                             : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
       const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
+      const uint64_t desc8 = ptx::make_kmajor_sw64_desc(ptx::smem_u32(smem));
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       for (int t = cluster_id; t < total_tiles; t += num_clusters) {
@@ -445,13 +471,30 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           // descriptor low word counts 16-byte units: stage / plane / K-step offsets are adds
           const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
           const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+          if (PASSES == 2) {
+            // x_H w_H: four K=16 fp16 MMAs; x_L w_C and x_C w_L: two K=32 e4m3 MMAs each (the
+            // e4m3 planes L, C sit behind the fp16 plane, 64-byte rows, 8 KB apart)
 #pragma unroll
-          for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-            const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
-            ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (PASSES == 3) {
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
+            const uint64_t b_l0 = a_l0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+            constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
+              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
+              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + kCoarse + 2 * k, b_l0 + 2 * k, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+              const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              if (PASSES == 3) {
+                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+              }
             }
           }
           ptx::mma_commit_pair_if(leader, &empty_bar[stage], 0x3);  // frees the slot in both CTAs

@@ -33,7 +33,8 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 
 // mode 0: (x - mean) / sqrt(var + eps) * g + b      nn.LayerNorm (clip/model.py:174-180)
 // mode 1: (x - mean) / (sqrt(var) + eps) * g + b    ChanLayerNorm of axial_attention (eps on std)
-template <int MODE>
+// ENC: encoding of out_split, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes (split.cuh)
+template <int MODE, int ENC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long ldx,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
@@ -80,12 +81,16 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
       y.w = v[i].w * rstd * g.w + b.w;
       if (out_f32 != nullptr) reinterpret_cast<float4*>(out_f32 + row * ld_f32)[c] = y;
       if (out_split != nullptr) {
-        uint32_t h01, l01, h23, l23;
-        split_pack2(y.x, y.y, h01, l01);
-        split_pack2(y.z, y.w, h23, l23);
-        __nv_bfloat16* dst = out_split + row * ld_split + 4 * c;
-        *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
-        *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(l01, l23);
+        if (ENC == 0) {
+          uint32_t h01, l01, h23, l23;
+          split_pack2(y.x, y.y, h01, l01);
+          split_pack2(y.z, y.w, h23, l23);
+          __nv_bfloat16* dst = out_split + row * ld_split + 4 * c;
+          *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
+          *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(l01, l23);
+        } else {
+          f16f8_store4_act(out_split, plane_stride, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
+        }
       }
     }
   }
@@ -212,8 +217,11 @@ __global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, un
 
 int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
               const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
-              void* out_split, long long ld_split, long long plane_stride, cudaStream_t stream) {
+              void* out_split, long long ld_split, long long plane_stride, int out_enc,
+              cudaStream_t stream) {
   ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
+  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && mode == 0 && ld_split % 16 == 0 && plane_stride % 16 == 0),
+                "layernorm: out_enc=%d unsupported here (f16f8 needs mode 0 and 16-element pitches)", out_enc);
   ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
   ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
                     (out_split == nullptr || ld_split % 4 == 0),
@@ -224,11 +232,14 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   auto* os = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_LAYERNORM, stream);
-  if (mode == 0)
-    layernorm_kernel<0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+  if (mode == 0 && out_enc == 1)
+    layernorm_kernel<0, 1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  else if (mode == 0)
+    layernorm_kernel<0, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   else
-    layernorm_kernel<1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+    layernorm_kernel<1, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   timing_end(KIND_LAYERNORM, stream, 8.0 * rows * D,
              (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? 4.0 : 0.0)));
@@ -284,9 +295,10 @@ int peer_wait(unsigned int* local_flags, int world, unsigned int epoch, cudaStre
 extern "C" int aclip_layernorm(const float* x, long long rows, int D, long long ldx,
                                const float* gamma, const float* beta, float eps, int mode,
                                float* out_f32, long long ld_f32, void* out_split,
-                               long long ld_split, long long plane_stride, void* stream) {
+                               long long ld_split, long long plane_stride, int out_enc,
+                               void* stream) {
   return aclip::layernorm(x, rows, D, ldx, gamma, beta, eps, mode, out_f32, ld_f32, out_split,
-                          ld_split, plane_stride, aclip::as_stream(stream));
+                          ld_split, plane_stride, out_enc, aclip::as_stream(stream));
 }
 
 extern "C" int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch,

@@ -232,6 +232,20 @@ __device__ __forceinline__ void mma_bf16_ss_pair_if(bool issue, uint32_t d_tmem,
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
       : "memory");
 }
+// Same for 8-bit float operands (kind::f8f6f4, K = 32 per instruction, twice the kind::f16 rate).
+__device__ __forceinline__ void mma_f8_ss_pair_if(bool issue, uint32_t d_tmem, uint64_t a_desc,
+                                                  uint64_t b_desc, uint32_t idesc,
+                                                  uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::f8f6f4 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_pair_if(bool issue, uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t"
@@ -265,6 +279,24 @@ __device__ __forceinline__ uint64_t make_kmajor_sw128_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;                     // [46,48) descriptor version
   d |= static_cast<uint64_t>(2) << 61;                     // [61,64) SWIZZLE_128B
   return d;
+}
+
+// Same for rows of 64 B (64 e4m3 values) stored with the 64-byte swizzle (TMA SWIZZLE_64B): the
+// swizzle atom is 8 rows x 64 B = 512 B, so SBO = 512 B.  Layout type 4 = SWIZZLE_64B.
+__device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(512 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(4) << 61;
+  return d;
+}
+
+// Instruction descriptor with operand format code 0 for A and B: fp16 x fp16 under kind::f16,
+// e4m3 x e4m3 under kind::f8f6f4; fp32 accumulate, both operands K-major.
+__host__ __device__ constexpr uint32_t make_idesc_fmt0_f32(int m, int n) {
+  return (1u << 4) | (static_cast<uint32_t>(n >> 3) << 17) | (static_cast<uint32_t>(m >> 4) << 24);
 }
 
 // Instruction descriptor, kind::f16: bf16 x bf16 -> fp32, both operands K-major.

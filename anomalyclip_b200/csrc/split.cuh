@@ -17,3 +17,61 @@ __device__ __forceinline__ void split_pack2(float a, float b, uint32_t& hi, uint
 }
 
 }  // namespace aclip
+
+// ---------------------------------------------------------------------------------------------
+// "f16f8" operand encoding (GEMM passes == 2): an fp32 value v travels as three planes
+//     H = fp16(v * 2^e_main)                         main product        (kind::f16 MMA)
+//     L = e4m3((v * 2^e_main - H) * 2^e_res)         residual of H       (kind::f8f6f4 MMA, 2x rate)
+//     C = e4m3(v * 2^e_coarse)                       coarse copy, multiplies the OTHER operand's L
+// and the GEMM accumulates  x_H w_H + x_L w_C + x_C w_L  = 2^(ex + ew) * x w  to ~2^-16 relative
+// (the dropped term is x_res * w_res ~ 2^-22).  Two pass-equivalents of tensor-pipe time instead of
+// the three bf16 passes.  Exponents must satisfy  ew_coarse = ew_main - ex_res  and
+// ex_coarse = ex_main - ew_res.  Activations use fixed exponents (|x| < 4094 keeps H finite, C
+// saturates at 448 which only perturbs a 2^-11 cross term); weights get a per-tensor e_main chosen
+// at pack time so that max|w| * 2^e_main lies in (2^14, 2^15].
+// Memory layout of a tensor [rows][ld] with plane stride P (elements): H at byte 0 (2 B/element),
+// L at byte 2P, C at byte 3P (1 B/element each): 4P bytes, the same as the two bf16 planes.
+#include <cuda_fp16.h>
+#include <cuda_fp8.h>
+
+namespace aclip {
+
+constexpr int kActExpMain = 4, kActExpRes = 7, kActExpCoarse = 0;   // activations (A operand)
+constexpr int kWgtExpRes = 4;                                       // weights: e_coarse = e_main - 7
+constexpr float kActScaleMain = 16.0f, kActScaleRes = 128.0f, kActScaleCoarse = 1.0f;
+
+// two values -> packed fp16x2 (a in the low half), e4m3x2 residual, e4m3x2 coarse (a in the low byte)
+__device__ __forceinline__ void f16f8_pack2(float a, float b, float s_main, float s_res,
+                                            float s_coarse, uint32_t& h, uint32_t& l, uint32_t& c) {
+  const float am = a * s_main, bm = b * s_main;
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h) : "f"(bm), "f"(am));
+  const float2 hf = __half22float2(*reinterpret_cast<const __half2*>(&h));
+  l = __nv_cvt_float2_to_fp8x2(make_float2((am - hf.x) * s_res, (bm - hf.y) * s_res),
+                               __NV_SATFINITE, __NV_E4M3);
+  c = __nv_cvt_float2_to_fp8x2(make_float2(a * s_coarse, b * s_coarse), __NV_SATFINITE, __NV_E4M3);
+}
+
+// four consecutive values -> 8 bytes of H, 4 bytes of L, 4 bytes of C
+__device__ __forceinline__ void f16f8_pack4(float v0, float v1, float v2, float v3, float s_main,
+                                            float s_res, float s_coarse, uint2& h, uint32_t& l,
+                                            uint32_t& c) {
+  uint32_t l0, c0, l1, c1;
+  f16f8_pack2(v0, v1, s_main, s_res, s_coarse, h.x, l0, c0);
+  f16f8_pack2(v2, v3, s_main, s_res, s_coarse, h.y, l1, c1);
+  l = l0 | (l1 << 16);
+  c = c0 | (c1 << 16);
+}
+
+// store four consecutive ACTIVATION values at element offset `off` of an f16f8 tensor
+__device__ __forceinline__ void f16f8_store4_act(void* base, long long plane_stride, long long off,
+                                                 float v0, float v1, float v2, float v3) {
+  uint2 h;
+  uint32_t l, c;
+  f16f8_pack4(v0, v1, v2, v3, kActScaleMain, kActScaleRes, kActScaleCoarse, h, l, c);
+  uint8_t* b = static_cast<uint8_t*>(base);
+  *reinterpret_cast<uint2*>(b + 2 * off) = h;
+  *reinterpret_cast<uint32_t*>(b + 2 * plane_stride + off) = l;
+  *reinterpret_cast<uint32_t*>(b + 3 * plane_stride + off) = c;
+}
+
+}  // namespace aclip

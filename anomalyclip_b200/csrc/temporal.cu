@@ -94,7 +94,7 @@ int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, v
       ACLIP_REQUIRE(a.norm_g && a.norm_b && a.qkv_w && a.out_w && a.out_b,
                     "temporal_forward: attention %d/%d has a null weight", d, axis);
       const float* src = axis == 0 ? P : A1;
-      ACLIP_TRY(layernorm(src, rows, E, E, a.norm_g, a.norm_b, 1e-5f, 0, nullptr, 0, H, E, hp, stream));
+      ACLIP_TRY(layernorm(src, rows, E, E, a.norm_g, a.norm_b, 1e-5f, 0, nullptr, 0, H, E, hp, 0, stream));
       {
         AclipGemmArgs g = linear(H, hp, rows, E, E, a.qkv_w, 3 * E, passes);
         g.out_f32 = QKV; g.ldc = 3 * E;
@@ -116,7 +116,7 @@ int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, v
                     "temporal_forward: feed-forward %d/%d has a null weight", d, fg);
       const float* src = fg == 0 ? P : A1;
       float* dst = fg == 0 ? A1 : P;
-      ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, stream));
+      ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, 0, stream));
       {
         AclipGemmArgs g = linear(H, hp, rows, 9 * E, E, c.conv1_w, 4 * E, passes);
         g.a_mode = 1; g.conv_c = E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);

@@ -36,7 +36,7 @@ VitPlan plan_vit(const AclipVitWeights& w, int mb) {
   const size_t patch_elems = static_cast<size_t>(mb) * p.grid2 * p.k0;
   p.big_plane = rows * 4 * w.width;
   if (patch_elems > p.big_plane) p.big_plane = patch_elems;
-  p.big_plane = (p.big_plane + 7) / 8 * 8;
+  p.big_plane = (p.big_plane + 15) / 16 * 16;
   p.off_x = 0;
   p.off_h = align_up(p.off_x + p.x_bytes);
   p.off_big = align_up(p.off_h + 2 * p.h_plane * 2);
@@ -45,8 +45,9 @@ VitPlan plan_vit(const AclipVitWeights& w, int mb) {
 }
 
 AclipGemmArgs linear(const void* a, long long a_plane, int M, int K, int lda, const void* w, int N,
-                     int passes) {
+                     int passes, float w_scale = 0.0f) {
   AclipGemmArgs g{};
+  g.out_scale = passes == 2 ? w_scale : 0.0f;
   g.a = a; g.w = w;
   g.M = M; g.N = N; g.K = K;
   g.lda = lda; g.ldw = K;
@@ -89,7 +90,11 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
   ACLIP_TRY(check_weights(w));
   ACLIP_REQUIRE(frames != nullptr && features_out != nullptr, "vit_forward: null frames/output");
   ACLIP_REQUIRE(num_frames >= 0 && micro_batch > 0, "vit_forward: bad frame count / micro-batch");
-  ACLIP_REQUIRE(passes == 1 || passes == 3, "vit_forward: passes must be 1 or 3");
+  ACLIP_REQUIRE(passes >= 1 && passes <= 3, "vit_forward: passes must be 1, 2 or 3");
+  ACLIP_REQUIRE(passes != 2 || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
+                                (3 * w.patch * w.patch) % 16 == 0),
+                "vit_forward: passes=2 (f16f8 operands) needs width and output_dim multiples of 256");
+  const int enc = passes == 2 ? 1 : 0;  // encoding of every GEMM A operand on this path
   if (num_frames == 0) return ACLIP_OK;
   if (micro_batch > num_frames) micro_batch = static_cast<int>(num_frames);
   const VitPlan pl = plan_vit(w, micro_batch);
@@ -114,9 +119,9 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
                          ? static_cast<const void*>(static_cast<const uint8_t*>(frames) + f0 * frame_elems)
                          : static_cast<const void*>(static_cast<const float*>(frames) + f0 * frame_elems);
     // patch embedding (:267-269) + positional embedding of the patch tokens (:278)
-    ACLIP_TRY(patchify(fr, frames_are_u8, Bm, w.resolution, w.patch, mean3_host, std3_host, BIG, bp, stream));
+    ACLIP_TRY(patchify(fr, frames_are_u8, Bm, w.resolution, w.patch, mean3_host, std3_host, BIG, bp, enc, stream));
     {
-      AclipGemmArgs g = linear(BIG, bp, Bm * pl.grid2, pl.k0, pl.k0, w.conv1_w, W, passes);
+      AclipGemmArgs g = linear(BIG, bp, Bm * pl.grid2, pl.k0, pl.k0, w.conv1_w, W, passes, w.conv1_s);
       g.residual = w.positional_embedding + W;  // rows 1.. of the table
       g.res_mod = pl.grid2;
       g.ldr = W;
@@ -126,38 +131,40 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
       ACLIP_TRY(gemm(g, stream));
     }
     ACLIP_TRY(cls_rows(X, Bm, T, W, w.class_embedding, w.positional_embedding, stream));  // :270-278
-    ACLIP_TRY(layernorm(X, M, W, W, w.ln_pre_g, w.ln_pre_b, 1e-5f, 0, X, W, nullptr, 0, 0, stream));  // :279
+    ACLIP_TRY(layernorm(X, M, W, W, w.ln_pre_g, w.ln_pre_b, 1e-5f, 0, X, W, nullptr, 0, 0, 0, stream));  // :279
 
     for (int l = 0; l < w.layers; ++l) {  // :214-217
       const AclipVitBlock& b = w.blocks[l];
       ACLIP_REQUIRE(b.ln1_g && b.ln1_b && b.ln2_g && b.ln2_b && b.qkv_w && b.qkv_b && b.out_w &&
                         b.out_b && b.fc_w && b.fc_b && b.proj_w && b.proj_b,
                     "vit_forward: block %d has a null weight", l);
-      ACLIP_TRY(layernorm(X, M, W, W, b.ln1_g, b.ln1_b, 1e-5f, 0, nullptr, 0, H, W, hp, stream));
+      ACLIP_TRY(layernorm(X, M, W, W, b.ln1_g, b.ln1_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.qkv_w, 3 * W, passes);
+        AclipGemmArgs g = linear(H, hp, M, W, W, b.qkv_w, 3 * W, passes, b.qkv_s);
         g.bias = b.qkv_b;
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 3 * W;
         ACLIP_TRY(gemm(g, stream));
       }
-      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, stream));
+      // q | k | v stay bf16 hi/lo planes (the attention kernel's operand format) in every mode
+      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, enc, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes);
+        AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes, b.out_s);
         g.bias = b.out_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;
         ACLIP_TRY(gemm(g, stream));
       }
-      ACLIP_TRY(layernorm(X, M, W, W, b.ln2_g, b.ln2_b, 1e-5f, 0, nullptr, 0, H, W, hp, stream));
+      ACLIP_TRY(layernorm(X, M, W, W, b.ln2_g, b.ln2_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.fc_w, 4 * W, passes);
+        AclipGemmArgs g = linear(H, hp, M, W, W, b.fc_w, 4 * W, passes, b.fc_s);
         g.bias = b.fc_b;
         g.act = ACLIP_ACT_QUICKGELU;
+        g.out_enc = enc;
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 4 * W;
         ACLIP_TRY(gemm(g, stream));
       }
       {
-        AclipGemmArgs g = linear(BIG, bp, M, 4 * W, 4 * W, b.proj_w, W, passes);
+        AclipGemmArgs g = linear(BIG, bp, M, 4 * W, 4 * W, b.proj_w, W, passes, b.proj_s);
         g.bias = b.proj_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;
@@ -166,9 +173,9 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
     }
     // ln_post on the CLS token (:285) and the output projection (:287-288)
     ACLIP_TRY(layernorm(X, Bm, W, static_cast<long long>(T) * W, w.ln_post_g, w.ln_post_b, 1e-5f, 0,
-                        nullptr, 0, H, W, hp, stream));
+                        nullptr, 0, H, W, hp, enc, stream));
     {
-      AclipGemmArgs g = linear(H, hp, Bm, W, W, w.proj_w, w.output_dim, passes);
+      AclipGemmArgs g = linear(H, hp, Bm, W, W, w.proj_w, w.output_dim, passes, w.proj_s);
       g.out_f32 = features_out + f0 * w.output_dim;
       g.ldc = w.output_dim;
       ACLIP_TRY(gemm(g, stream));

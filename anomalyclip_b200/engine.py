@@ -54,9 +54,13 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 class PackedVit:
     """VisionTransformer state_dict (clip/model.py:233-264 names) -> AclipVitWeights."""
 
-    def __init__(self, sd: Weights, device: torch.device, heads: Optional[int] = None) -> None:
+    def __init__(self, sd: Weights, device: torch.device, heads: Optional[int] = None,
+                 passes: int = 3) -> None:
+        """passes: the GEMM mode the weights are packed for -- 3 / 1: bf16 hi/lo planes,
+        2: f16f8 planes with a per-tensor exponent (include/aclip_b200.h)."""
         _require_cuda(device)
         self.device = device
+        self.f16f8 = passes == 2
         conv = sd["conv1.weight"]
         self.width, _, self.patch, _ = conv.shape
         tokens = sd["positional_embedding"].shape[0]
@@ -78,9 +82,14 @@ class PackedVit:
             return t.data_ptr()
 
         def spl(t):
+            """-> (device pointer of the packed weight, accumulator scale of its GEMM)"""
+            if self.f16f8:
+                e = ops.encode_f16f8(_dev_f32(t, device), weight=True)
+                keep.append(e)
+                return e.data_ptr(), 2.0 ** -(ops.ACT_EXP[0] + e.exp)
             s = _split_weight(t, device)
             keep.append(s)
-            return s.data_ptr()
+            return s.data_ptr(), 0.0
 
         self.blocks = (_lib.VitBlock * max(self.layers, 1))()
         for i in range(self.layers):
@@ -88,19 +97,19 @@ class PackedVit:
             b = self.blocks[i]
             b.ln1_g, b.ln1_b = f32(p + "ln_1.weight"), f32(p + "ln_1.bias")
             b.ln2_g, b.ln2_b = f32(p + "ln_2.weight"), f32(p + "ln_2.bias")
-            b.qkv_w, b.qkv_b = spl(sd[p + "attn.in_proj_weight"]), f32(p + "attn.in_proj_bias")
-            b.out_w, b.out_b = spl(sd[p + "attn.out_proj.weight"]), f32(p + "attn.out_proj.bias")
-            b.fc_w, b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
-            b.proj_w, b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
+            (b.qkv_w, b.qkv_s), b.qkv_b = spl(sd[p + "attn.in_proj_weight"]), f32(p + "attn.in_proj_bias")
+            (b.out_w, b.out_s), b.out_b = spl(sd[p + "attn.out_proj.weight"]), f32(p + "attn.out_proj.bias")
+            (b.fc_w, b.fc_s), b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
+            (b.proj_w, b.proj_s), b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
         w = self.struct = _lib.VitWeights()
         w.width, w.layers, w.heads = self.width, self.layers, self.heads
         w.patch, w.resolution, w.output_dim = self.patch, self.resolution, self.output_dim
-        w.conv1_w = spl(conv.reshape(self.width, -1))
+        w.conv1_w, w.conv1_s = spl(conv.reshape(self.width, -1))
         w.class_embedding = f32("class_embedding")
         w.positional_embedding = f32("positional_embedding")
         w.ln_pre_g, w.ln_pre_b = f32("ln_pre.weight"), f32("ln_pre.bias")
         w.ln_post_g, w.ln_post_b = f32("ln_post.weight"), f32("ln_post.bias")
-        w.proj_w = spl(sd["proj"].t())
+        w.proj_w, w.proj_s = spl(sd["proj"].t())
         w.blocks = C.cast(self.blocks, C.POINTER(_lib.VitBlock))
 
 
@@ -108,6 +117,9 @@ class VitEncoder:
     """frames -> 512-d features through `aclip_vit_forward`."""
 
     def __init__(self, packed: PackedVit, micro_batch: int = 256, passes: int = 3) -> None:
+        if (passes == 2) != packed.f16f8:
+            raise _lib.AclipError("VitEncoder: passes=2 needs weights packed with PackedVit(passes=2) "
+                                  "(and only then)")
         self.packed = packed
         self.micro_batch = micro_batch
         self.passes = passes

@@ -86,7 +86,8 @@ class VisionTransformer(nn.Module):
         key = _versions(self)
         if self._encoder is None or key != self._key:
             device = self.proj.device
-            packed = engine.PackedVit({k: v for k, v in self.state_dict().items()}, device, self.heads)
+            packed = engine.PackedVit({k: v for k, v in self.state_dict().items()}, device, self.heads,
+                                      passes=self.passes)
             self._encoder, self._key = engine.VitEncoder(packed, self.micro_batch, self.passes), key
         return self._encoder
 
@@ -404,7 +405,10 @@ class AnomalyCLIP(nn.Module):
                 emb_size=self.emb_size, depth=self.depth, heads=self.heads,
                 num_segments=self.num_segments, seg_length=self.seg_length,
                 concat_features=self.concat_features, feature_dim=ARCHS[self.arch]["embed_dim"])
-            self._scorer, self._scorer_key = engine.TemporalScorer(packed, passes=self.passes), key
+            # passes = 2 (f16f8 operands) exists for the image encoder's GEMMs only; the temporal
+            # stage (0.1 % of the work) then runs its fp32-faithful three-pass mode
+            self._scorer = engine.TemporalScorer(packed, passes=3 if self.passes == 2 else self.passes)
+            self._scorer_key = key
         return self._scorer
 
     @torch.no_grad()

@@ -43,21 +43,93 @@ def split(x: torch.Tensor, ld_out: Optional[int] = None,
     return out
 
 
+ACT_EXP = (4, 7, 0)   # (e_main, e_res, e_coarse) of f16f8 activations (csrc/split.cuh)
+WGT_EXP_RES = 4
+
+
+class F16F8:
+    """An fp32 [rows, ld] tensor in the f16f8 operand encoding (include/aclip_b200.h): one uint8
+    buffer of 4 * rows * ld bytes = fp16 plane H | e4m3 plane L | e4m3 plane C.  `exp` is e_main."""
+
+    def __init__(self, rows: int, ld: int, device, exp: int = ACT_EXP[0]) -> None:
+        if ld % 16 != 0:
+            raise ValueError("f16f8 rows must be a multiple of 16 elements wide")
+        self.rows, self.ld, self.exp = rows, ld, exp
+        self.buf = torch.empty(4 * rows * ld, dtype=torch.uint8, device=device)
+
+    @property
+    def plane_stride(self) -> int:
+        return self.rows * self.ld
+
+    def data_ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def planes(self):
+        """(H fp16, L e4m3, C e4m3) views [rows, ld]."""
+        P = self.plane_stride
+        return (self.buf[: 2 * P].view(torch.float16).reshape(self.rows, self.ld),
+                self.buf[2 * P: 3 * P].view(torch.float8_e4m3fn).reshape(self.rows, self.ld),
+                self.buf[3 * P:].view(torch.float8_e4m3fn).reshape(self.rows, self.ld))
+
+    def decode(self, e_res: int = ACT_EXP[1]) -> torch.Tensor:
+        """H + L back to fp64 values (what the GEMM effectively multiplies)."""
+        h, l, _ = self.planes()
+        return (h.double() + l.to(torch.float32).double() * 2.0 ** -e_res) * 2.0 ** -self.exp
+
+
+def weight_exponent(w: torch.Tensor) -> int:
+    """e_main of a weight tensor: max|w| * 2^e in (2^14, 2^15]  (fp16 main plane stays finite)."""
+    import math
+    m = float(w.abs().max())
+    return 15 - math.ceil(math.log2(m)) if m > 0 else 0
+
+
+def encode_f16f8(x: torch.Tensor, *, weight: bool = False, ld_out: Optional[int] = None) -> F16F8:
+    """fp32 [rows, cols] -> f16f8 planes; weight=True picks the per-tensor exponent."""
+    x = _f32c(x, "x")
+    rows, cols = x.reshape(-1, x.shape[-1]).shape
+    ld = ld_out if ld_out is not None else (cols + 15) // 16 * 16
+    if weight:
+        e = weight_exponent(x)
+        exps = (e, WGT_EXP_RES, e - ACT_EXP[1])
+    else:
+        exps = ACT_EXP
+    out = F16F8(rows, ld, x.device, exps[0])
+    lib = _lib.load()
+    _lib.check(lib.aclip_encode_f16f8(x.data_ptr(), rows, cols, cols, out.data_ptr(), ld,
+                                      out.plane_stride, exps[0], exps[1], exps[2], _stream()))
+    return out
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, res_mod: int = 0,
          out_f32: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
          want_split: bool = False, passes: int = 3, K: Optional[int] = None,
          conv: Optional[tuple] = None, row_map: Optional[tuple] = None, out_rows: Optional[int] = None,
-         max_ctas: int = 0, kernel: int = 0) -> torch.Tensor:
+         max_ctas: int = 0, kernel: int = 0, out_enc: int = 0) -> torch.Tensor:
     """out = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: split [2, M, lda] (linear) or split NHWC grid [2, S, H, W, C] with conv=(S, H, W, C).
     w: split [2, N, ldw].
+    passes=2: a and w are `F16F8` operands; out_enc=1 with want_split returns an `F16F8` output.
     """
     lib = _lib.load()
     g = GemmArgs()
-    N = w.shape[1]
-    if conv is not None:
+    if passes == 2:
+        if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
+            raise TypeError("gemm(passes=2) needs F16F8 operands")
+        N, M = w.rows, a.rows
+        Kk = K if K is not None else a.ld
+        g.lda, g.ldw = a.ld, w.ld
+        g.a_plane_stride, g.w_plane_stride = a.plane_stride, w.plane_stride
+        g.out_scale = 2.0 ** -(a.exp + w.exp)
+        dev = a.buf.device
+    else:
+        N = w.shape[1]
+        dev = a.device
+    if passes == 2:
+        pass
+    elif conv is not None:
         S, H, Wd, Cc = conv
         M, Kk = S * H * Wd, 9 * Cc
         g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
@@ -68,9 +140,11 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.lda = a.stride(1)
     g.a, g.w = a.data_ptr(), w.data_ptr()
     g.M, g.N, g.K = M, N, Kk
-    g.ldw = w.stride(1)
-    g.a_plane_stride, g.w_plane_stride = a.stride(0), w.stride(0)
+    if passes != 2:
+        g.ldw = w.stride(1)
+        g.a_plane_stride, g.w_plane_stride = a.stride(0), w.stride(0)
     g.passes = passes
+    g.out_enc = out_enc
     g.bias = _ptr(bias)
     g.act = act
     g.res_mod = res_mod
@@ -78,13 +152,18 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.residual, g.ldr = residual.data_ptr(), residual.stride(-2)
     rows = out_rows if out_rows is not None else M
     if out_f32 is None and out_split is None:
-        if want_split:
-            out_split = torch.empty((2, rows, N), dtype=torch.bfloat16, device=a.device)
+        if want_split and out_enc == 1:
+            out_split = F16F8(rows, N, dev)
+        elif want_split:
+            out_split = torch.empty((2, rows, N), dtype=torch.bfloat16, device=dev)
         else:
-            out_f32 = torch.empty((rows, N), dtype=torch.float32, device=a.device)
+            out_f32 = torch.empty((rows, N), dtype=torch.float32, device=dev)
     if out_f32 is not None:
         g.out_f32, g.ldc = out_f32.data_ptr(), out_f32.stride(-2)
-    if out_split is not None:
+    if isinstance(out_split, F16F8):
+        g.out_split, g.ld_split = out_split.data_ptr(), out_split.ld
+        g.split_plane_stride = out_split.plane_stride
+    elif out_split is not None:
         g.out_split, g.ld_split = out_split.data_ptr(), out_split.stride(1)
         g.split_plane_stride = out_split.stride(0)
     if row_map is not None:
@@ -96,30 +175,42 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5,
-              chan_mode: bool = False, want_f32: bool = True, want_split: bool = False):
-    """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std)."""
+              chan_mode: bool = False, want_f32: bool = True, want_split: bool = False,
+              out_enc: int = 0):
+    """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std).
+    out_enc=1: the split output is an `F16F8` activation tensor."""
     x = _f32c(x, "x")
     rows, D = x.reshape(-1, x.shape[-1]).shape
     out_f32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
-    out_split = torch.empty((2, rows, D), dtype=torch.bfloat16, device=x.device) if want_split else None
+    out_split = None
+    if want_split:
+        out_split = F16F8(rows, D, x.device) if out_enc == 1 else \
+            torch.empty((2, rows, D), dtype=torch.bfloat16, device=x.device)
+    plane = 0 if out_split is None else (out_split.plane_stride if out_enc == 1 else out_split.stride(0))
     lib = _lib.load()
     _lib.check(lib.aclip_layernorm(
         x.data_ptr(), rows, D, D, _f32c(gamma, "gamma").data_ptr(), _f32c(beta, "beta").data_ptr(),
-        eps, 1 if chan_mode else 0, _ptr(out_f32), D, _ptr(out_split), D,
-        out_split.stride(0) if out_split is not None else 0, _stream()))
+        eps, 1 if chan_mode else 0, _ptr(out_f32), D,
+        out_split.data_ptr() if out_split is not None else None, D, plane, out_enc, _stream()))
     if want_f32 and want_split:
         return out_f32, out_split
     return out_f32 if want_f32 else out_split
 
 
-def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int, kernel: int = 0) -> torch.Tensor:
-    """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64]."""
+def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int, kernel: int = 0,
+                  out_enc: int = 0):
+    """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64] (out_enc=1: `F16F8`)."""
     W = heads * 64
-    out = torch.empty((2, B * L, W), dtype=torch.bfloat16, device=qkv_split.device)
     lib = _lib.load()
+    if out_enc == 1:
+        out = F16F8(B * L, W, qkv_split.device)
+        plane, ld = out.plane_stride, W
+    else:
+        out = torch.empty((2, B * L, W), dtype=torch.bfloat16, device=qkv_split.device)
+        plane, ld = out.stride(0), out.stride(1)
     _lib.check(lib.aclip_vit_attention(qkv_split.data_ptr(), qkv_split.stride(0),
                                        qkv_split.stride(1), B, L, heads, out.data_ptr(),
-                                       out.stride(0), out.stride(1), kernel, _stream()))
+                                       plane, ld, kernel, out_enc, _stream()))
     return out
 
 

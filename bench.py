@@ -33,14 +33,23 @@ VIT_GFLOP_PER_FRAME = 35.127      # SURVEY 8d / BASELINE.md 2 (algorithmic, fp32
 TEMPORAL_MFLOP_PER_FRAME = 40.2   # ShanghaiTech configuration
 
 
-def _workload_config(n_gpus: int, micro_batch: int = 256) -> dict:
+PRECISION = {
+    3: ("bf16x3-split operands, f32 accumulate/residual",
+        "split-bf16 x3 tensor-core passes, fp32 accumulate (parity mode)"),
+    2: ("f16 + e4m3 cross-term operands (2 pass-equivalents), f32 accumulate/residual",
+        "fp16 main product + two e4m3 cross-term products per GEMM (2 bf16-pass equivalents of "
+        "tensor time), fp32 accumulate (parity mode); attention and the temporal stage: split-bf16 x3"),
+}
+
+
+def _workload_config(n_gpus: int, micro_batch: int = 256, passes: int = 3) -> dict:
     return {
         "workload": ("configs[2]: ShanghaiTech-shaped raw frames 224x224 uint8, 512 frames/step/GPU "
                      "(2 ViT micro-batches of 256 = one 32x16 temporal unit), full ViT-B/16 + selector "
                      "+ temporal + score path"),
         "frames_per_step_per_gpu": FRAMES_PER_STEP,
         "vit_micro_batch": micro_batch,
-        "precision": "split-bf16 x3 tensor-core passes, fp32 accumulate (parity mode)",
+        "precision": PRECISION[passes][1],
         "l2": "inputs rotate over 4 frame buffers (308 MB) and activations are ~0.9 GB per micro-batch, both > 126 MB L2",
         "parallelism": f"dp{n_gpus} over sub-videos, one exchange of score rows per step",
     }
@@ -229,7 +238,7 @@ def run_b200(args) -> None:
                       num_segments=cfg.num_segments, seg_length=cfg.seg_length,
                       concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=cfg.stride,
                       load_from_features=False, ncrops=cfg.ncrops, build_text_tower=False,
-                      micro_batch=args.micro_batch, passes=3)
+                      micro_batch=args.micro_batch, passes=args.passes)
     missing, unexpected = net.load_state_dict(syn.make_state_dict(cfg, with_vit=True), strict=False)
     assert not unexpected and not missing, (missing, unexpected)
     net.set_text_features(syn.make_text_features(cfg))
@@ -356,13 +365,16 @@ def run_b200(args) -> None:
         # capture profiles/r1_ncu_full_block_final.json; the algorithmic figure is next to it
         "traffic": 684e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(gemm["launches"], 1),
-        "passes": 3, "tensor_pipe_issued_tflops": 3 * achieved,
-        "tensor_pipe_issued_frac": 3 * achieved / peaks["tf_sustained"],
+        "passes": args.passes, "tensor_pipe_issued_tflops": args.passes * achieved,
+        "tensor_pipe_issued_frac": args.passes * achieved / peaks["tf_sustained"],
         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
         "share_of_step_kernel_time": gemm["ms"] / total_kernel_ms,
-        "note": "achieved counts ALGORITHMIC flops (2MNK once); every product is issued as 3 bf16 "
-                "MMA passes (hi*hi + lo*hi + hi*lo) to meet the 1e-3 fp32 parity bar, so the tensor "
-                "pipe executes 3x this figure",
+        "note": ("achieved counts ALGORITHMIC flops (2MNK once); every product is issued as 3 bf16 "
+                 "MMA passes (hi*hi + lo*hi + hi*lo) to meet the 1e-3 fp32 parity bar, so the tensor "
+                 "pipe executes 3x this figure") if args.passes == 3 else
+                ("achieved counts ALGORITHMIC flops (2MNK once); every product is issued as one fp16 "
+                 "MMA pass plus two e4m3 MMA passes at twice the rate (x_H w_H + x_L w_C + x_C w_L) to "
+                 "meet the 1e-3 fp32 parity bar: 2 bf16-pass equivalents of tensor-pipe time"),
     }
     breakdown = {name: {"ms": round(k["ms"], 4), "launches": k["launches"],
                         "share": round(k["ms"] / total_kernel_ms, 4),
@@ -393,8 +405,9 @@ def run_b200(args) -> None:
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
             "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16x3-split operands, f32 accumulate/residual", "data": "synthetic",
-            "config": dict(_workload_config(n_gpus, args.micro_batch), exchange=transport), "clocks": clocks,
+            "dtype": PRECISION[args.passes][0], "data": "synthetic",
+            "config": dict(_workload_config(n_gpus, args.micro_batch, args.passes), exchange=transport),
+            "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 3 * 224 * 224,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * width * 4 * n_gpus},
@@ -434,6 +447,9 @@ def main() -> None:
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
+    ap.add_argument("--passes", type=int, choices=(2, 3), default=3,
+                    help="GEMM operand mode of the image encoder, both fp32-faithful: 3 = split-bf16 x3, "
+                         "2 = fp16 + e4m3 cross terms (two pass-equivalents)")
     ap.add_argument("--torch-gpu-baseline", action="store_true",
                     help="also time the reference arithmetic as stock PyTorch ops ON THE GPU (fp32 and "
                          "TF32-allowed): the bar a hand-written path has to beat (SURVEY 8d)")

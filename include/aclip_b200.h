@@ -22,6 +22,13 @@
  *     of the calling thread's last failure. Nothing throws across this boundary.
  *   - "split" tensors carry an fp32 value as two bf16 planes (hi, lo): hi = bf16(x),
  *     lo = bf16(x - hi); plane 0 is hi, plane 1 is lo, `plane_stride` elements apart.
+ *   - "f16f8" tensors (GEMM passes = 2) carry an fp32 value v as three planes in the same 4 bytes
+ *     per element: H = fp16(v * 2^e_main) at byte 0, L = e4m3((v * 2^e_main - H) * 2^e_res) at byte
+ *     2 * plane_stride, C = e4m3(v * 2^e_coarse) at byte 3 * plane_stride.  The GEMM accumulates
+ *     x_H w_H (fp16 MMA) + x_L w_C + x_C w_L (e4m3 MMAs at twice the rate) = 2^(ex+ew) x w, i.e. two
+ *     pass-equivalents instead of the three bf16 passes at the same ~1e-5 end-to-end error.
+ *     Activations use (e_main, e_res, e_coarse) = (4, 7, 0); a weight tensor packed with exponent
+ *     ew uses (ew, 4, ew - 7) with ew chosen so that max|w| * 2^ew lies in (2^14, 2^15].
  */
 #ifndef ACLIP_B200_H_
 #define ACLIP_B200_H_
@@ -68,6 +75,11 @@ int aclip_timing_collect(AclipTimingRow* rows, int max_rows);
 int aclip_split_f32(const float* in, long long rows, int cols, int ld_in, void* out_split,
                     int ld_out, long long plane_stride, void* stream);
 
+/* fp32 [rows][cols] -> f16f8 planes [rows][ld_out] (ld_out and plane_stride multiples of 16). */
+int aclip_encode_f16f8(const float* in, long long rows, int cols, int ld_in, void* out,
+                       int ld_out, long long plane_stride, int e_main, int e_res, int e_coarse,
+                       void* stream);
+
 /* (x - centroid) of fp32 feature rows [rows][D] -> split-bf16 rows of pitch ld_out, regrouped from
  * the caller's "(b n s l)" order to sub-video order "(b s) n l" (temporal_model.py:46-53);
  * n = s = l = 1 keeps the order.  Replaces the two centroid subtractions of the reference
@@ -80,7 +92,7 @@ int aclip_center_regroup(const float* feats, long long rows, int D, const float*
  * [2][B*(R/P)^2][3*P*P] (split-bf16) for the patch-embedding GEMM (clip/model.py:246-252,267). */
 int aclip_patchify(const void* frames, int frames_are_u8, int B, int R, int P,
                    const float* mean3_host, const float* std3_host, void* out_split,
-                   long long plane_stride, void* stream);
+                   long long plane_stride, int out_enc, void* stream);
 
 /* Pillow-exact bicubic resize + centre crop of decoded frames (H x W x 3 uint8) to planar
  * (3, size, size) uint8: the reference's GroupScale(224, BICUBIC) + GroupCenterCrop(224)
@@ -100,7 +112,8 @@ typedef struct AclipGemmArgs {
   int M, N, K;    /* C[M,N] = A[M,K] * W[N,K]^T ; conv3x3: M = S*H*W, K = 9*C            */
   int lda, ldw;   /* row pitches in elements, multiples of 8                              */
   long long a_plane_stride, w_plane_stride; /* elements between hi and lo plane          */
-  int passes;     /* 3 = split-bf16 (fp32-faithful), 1 = plain bf16 (hi plane only)      */
+  int passes;     /* 3 = split-bf16 (fp32-faithful), 1 = plain bf16 (hi plane only),
+                     2 = f16f8 operands (fp32-faithful, CTA-pair kernel, N % 256 == 0)     */
   int a_mode;     /* 0 linear, 1 conv3x3 (zero padding 1, stride 1)                      */
   int conv_c, conv_h, conv_w, conv_s; /* conv3x3: channels, grid height, width, images  */
   /* epilogue: out = act(acc + bias) + residual */
@@ -119,16 +132,21 @@ typedef struct AclipGemmArgs {
   int row_group, row_group_stride, row_offset;
   int max_ctas;          /* 0 = one persistent CTA per SM */
   int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256) */
+  float out_scale;       /* passes = 2: 2^-(e_act + e_weight) applied to the accumulator; 0 = 1 */
+  int out_enc;           /* encoding of out_split: 0 = bf16 hi/lo, 1 = f16f8 activation planes */
 } AclipGemmArgs;
 
 /* tcgen05 / TMA GEMM with fused epilogue. N must be a multiple of 32, K a multiple of 8. */
 int aclip_gemm(const AclipGemmArgs* args, void* stream);
 
-/* nn.LayerNorm (mode 0, clip/model.py:174-180) or axial_attention's ChanLayerNorm (mode 1:
+/* out_enc (here and below): encoding of the split output, 0 = bf16 hi/lo planes, 1 = f16f8
+ * activation planes (the A operand of a passes = 2 GEMM).
+ * nn.LayerNorm (mode 0, clip/model.py:174-180) or axial_attention's ChanLayerNorm (mode 1:
  * (x-mean)/(std+eps)) over rows of D fp32 values; writes fp32 and/or split-bf16 rows. */
 int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
                     const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
-                    void* out_split, long long ld_split, long long plane_stride, void* stream);
+                    void* out_split, long long ld_split, long long plane_stride, int out_enc,
+                    void* stream);
 
 /* softmax(Q K^T / 8) V for B frames of L tokens, `heads` heads of 64 dims; qkv_split is the
  * split-bf16 [2][B*L][ld_in] output of the in_proj GEMM (q | k | v), out_split [2][B*L][ld_out].
@@ -136,7 +154,7 @@ int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const 
  * kernel: 0 = default (tcgen05/TMEM kernel), 1 = warp-level mma.sync kernel, 2 = tcgen05 kernel. */
 int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                         int heads, void* out_split, long long out_plane_stride, int ld_out,
-                        int kernel, void* stream);
+                        int kernel, int out_enc, void* stream);
 
 /* Axial self-attention over fp32 qkv rows [sub_videos*n*l][3E] in sub-video order; axis 0 = along
  * the n segments, axis 1 = along the l frames.  Output split-bf16 [2][rows][E].
@@ -156,6 +174,9 @@ typedef struct AclipVitBlock {      /* one ResidualAttentionBlock, clip/model.py
   const void* out_w;  const float* out_b;   /* attn.out_proj.weight split [2][W][W]   */
   const void* fc_w;   const float* fc_b;    /* mlp.c_fc.weight      split [2][4W][W]  */
   const void* proj_w; const float* proj_b;  /* mlp.c_proj.weight    split [2][W][4W]  */
+  /* passes = 2 only: the four weights are f16f8 planes and *_s = 2^-(4 + e_weight) is the
+   * accumulator scale of that GEMM (4 = the activations' e_main); ignored otherwise */
+  float qkv_s, out_s, fc_s, proj_s;
 } AclipVitBlock;
 
 typedef struct AclipVitWeights {    /* VisionTransformer, clip/model.py:233-264 */
@@ -166,6 +187,7 @@ typedef struct AclipVitWeights {    /* VisionTransformer, clip/model.py:233-264 
   const float *ln_pre_g, *ln_pre_b, *ln_post_g, *ln_post_b;
   const void* proj_w;                 /* proj^T split [2][output_dim][W] */
   const AclipVitBlock* blocks;        /* host array [layers] */
+  float conv1_s, proj_s;              /* passes = 2: accumulator scales of conv1_w / proj_w */
 } AclipVitWeights;
 
 size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
@@ -175,7 +197,9 @@ size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
  * ToTensor + Normalize(mean3_host, std3_host) (src/utils/augmentations.py:21-34) run on the GPU.
  * Frames are processed in micro-batches of `micro_batch` through `workspace`
  * (>= aclip_vit_workspace_bytes(w, micro_batch) bytes, 1024-byte aligned).
- * passes = 3: split-bf16 GEMMs (fp32-faithful, the parity mode); passes = 1: plain bf16 GEMMs. */
+ * passes = 3: split-bf16 GEMMs (fp32-faithful, the parity mode); passes = 1: plain bf16 GEMMs;
+ * passes = 2: f16f8 operands (fp32-faithful at two pass-equivalents; the weights in `w` must have
+ * been packed with aclip_encode_f16f8 and width / output_dim must be multiples of 256). */
 int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
                       long long num_frames, int micro_batch, const float* mean3_host,
                       const float* std3_host, float* features_out, void* workspace,

@@ -64,6 +64,19 @@ def main():
             res.append({"op": f"gemm_{name}", "kernel": kern, "ms": round(ms, 4),
                         "algo_tflops": round(fl / ms / 1e9, 1), "issued_tflops": round(3 * fl / ms / 1e9, 1)})
             print(json.dumps(res[-1]), flush=True)
+        # f16f8 operands: fp16 main product + e4m3 cross terms (2 pass-equivalents), CTA-pair kernel
+        a8 = ops.encode_f16f8(torch.randn(M, K, device=dev))
+        w8 = ops.encode_f16f8(torch.randn(N, K, device=dev) * 0.03, weight=True)
+        if kw.get("split"):
+            extra = dict(out_split=ops.F16F8(M, N, dev), out_enc=1) if kw.get("act") else \
+                dict(out_split=torch.empty(2, M, N, dtype=torch.bfloat16, device=dev))
+        ms = timeit(lambda: ops.gemm(a8, w8, bias=bias, act=kw.get("act", 0), passes=2, **extra),
+                    args.iters, flush)
+        fl = 2.0 * M * N * K
+        res.append({"op": f"gemm_{name}", "kernel": "f16f8", "ms": round(ms, 4),
+                    "algo_tflops": round(fl / ms / 1e9, 1),
+                    "bf16_pass_equiv_tflops": round(2 * fl / ms / 1e9, 1)})
+        print(json.dumps(res[-1]), flush=True)
 
     if not args.only or "gemm" in args.only:
         gemm_case("qkv", 3 * W, W, split=True)

@@ -184,3 +184,73 @@ def test_gemm_random_shapes(ops):
         ref = a.double() @ w.double().T + bias.double()
         assert _rel(out, ref + res.double()) < 3e-5, (M, N, K)
         assert _rel(_unsplit(s), ref) < 3e-5, (M, N, K)
+
+
+# ---------------------------------------------------------------------------------------------
+# f16f8 operands (passes = 2): fp16 main product + e4m3 cross terms, two pass-equivalents
+# ---------------------------------------------------------------------------------------------
+def _emulate_f16f8(x, e_main, e_res, e_coarse):
+    """torch restatement of csrc/split.cuh:f16f8_pack2 -> (H fp16, L e4m3, C e4m3)."""
+    xm = x.float() * 2.0 ** e_main
+    h = xm.clamp(-65504, 65504).half()
+    l = ((xm - h.float()) * 2.0 ** e_res).clamp(-448, 448).to(torch.float8_e4m3fn)
+    c = (x.float() * 2.0 ** e_coarse).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return h, l, c
+
+
+def test_encode_f16f8_planes(ops):
+    torch.manual_seed(3)
+    x = torch.randn(131, 200, device="cuda") * 2
+    x[0, :4] = torch.tensor([5000.0, -7000.0, 1e-6, 0.0], device="cuda")  # saturation / tiny / zero
+    t = ops.encode_f16f8(x, ld_out=208)
+    h, l, c = t.planes()
+    eh, el, ec = _emulate_f16f8(x, *ops.ACT_EXP)
+    assert torch.equal(h[:, :200], eh) and torch.all(h[:, 200:] == 0)
+    assert torch.equal(l[:, :200].view(torch.uint8), el.view(torch.uint8))
+    assert torch.equal(c[:, :200].view(torch.uint8), ec.view(torch.uint8))
+    ok = x.abs() < 4000
+    assert _rel(t.decode()[:, :200][ok], x[ok]) < 3e-5
+    w = torch.randn(64, 256, device="cuda") * 0.03
+    tw = ops.encode_f16f8(w, weight=True)
+    assert 2 ** 14 < float(w.abs().max()) * 2.0 ** tw.exp <= 2 ** 15
+    assert _rel(tw.decode(e_res=ops.WGT_EXP_RES), w) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 256, 768), (1000, 768, 768),
+                                   (197 * 8, 2304, 768), (129, 768, 3072), (4096, 3072, 768),
+                                   (50432, 768, 768)])
+def test_gemm_f16f8(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    out = ops.gemm(ops.encode_f16f8(a), ops.encode_f16f8(w, weight=True), passes=2)
+    torch.cuda.synchronize()
+    ref = a.double() @ w.double().T
+    err = _rel(out, ref)
+    out3 = ops.gemm(ops.split(a), ops.split(w), passes=3)
+    print(f"gemm f16f8 M={M} N={N} K={K}: rel err {err:.3e} (bf16x3: {_rel(out3, ref):.3e})")
+    assert err < 3e-5
+
+
+def test_gemm_f16f8_epilogue_and_encoded_output(ops):
+    torch.manual_seed(5)
+    M, N, K = 777, 768, 512
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    ea, ew = ops.encode_f16f8(a), ops.encode_f16f8(w, weight=True)
+    pre = a.double() @ w.double().T + bias.double()
+    out = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, residual=res, passes=2)
+    assert _rel(out, pre * torch.sigmoid(1.702 * pre) + res.double()) < 3e-5
+    # hidden activations leave the epilogue already encoded for the next GEMM (c_fc -> c_proj)
+    enc = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=2, want_split=True, out_enc=1)
+    f32 = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=2)
+    h, l, c = enc.planes()
+    eh, el, ec = _emulate_f16f8(f32, *ops.ACT_EXP)
+    assert torch.equal(h, eh)
+    assert torch.equal(l.view(torch.uint8), el.view(torch.uint8))
+    assert torch.equal(c.view(torch.uint8), ec.view(torch.uint8))
+    # bf16 hi/lo output from f16f8 operands (in_proj feeds the attention kernel)
+    s = ops.gemm(ea, ew, bias=bias, passes=2, want_split=True)
+    assert _rel(_unsplit(s), pre) < 3e-5

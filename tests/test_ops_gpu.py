@@ -53,6 +53,45 @@ def test_vit_attention(ops, B, L, heads, kernel):
     assert_parity(out, ref, f"vit attention kernel={kernel} B={B} L={L} h={heads}", rtol=1e-4)
 
 
+def _f16f8_reference_planes(y, ops):
+    """torch restatement of the activation encoding (csrc/split.cuh) of fp32 values y."""
+    e_main, e_res, e_coarse = ops.ACT_EXP
+    ym = y.float() * 2.0 ** e_main
+    h = ym.clamp(-65504, 65504).half()
+    l = ((ym - h.float()) * 2.0 ** e_res).clamp(-448, 448).to(torch.float8_e4m3fn)
+    c = (y.float() * 2.0 ** e_coarse).clamp(-448, 448).to(torch.float8_e4m3fn)
+    return h, l, c
+
+
+@pytest.mark.parametrize("rows,D", [(1, 768), (197 * 3, 768), (1000, 256)])
+def test_layernorm_f16f8_output(ops, rows, D):
+    """The f16f8 output planes are exactly the encoding of the kernel's own fp32 output."""
+    torch.manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    g = 1 + 0.2 * torch.randn(D, device="cuda")
+    b = 0.1 * torch.randn(D, device="cuda")
+    out, enc = ops.layernorm(x, g, b, want_f32=True, want_split=True, out_enc=1)
+    h, l, c = enc.planes()
+    eh, el, ec = _f16f8_reference_planes(out, ops)
+    assert torch.equal(h, eh)
+    assert torch.equal(l.view(torch.uint8), el.view(torch.uint8))
+    assert torch.equal(c.view(torch.uint8), ec.view(torch.uint8))
+    assert_parity(enc.decode(), out, "layernorm f16f8 decode", rtol=3e-5)
+
+
+@pytest.mark.parametrize("B,L,heads", [(1, 197, 12), (3, 197, 4), (2, 5, 2), (2, 130, 4), (40, 197, 12)])
+def test_vit_attention_f16f8_output(ops, B, L, heads):
+    torch.manual_seed(B * 1000 + L)
+    W = heads * 64
+    s = ops.split(torch.randn(B * L, 3 * W, device="cuda") * 1.5)
+    ref = _unsplit(ops.vit_attention(s, B, L, heads))          # bf16 hi/lo output of the same kernel
+    enc = ops.vit_attention(s, B, L, heads, out_enc=1)
+    assert_parity(enc.decode(), ref, f"vit attention f16f8 B={B} L={L} h={heads}", rtol=3e-5)
+    h, l, c = enc.planes()
+    # coarse plane = e4m3 of the value itself (within one e4m3 ulp of the decoded value)
+    assert_parity(c.float(), ref.clamp(-448, 448), "coarse plane", rtol=7e-2)
+
+
 @pytest.mark.parametrize("E,heads", [(256, 8), (128, 8), (64, 2)])
 @pytest.mark.parametrize("axis", [0, 1])
 def test_axial_attention(ops, E, heads, axis):

@@ -16,7 +16,7 @@ GOLD = Path(__file__).resolve().parent / "golden"
 
 def _encoder(sd, heads=None, micro_batch=256, passes=3):
     from anomalyclip_b200.engine import PackedVit, VitEncoder
-    return VitEncoder(PackedVit(sd, torch.device("cuda"), heads=heads), micro_batch, passes)
+    return VitEncoder(PackedVit(sd, torch.device("cuda"), heads=heads, passes=passes), micro_batch, passes)
 
 
 def test_small_vit_matches_reference_golden():
@@ -70,6 +70,44 @@ def test_bf16_single_pass_mode_is_less_accurate_but_close(vitb16):
     err = rel_l2(out, ref)
     print(f"passes=1 rel-L2 {err:.3e}")
     assert 1e-4 < err < 5e-2  # the plain-bf16 mode misses the 1e-3 bar: this is why passes=3 is the default
+
+
+# ---- passes = 2: f16f8 operands (fp16 main product + e4m3 cross terms), two pass-equivalents
+def test_vit_b16_f16f8_mode_matches_oracle(vitb16):
+    sd, enc3 = vitb16
+    enc2 = _encoder(sd, passes=2)
+    torch.manual_seed(5)
+    frames = torch.randn(3, 3, 224, 224)
+    ref = oracle.vit_forward(sd, frames)
+    out = enc2(frames.cuda())
+    assert_parity(out, ref, "ViT-B/16 features, f16f8 GEMM operands")
+    from tests.parity import rel_l2
+    e2, e3 = rel_l2(out, ref), rel_l2(enc3(frames.cuda()), ref)
+    print(f"rel-L2 vs oracle: f16f8 {e2:.3e}, bf16x3 {e3:.3e}")
+    assert e2 < 1e-4   # two orders of magnitude inside the 1e-3 bar, like the three-pass mode
+    u8 = make_frames_u8(5, seed=3)
+    assert_parity(enc2(u8.cuda()), oracle.vit_forward(sd, normalise_frames(u8)),
+                  "ViT-B/16 features from uint8 frames, f16f8")
+    from anomalyclip_b200.engine import VitEncoder
+    assert torch.equal(enc2(u8.cuda()), VitEncoder(enc2.packed, micro_batch=2, passes=2)(u8.cuda()))
+
+
+def test_small_wide_vit_f16f8_mode():
+    sd = make_vit_weights(width=256, layers=2, patch=16, resolution=64, output_dim=256, seed=7)
+    torch.manual_seed(8)
+    frames = torch.randn(9, 3, 64, 64)
+    ref = oracle.vit_forward(sd, frames)
+    assert_parity(_encoder(sd, passes=2)(frames.cuda()), ref, "width-256 ViT, f16f8")
+
+
+def test_f16f8_mode_rejects_unsupported_shapes_and_mixed_packing():
+    from anomalyclip_b200._lib import AclipError
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    sd = make_vit_weights(width=128, layers=1, patch=16, resolution=32, output_dim=256, seed=7)
+    with pytest.raises(AclipError):   # width must be a multiple of 256 for the CTA-pair kernel
+        _encoder(sd, heads=2, passes=2)(torch.zeros(1, 3, 32, 32, device="cuda"))
+    with pytest.raises(AclipError):   # bf16-packed weights cannot be run with passes=2
+        VitEncoder(PackedVit(sd, torch.device("cuda"), heads=2), passes=2)
 
 
 def test_bad_inputs_raise():
