@@ -5,10 +5,12 @@ There is no fallback: if the library cannot be loaded, every operator raises.
 from __future__ import annotations
 
 import ctypes as C
+import os
 from pathlib import Path
 
 _PKG = Path(__file__).resolve().parent
-LIB_PATH = _PKG / "lib" / "libaclip_b200.so"
+# ACLIP_LIB: load another build of the same library (A/B timing of kernel changes on one box)
+LIB_PATH = Path(os.environ.get("ACLIP_LIB") or _PKG / "lib" / "libaclip_b200.so")
 
 ACLIP_OK = 0
 ACT_NONE, ACT_QUICKGELU, ACT_LEAKYRELU = 0, 1, 2

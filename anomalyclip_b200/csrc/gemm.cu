@@ -141,6 +141,60 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return ACLIP_OK;
 }
 
+template <int PASSES>
+static int launch_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA8,
+                       const CUtensorMap& tmB8, const GemmParams& p, int max_ctas,
+                       cudaStream_t stream) {
+  using Cfg = Gemm2Cfg<PASSES>;
+  auto kernel = gemm4_tcgen05_kernel<PASSES>;
+  static PerDeviceOnce once;
+  int once_dev;
+  if (once.need(once_dev)) {
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       Cfg::SMEM_BYTES));
+    once.mark(once_dev);
+  }
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  const int super_tiles = ((m_tiles + 1) / 2) * n_tiles;
+  // A persistent grid must be fully co-resident: clusters of four only fit where a GPC has four
+  // free SMs, so ask the driver how many can be active at once (per device, cached).
+  static std::atomic<int> max_clusters[64];
+  int cap = 0;
+  if (once_dev >= 0 && once_dev < 64) cap = max_clusters[once_dev].load(std::memory_order_relaxed);
+  if (cap == 0) {
+    cudaLaunchConfig_t cfg{};
+    cfg.gridDim = dim3(4 * (sm_count() / 4));
+    cfg.blockDim = dim3(Cfg::THREADS);
+    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+    cudaLaunchAttribute attr{};
+    attr.id = cudaLaunchAttributeClusterDimension;
+    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
+    cfg.attrs = &attr;
+    cfg.numAttrs = 1;
+    if (cudaOccupancyMaxActiveClusters(&cap, kernel, &cfg) != cudaSuccess || cap <= 0) {
+      cudaGetLastError();
+      cap = sm_count() / 4;
+    }
+    if (getenv("ACLIP_DEBUG") != nullptr) fprintf(stderr, "[aclip] four-CTA clusters co-resident: %d\n", cap);
+    if (once_dev >= 0 && once_dev < 64) max_clusters[once_dev].store(cap, std::memory_order_relaxed);
+  }
+  int clusters = max_ctas > 0 ? max_ctas / 4 : cap;
+  if (clusters > cap) clusters = cap;
+  if (clusters > super_tiles) clusters = super_tiles;
+  if (clusters < 1) clusters = 1;
+  timing_begin(KIND_GEMM, stream);
+  kernel<<<4 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA8, tmB8, p);
+  {
+    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
+    timing_end(KIND_GEMM, stream, 2.0 * p.M * (double)p.N * p.K,
+               4.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * (double)p.M * p.N);
+  }
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
+}
+
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
@@ -178,9 +232,15 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   // 128-wide tiles when they waste fewer padded columns than 256-wide ones (e.g. N = 128, 384)
   // CTA-pair kernel (256 x 256 tiles over two SMs) whenever N tiles evenly and there is enough
   // work to fill the machine; kernel = 1 / 2 forces the single-CTA / pair kernel (tests).
-  ACLIP_REQUIRE(g.kernel >= 0 && g.kernel <= 2, "gemm: kernel must be 0 (auto), 1 or 2");
-  ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
-  const bool pair = g.kernel == 2 || g.passes == 2 || (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
+  ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2 || g.kernel == 4,
+                "gemm: kernel must be 0 (auto), 1 (single CTA), 2 (CTA pair) or 4 (two pairs sharing W)");
+  ACLIP_REQUIRE((g.kernel != 2 && g.kernel != 4) || g.N % 256 == 0,
+                "gemm: the CTA-pair kernels need N %% 256 == 0");
+  ACLIP_REQUIRE(g.kernel != 4 || (g.passes != 1 && g.a_mode == 0),
+                "gemm: the four-CTA kernel needs passes 2 or 3 and a linear A operand");
+  const bool quad = g.kernel == 4;
+  const bool pair = quad || g.kernel == 2 || g.passes == 2 ||
+                    (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
   // more SMs share the K loop.  128 is also preferred when it wastes fewer padded columns.
@@ -215,6 +275,12 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.row_offset = g.row_offset;
   p.out_scale = g.out_scale > 0.0f ? g.out_scale : 1.0f;
   p.out_enc = g.out_enc;
+  {
+    // profiling experiments (results wrong by construction) only with the environment switch
+    const char* allow = getenv("ACLIP_PROFILING_EXPERIMENTS");
+    const char* dbg = getenv("ACLIP_GEMM_DEBUG");
+    p.debug = (allow != nullptr && allow[0] == '1' && dbg != nullptr) ? atoi(dbg) : 0;
+  }
   ACLIP_REQUIRE(g.out_enc == 0 || g.out_split == nullptr ||
                     (p.ld_split % 16 == 0 && g.split_plane_stride % 16 == 0),
                 "gemm: an f16f8 output needs a pitch and plane stride that are multiples of 16");
@@ -230,17 +296,20 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
       ACLIP_REQUIRE(ps >= rows * ld, "gemm: plane stride smaller than the operand");
       cuuint64_t dims_h[3] = {(cuuint64_t)g.K, rows, 1};
       cuuint64_t str_h[2] = {ld * 2, ld * 2 * rows};
-      cuuint32_t box_h[3] = {64, 128, 1};
+      // the four-CTA kernel fetches W in quarters of 64 rows, one plane per TMA box
+      const bool quarter = quad && op == 1;
+      cuuint32_t box_h[3] = {64, quarter ? 64u : 128u, 1};
       ACLIP_TRY(make_tmap(op == 0 ? &tmA : &tmB, base, 3, dims_h, str_h, box_h,
                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
       cuuint64_t dims_8[3] = {(cuuint64_t)g.K, rows, 2};
       cuuint64_t str_8[2] = {ld, ps};
-      cuuint32_t box_8[3] = {64, 128, 2};
+      cuuint32_t box_8[3] = {64, quarter ? 64u : 128u, quarter ? 1u : 2u};
       ACLIP_TRY(make_tmap(op == 0 ? &tmA8 : &tmB8, static_cast<const uint8_t*>(base) + 2 * ps, 3,
                           dims_8, str_8, box_8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
                           CU_TENSOR_MAP_SWIZZLE_64B));
     }
-    return launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
+    return quad ? launch_quad<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
+                : launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
   }
   if (g.a_mode == 0) {
     ACLIP_REQUIRE(g.lda % 8 == 0 && g.lda >= g.K, "gemm: lda=%d invalid for K=%d", g.lda, g.K);
@@ -276,11 +345,13 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     cuuint64_t strides[2] = {(cuuint64_t)g.ldw * 2, planes == 1 ? (cuuint64_t)g.ldw * 2 * g.N
                                                                 : (cuuint64_t)g.w_plane_stride * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)block_n, (cuuint32_t)planes};
+    if (quad) { box[1] = 64; box[2] = 1; }
     ACLIP_REQUIRE(planes == 1 || (g.w_plane_stride % 8 == 0 && g.w_plane_stride > 0),
                   "gemm: w_plane_stride must be a positive multiple of 8");
     ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box));
   }
 
+  if (quad) return launch_quad<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
   if (pair)
     return g.passes == 3 ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
                          : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);

@@ -57,6 +57,8 @@ struct GemmParams {
   int row_group, row_group_stride, row_offset;
   float out_scale;  // multiplies the accumulator before bias (f16f8 operands: 2^-(ex + ew)), else 1
   int out_enc;      // encoding of out_split: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes
+  int debug;        // profiling experiments only (ACLIP_PROFILING_EXPERIMENTS=1): 1 = issue no MMAs
+                    // (operand feed + epilogue only; results are wrong by construction)
 };
 
 template <int BLOCK_N_, int PASSES_>
@@ -84,43 +86,117 @@ struct GemmCfg {
                 "TMEM columns must be a power of two");
 };
 
-__device__ __forceinline__ float apply_act(float x, int act) {
-  if (act == ACT_QUICKGELU) {
-    // x * sigmoid(1.702 x)  (reference: clip/model.py:183-185)
-    return __fdividef(x, 1.0f + __expf(-1.702f * x));
-  } else if (act == ACT_LEAKYRELU) {
-    return x > 0.0f ? x : 0.01f * x;
-  }
-  return x;
+// x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x))   (reference: clip/model.py:183-185)
+// one multiply, ex2.approx, one add, rcp.approx, one multiply.
+__device__ __forceinline__ float quick_gelu(float x) {
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * -2.4554669595930157f));
+  return __fdividef(x, 1.0f + e);
 }
 
 // Epilogue of one 32-row x 32-column chunk per warp.  The accumulator comes out of TMEM with one
-// row per lane; bias and activation are applied in that layout, then the chunk is transposed through
-// a 4 KB per-warp staging buffer (16-byte pieces XOR-swizzled by the row) so that every global
-// access is row-contiguous: a load/store instruction touches 4 rows x 128 B instead of 32 rows x
-// 16 B.  In the transposed layout lane = (row & 3 within a group of 4 rows, 16-byte piece 0..7).
+// row per lane; scale, bias and activation are applied in that layout, then the chunk is transposed
+// through a 4 KB per-warp staging buffer (16-byte pieces XOR-swizzled by the row) so that every
+// global access is row-contiguous: a load/store instruction touches 4 rows x 128 B instead of 32
+// rows x 16 B.  In the transposed layout lane = (row & 3 within a group of 4 rows, 16-byte piece
+// 0..7).  The bias and residual loads are issued before the wait on the TMEM load so that their
+// latency overlaps it and the arithmetic; every warp-uniform option is tested once per chunk, not
+// once per row.
 constexpr int EPI_STAGE_BYTES = 32 * 128;
+
+// SPLIT: 0 = no split output, 1 = bf16 hi/lo planes, 2 = f16f8 activation planes
+template <bool F32, int SPLIT>
+__device__ __forceinline__ void epilogue_store(const GemmParams& p, const int (&orow)[8],
+                                               const float4 (&val)[8], int col, int lane,
+                                               const uint8_t* stage) {
+  const int piece = lane & 7;
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = i * 4 + (lane >> 3);
+    if (orow[i] >= 0) {
+      const float4 a = *reinterpret_cast<const float4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
+      const float4 v4 = make_float4(a.x + val[i].x, a.y + val[i].y, a.z + val[i].z, a.w + val[i].w);
+      if (F32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(orow[i]) * p.ldc + col) = v4;
+      if (SPLIT == 1) {
+        uint32_t h0, l0, h1, l1;
+        split_pack2(v4.x, v4.y, h0, l0);
+        split_pack2(v4.z, v4.w, h1, l1);
+        __nv_bfloat16* dst = p.out_split + static_cast<long long>(orow[i]) * p.ld_split + col;
+        *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
+        *reinterpret_cast<uint2*>(dst + p.split_plane_stride) = make_uint2(l0, l1);
+      } else if (SPLIT == 2) {
+        f16f8_store4_act(p.out_split, p.split_plane_stride,
+                         static_cast<long long>(orow[i]) * p.ld_split + col, v4.x, v4.y, v4.z, v4.w);
+      }
+    }
+  }
+}
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
                                                int m_base, int lane, uint8_t* stage) {
   uint32_t raw[32];
   ptx::tmem_ld_32x32(taddr, raw);
-  ptx::tmem_ld_wait();
-  if (m_base >= p.M) return;  // warp-uniform: the whole block is padding
-  float v[32];
+  // ---- everything that does not depend on the accumulator, while the TMEM load is in flight
+  float4 b4[8];
+  const bool has_bias = p.bias != nullptr;
+  if (has_bias) {
 #pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * p.out_scale;
-  if (p.bias != nullptr) {
-    const float4* b4 = reinterpret_cast<const float4*>(p.bias + n);
+    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+  } else {
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const float4 b = __ldg(b4 + j);
-      v[4 * j + 0] += b.x; v[4 * j + 1] += b.y; v[4 * j + 2] += b.z; v[4 * j + 3] += b.w;
+    for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  const int col = n + (lane & 7) * 4;
+  int orow[8];      // output row of the 8 rows this lane stores (-1: beyond M)
+  if (p.row_group_stride != 0) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m_base + i * 4 + (lane >> 3);
+      orow[i] = m < p.M ? (m / p.row_group) * p.row_group_stride + (m % p.row_group) + p.row_offset : -1;
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int m = m_base + i * 4 + (lane >> 3);
+      orow[i] = m < p.M ? m + p.row_offset : -1;
     }
   }
-  if (p.act != ACT_NONE) {
+  float4 val[8];    // residual (out_f32 may alias it: each lane reads exactly what it later writes)
 #pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = apply_act(v[j], p.act);
+  for (int i = 0; i < 8; ++i) val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (p.residual != nullptr && m_base < p.M) {
+    if (p.res_mod > 0) {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (orow[i] >= 0) {
+          const int m = m_base + i * 4 + (lane >> 3);
+          val[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(m % p.res_mod) * p.ldr + col);
+        }
+    } else {
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+        if (orow[i] >= 0)
+          val[i] = *reinterpret_cast<const float4*>(p.residual + static_cast<long long>(orow[i]) * p.ldr + col);
+    }
+  }
+  ptx::tmem_ld_wait();
+  if (m_base >= p.M) return;  // warp-uniform: the whole block is padding
+  // ---- accumulator * scale + bias, activation (one row per lane)
+  float v[32];
+  const float sc = p.out_scale;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    v[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), sc, b4[j].x);
+    v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), sc, b4[j].y);
+    v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), sc, b4[j].z);
+    v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), sc, b4[j].w);
+  }
+  if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+  } else if (p.act == ACT_LEAKYRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
   }
   __syncwarp();  // the previous chunk's readers are done with the staging buffer
 #pragma unroll
@@ -128,52 +204,15 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
     *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
         make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
   __syncwarp();
-  const int piece = lane & 7;
-  const int col = n + piece * 4;
-  // phase 1: all residual loads in flight before anything is stored (out_f32 may alias residual)
-  float4 val[8];
-  long long out_rows[8];
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3);
-    const int m = m_base + row;
-    out_rows[i] = -1;
-    if (m < p.M) {
-      long long out_row = m;
-      if (p.row_group_stride != 0)
-        out_row = static_cast<long long>(m / p.row_group) * p.row_group_stride + (m % p.row_group);
-      out_row += p.row_offset;
-      out_rows[i] = out_row;
-      val[i] = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (p.residual != nullptr) {
-        const long long res_row = p.res_mod > 0 ? (m % p.res_mod) : out_row;
-        val[i] = *reinterpret_cast<const float4*>(p.residual + res_row * p.ldr + col);
-      }
-    }
-  }
-  // phase 2: add the staged accumulator values and store row-contiguously
-#pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = i * 4 + (lane >> 3);
-    if (out_rows[i] >= 0) {
-      const float4 a = *reinterpret_cast<const float4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
-      const float4 v4 = make_float4(a.x + val[i].x, a.y + val[i].y, a.z + val[i].z, a.w + val[i].w);
-      if (p.out_f32 != nullptr)
-        *reinterpret_cast<float4*>(p.out_f32 + out_rows[i] * p.ldc + col) = v4;
-      if (p.out_split != nullptr) {
-        if (p.out_enc == 0) {
-          uint32_t h0, l0, h1, l1;
-          split_pack2(v4.x, v4.y, h0, l0);
-          split_pack2(v4.z, v4.w, h1, l1);
-          __nv_bfloat16* dst = p.out_split + out_rows[i] * p.ld_split + col;
-          *reinterpret_cast<uint2*>(dst) = make_uint2(h0, h1);
-          *reinterpret_cast<uint2*>(dst + p.split_plane_stride) = make_uint2(l0, l1);
-        } else {
-          f16f8_store4_act(p.out_split, p.split_plane_stride, out_rows[i] * p.ld_split + col, v4.x,
-                           v4.y, v4.z, v4.w);
-        }
-      }
-    }
+  // ---- add the residual to the staged values and store row-contiguously
+  const int kind = p.out_split == nullptr ? 0 : 1 + p.out_enc;
+  if (p.out_f32 != nullptr) {
+    if (kind == 0) epilogue_store<true, 0>(p, orow, val, col, lane, stage);
+    else if (kind == 1) epilogue_store<true, 1>(p, orow, val, col, lane, stage);
+    else epilogue_store<true, 2>(p, orow, val, col, lane, stage);
+  } else {
+    if (kind == 1) epilogue_store<false, 1>(p, orow, val, col, lane, stage);
+    else if (kind == 2) epilogue_store<false, 2>(p, orow, val, col, lane, stage);
   }
 }
 
@@ -471,16 +510,21 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           // descriptor low word counts 16-byte units: stage / plane / K-step offsets are adds
           const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
           const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
-          if (PASSES == 2) {
+          if (p.debug & 1) {
+            // feed-rate experiment: consume the stage without issuing MMAs
+          } else if (PASSES == 2) {
             // x_H w_H: four K=16 fp16 MMAs; x_L w_C and x_C w_L: two K=32 e4m3 MMAs each (the
-            // e4m3 planes L, C sit behind the fp16 plane, 64-byte rows, 8 KB apart)
+            // e4m3 tile sits behind the fp16 tile)
+            if (!(p.debug & 4)) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
+              for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
+                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
+                                         (kb | k) != 0 ? 1u : 0u);
+            }
             const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
             const uint64_t b_l0 = a_l0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
             constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
+            if (!(p.debug & 2))
 #pragma unroll
             for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
               ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
@@ -534,6 +578,191 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   ptx::tc_fence_before();
   ptx::cluster_sync();  // nobody leaves while the pair may still touch its smem / TMEM / barriers
+  if (warp == 1) {
+    ptx::tc_fence_after();
+    ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// Four-CTA variant: a cluster of two CTA pairs computes two M-adjacent 256 x 256 tiles against the
+// SAME W tile.  Each of the four CTAs fetches a quarter (64 rows) of the W tile per K block and
+// multicasts it to the CTA at its position in the other pair, so the W operand crosses the
+// L2 -> SM fabric once per cluster instead of once per pair: 96 KB instead of 128 KB of L2 reads per
+// pair and K block.  (The pair kernel at three stages is bound by the L2 -> SM throughput of
+// ~6300 B/clk as much as by the tensor pipe.)  Everything else -- roles, TMEM double buffering,
+// epilogue -- is the pair kernel's; the shared-memory slot of a stage is released only when BOTH
+// pairs' MMAs have consumed it (empty barriers count two multicast commits).
+template <int PASSES>
+__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(320, 1)
+gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
+                     const __grid_constant__ CUtensorMap tmB,
+                     const __grid_constant__ CUtensorMap tmA8,
+                     const __grid_constant__ CUtensorMap tmB8, const GemmParams p) {
+  using Cfg = Gemm2Cfg<PASSES>;
+  constexpr int STAGES = Cfg::STAGES;
+  static_assert(PASSES == 2 || PASSES == 3, "the four-CTA kernel carries two operand planes");
+
+  extern __shared__ uint8_t smem_raw[];
+  uint8_t* smem = reinterpret_cast<uint8_t*>(
+      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
+  uint64_t* empty_bar = full_bar + STAGES;
+  uint64_t* tfull_bar = empty_bar + STAGES;
+  uint64_t* tempty_bar = tfull_bar + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const uint32_t crank = ptx::cluster_ctarank();   // 0..3
+  const int pair = static_cast<int>(crank >> 1);    // which of the two M tiles
+  const int rank = static_cast<int>(crank & 1);     // position inside the pair, 0 = pair leader
+  const int cluster_id = blockIdx.x >> 2;
+  const int num_clusters = gridDim.x >> 2;
+  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * pair));
+  const uint16_t w_mask = static_cast<uint16_t>(0x5u << rank);  // this position in both pairs
+
+  if (warp == 0 && lane == 0) {
+    ptx::prefetch_tmap(&tmA);
+    ptx::prefetch_tmap(&tmB);
+    if (PASSES == 2) {
+      ptx::prefetch_tmap(&tmA8);
+      ptx::prefetch_tmap(&tmB8);
+    }
+    for (int s = 0; s < STAGES; ++s) {
+      ptx::mbar_init(&full_bar[s], 1);   // pair leader's producer (arrive.expect_tx)
+      ptx::mbar_init(&empty_bar[s], 2);  // one multicast tcgen05.commit from each pair
+    }
+    for (int a = 0; a < 2; ++a) {
+      ptx::mbar_init(&tfull_bar[a], 1);
+      ptx::mbar_init(&tempty_bar[a], 2 * Cfg::EPI_WARPS);
+    }
+    ptx::fence_mbar_init();
+  }
+  if (warp == 1) {
+    ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
+    ptx::tmem_relinquish_pair();
+  }
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
+  ptx::tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
+  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
+  const int total_tiles = ((m_tiles + 1) >> 1) * n_tiles;   // super-tiles of two M tiles
+
+  if (warp == 0) {
+    // ------------------------------------------------------------ TMA producer (all four CTAs)
+    if (lane == 0) {
+      uint32_t stage = 0, phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        // W rows of this CTA's position in the pair; this CTA fetches quarter `pair` of them
+        const int n0 = (t % n_tiles) * Cfg::BLOCK_N + rank * Cfg::CTA_N;
+        const int nq = n0 + pair * (Cfg::CTA_N / 2);
+        const int m0 = (((t / n_tiles) * 2 + pair) * 2 + rank) * Cfg::CTA_M;  // may lie beyond M: zero fill
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          const int k0 = kb * Cfg::BLOCK_K;
+          if (PASSES == 2) {
+            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
+            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], k0, m0, 0);
+            ptx::tma_load_3d_pair_mc(sb + pair * (Cfg::B_PLANE_BYTES / 2), &tmB, &full_bar[stage], k0, nq, 0, w_mask);
+            uint8_t* s8 = sb + Cfg::B_PLANE_BYTES + pair * (Cfg::B_PLANE_BYTES / 4);
+            ptx::tma_load_3d_pair_mc(s8, &tmB8, &full_bar[stage], k0, nq, 0, w_mask);
+            ptx::tma_load_3d_pair_mc(s8 + Cfg::B_PLANE_BYTES / 2, &tmB8, &full_bar[stage], k0, nq, 1, w_mask);
+          } else {
+            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
+            uint8_t* sq = sb + pair * (Cfg::B_PLANE_BYTES / 2);
+            ptx::tma_load_3d_pair_mc(sq, &tmB, &full_bar[stage], k0, nq, 0, w_mask);
+            ptx::tma_load_3d_pair_mc(sq + Cfg::B_PLANE_BYTES, &tmB, &full_bar[stage], k0, nq, 1, w_mask);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------------------------------------ MMA issuer (pair leaders)
+    if (rank == 0) {
+      const bool leader = ptx::elect_one();
+      constexpr uint32_t idesc = PASSES == 2 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
+                                             : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
+      const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
+      const uint64_t desc8 = ptx::make_kmajor_sw64_desc(ptx::smem_u32(smem));
+      uint32_t stage = 0, phase = 0;
+      uint32_t acc = 0, acc_phase = 0;
+      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        ptx::tc_fence_after();
+        const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
+        for (int kb = 0; kb < p.num_kb; ++kb) {
+          ptx::mbar_wait(&full_bar[stage], phase);
+          ptx::tc_fence_after();
+          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+          if (p.debug & 1) {
+          } else if (PASSES == 2) {
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
+            const uint64_t b_l0 = a_l0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+            constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
+              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
+              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + kCoarse + 2 * k, b_l0 + 2 * k, idesc, 1u);
+            }
+          } else {
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+              const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+            }
+          }
+          ptx::mma_commit_pair_if(leader, &empty_bar[stage], 0xF);  // one of two arrivals, all four CTAs
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        ptx::mma_commit_pair_if(leader, &tfull_bar[acc], pair_mask);
+        acc ^= 1;
+        if (acc == 0) acc_phase ^= 1;
+      }
+    }
+  } else {
+    // ------------------------------------------------------------ epilogue (warps 2..9)
+    const int quarter = warp & 3;
+    const int col_half = (warp - 2) >> 2;
+    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
+    uint32_t acc = 0, acc_phase = 0;
+    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
+      const int n0 = (t % n_tiles) * Cfg::BLOCK_N + col_half * 128;
+      const int m_base = (((t / n_tiles) * 2 + pair) * 2 + rank) * Cfg::CTA_M + quarter * 32;
+      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
+      ptx::tc_fence_after();
+      const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
+                             (static_cast<uint32_t>(quarter * 32) << 16);
+#pragma unroll 1
+      for (int c = 0; c < 4; ++c) {
+        const int n = n0 + c * 32;
+        if (n >= p.N) break;
+        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+      }
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive_remote(&tempty_bar[acc], static_cast<uint32_t>(2 * pair));
+      acc ^= 1;
+      if (acc == 0) acc_phase ^= 1;
+    }
+  }
+
+  ptx::tc_fence_before();
+  ptx::cluster_sync();
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);

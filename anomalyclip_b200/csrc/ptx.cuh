@@ -181,6 +181,19 @@ __device__ __forceinline__ void tma_load_3d_pair(void* smem_dst, const CUtensorM
       "r"(smem_u32(bar) & kPeerBitMask), "r"(c0), "r"(c1), "r"(c2)
       : "memory");
 }
+// Multicast form: the box lands at the same shared-memory offset in every CTA of `cta_mask`, and the
+// transaction bytes are credited, per destination CTA, to the barrier at this offset in the leader
+// (even) CTA of that destination's pair.
+__device__ __forceinline__ void tma_load_3d_pair_mc(void* smem_dst, const CUtensorMap* m,
+                                                    uint64_t* bar, int c0, int c1, int c2,
+                                                    uint16_t cta_mask) {
+  asm volatile(
+      "cp.async.bulk.tensor.3d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+      ".multicast::cluster [%0], [%1, {%4, %5, %6}], [%2], %3;"
+      ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(m)),
+      "r"(smem_u32(bar) & kPeerBitMask), "h"(cta_mask), "r"(c0), "r"(c1), "r"(c2)
+      : "memory");
+}
 __device__ __forceinline__ void tma_load_5d_pair(void* smem_dst, const CUtensorMap* m,
                                                  uint64_t* bar, int c0, int c1, int c2, int c3,
                                                  int c4) {

@@ -131,7 +131,8 @@ typedef struct AclipGemmArgs {
    * out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset */
   int row_group, row_group_stride, row_offset;
   int max_ctas;          /* 0 = one persistent CTA per SM */
-  int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256) */
+  int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256),
+                            4 = clusters of two CTA pairs sharing the W tile by TMA multicast */
   float out_scale;       /* passes = 2: 2^-(e_act + e_weight) applied to the accumulator; 0 = 1 */
   int out_enc;           /* encoding of out_split: 0 = bf16 hi/lo, 1 = f16f8 activation planes */
 } AclipGemmArgs;

@@ -57,9 +57,13 @@ def main():
             extra = dict(out_split=torch.empty(2, M, N, dtype=torch.bfloat16, device=dev))
         else:
             extra = dict(out_f32=torch.empty(M, N, device=dev))
-        for kern in (2, 1):
-            ms = timeit(lambda: ops.gemm(a, w, bias=bias, act=kw.get("act", 0), kernel=kern, **extra),
-                        args.iters, flush)
+        for kern in (2, 4, 1):
+            try:
+                ms = timeit(lambda: ops.gemm(a, w, bias=bias, act=kw.get("act", 0), kernel=kern, **extra),
+                            args.iters, flush)
+            except Exception as exc:  # noqa: BLE001 - e.g. an older library build without this kernel
+                print(f"gemm_{name} kernel {kern}: {exc}", file=sys.stderr)
+                continue
             fl = 2.0 * M * N * K
             res.append({"op": f"gemm_{name}", "kernel": kern, "ms": round(ms, 4),
                         "algo_tflops": round(fl / ms / 1e9, 1), "issued_tflops": round(3 * fl / ms / 1e9, 1)})
@@ -70,13 +74,18 @@ def main():
         if kw.get("split"):
             extra = dict(out_split=ops.F16F8(M, N, dev), out_enc=1) if kw.get("act") else \
                 dict(out_split=torch.empty(2, M, N, dtype=torch.bfloat16, device=dev))
-        ms = timeit(lambda: ops.gemm(a8, w8, bias=bias, act=kw.get("act", 0), passes=2, **extra),
-                    args.iters, flush)
-        fl = 2.0 * M * N * K
-        res.append({"op": f"gemm_{name}", "kernel": "f16f8", "ms": round(ms, 4),
-                    "algo_tflops": round(fl / ms / 1e9, 1),
-                    "bf16_pass_equiv_tflops": round(2 * fl / ms / 1e9, 1)})
-        print(json.dumps(res[-1]), flush=True)
+        for kern in (2, 4):
+            try:
+                ms = timeit(lambda: ops.gemm(a8, w8, bias=bias, act=kw.get("act", 0), passes=2, kernel=kern,
+                                             **extra), args.iters, flush)
+            except Exception as exc:  # noqa: BLE001
+                print(f"gemm_{name} f16f8 kernel {kern}: {exc}", file=sys.stderr)
+                continue
+            fl = 2.0 * M * N * K
+            res.append({"op": f"gemm_{name}", "kernel": f"f16f8/{kern}", "ms": round(ms, 4),
+                        "algo_tflops": round(fl / ms / 1e9, 1),
+                        "bf16_pass_equiv_tflops": round(2 * fl / ms / 1e9, 1)})
+            print(json.dumps(res[-1]), flush=True)
 
     if not args.only or "gemm" in args.only:
         gemm_case("qkv", 3 * W, W, split=True)
