@@ -145,10 +145,12 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 3 * W;
         ACLIP_TRY(gemm(g, stream));
       }
-      // q | k | v stay bf16 hi/lo planes (the attention kernel's operand format) in every mode
-      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, enc, stream));
+      // q | k | v and the attention output stay bf16 hi/lo planes in every mode: out_proj is the
+      // smallest GEMM of the block and runs the three-pass kernel also when passes = 2 (the f16f8
+      // encode in the attention epilogue costs more than the two-pass out_proj saves)
+      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, 0, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes, b.out_s);
+        AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes == 2 ? 3 : passes);
         g.bias = b.out_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;

@@ -98,7 +98,10 @@ class PackedVit:
             b.ln1_g, b.ln1_b = f32(p + "ln_1.weight"), f32(p + "ln_1.bias")
             b.ln2_g, b.ln2_b = f32(p + "ln_2.weight"), f32(p + "ln_2.bias")
             (b.qkv_w, b.qkv_s), b.qkv_b = spl(sd[p + "attn.in_proj_weight"]), f32(p + "attn.in_proj_bias")
-            (b.out_w, b.out_s), b.out_b = spl(sd[p + "attn.out_proj.weight"]), f32(p + "attn.out_proj.bias")
+            # out_proj always takes bf16 hi/lo operands (its A operand is the attention output)
+            wo = _split_weight(sd[p + "attn.out_proj.weight"], device)
+            keep.append(wo)
+            b.out_w, b.out_s, b.out_b = wo.data_ptr(), 0.0, f32(p + "attn.out_proj.bias")
             (b.fc_w, b.fc_s), b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
             (b.proj_w, b.proj_s), b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
         w = self.struct = _lib.VitWeights()

@@ -66,8 +66,13 @@ class VisionTransformer(nn.Module):
     """clip/model.py:233-290.  forward(frames (B,3,R,R) fp32 normalised | uint8) -> (B, output_dim)."""
 
     def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int,
-                 output_dim: int, micro_batch: int = 256, passes: int = 3) -> None:
+                 output_dim: int, micro_batch: int = 256, passes: Optional[int] = None) -> None:
+        """passes: GEMM operand mode -- 3 = split-bf16 x3, 2 = fp16 + e4m3 cross terms (both
+        fp32-faithful, ~1e-5 on the features), 1 = plain bf16; None picks 2 where the CTA-pair
+        kernel applies (width and output_dim multiples of 256, e.g. every CLIP ViT-B/L) else 3."""
         super().__init__()
+        if passes is None:
+            passes = 2 if width % 256 == 0 and output_dim % 256 == 0 and patch_size % 4 == 0 else 3
         self.input_resolution, self.output_dim = input_resolution, output_dim
         self.heads, self.micro_batch, self.passes = heads, micro_batch, passes
         self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)
@@ -344,7 +349,7 @@ class AnomalyCLIP(nn.Module):
         self.image_encoder = VisionTransformer(a["resolution"], a["patch"], a["width"], a["layers"],
                                                a["width"] // 64, a["embed_dim"],
                                                micro_batch=get("micro_batch", 256),
-                                               passes=get("passes", 3))
+                                               passes=get("passes", None))
         self.has_text_tower = bool(get("build_text_tower", True))
         if self.has_text_tower:
             self.prompt_learner = PromptLearner(n_cls, get("n_ctx", 8), a["text_width"],
@@ -365,7 +370,7 @@ class AnomalyCLIP(nn.Module):
                                             output_size=1, heads=self.heads, dim_heads=self.dim_heads,
                                             depth=self.depth, num_segments=self.num_segments,
                                             seg_length=self.seg_length)
-        self.passes = get("passes", 3)
+        self.passes = self.image_encoder.passes
         self._text_features: Optional[torch.Tensor] = None
         self._text_key = None
         self._scorer: Optional[engine.TemporalScorer] = None

@@ -447,7 +447,7 @@ def main() -> None:
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
-    ap.add_argument("--passes", type=int, choices=(2, 3), default=3,
+    ap.add_argument("--passes", type=int, choices=(2, 3), default=2,
                     help="GEMM operand mode of the image encoder, both fp32-faithful: 3 = split-bf16 x3, "
                          "2 = fp16 + e4m3 cross terms (two pass-equivalents)")
     ap.add_argument("--torch-gpu-baseline", action="store_true",

@@ -175,8 +175,9 @@ typedef struct AclipVitBlock {      /* one ResidualAttentionBlock, clip/model.py
   const void* out_w;  const float* out_b;   /* attn.out_proj.weight split [2][W][W]   */
   const void* fc_w;   const float* fc_b;    /* mlp.c_fc.weight      split [2][4W][W]  */
   const void* proj_w; const float* proj_b;  /* mlp.c_proj.weight    split [2][W][4W]  */
-  /* passes = 2 only: the four weights are f16f8 planes and *_s = 2^-(4 + e_weight) is the
-   * accumulator scale of that GEMM (4 = the activations' e_main); ignored otherwise */
+  /* passes = 2 only: qkv_w, fc_w and proj_w are f16f8 planes and *_s = 2^-(4 + e_weight) is the
+   * accumulator scale of that GEMM (4 = the activations' e_main); out_w stays bf16 hi/lo (the
+   * attention output feeds out_proj in that form) and out_s is unused.  Ignored otherwise. */
   float qkv_s, out_s, fc_s, proj_s;
 } AclipVitBlock;
 

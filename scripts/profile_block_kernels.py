@@ -21,7 +21,8 @@ enc_w = (lambda t: ops.encode_f16f8(t, weight=True)) if PASSES == 2 else ops.spl
 ENC = 1 if PASSES == 2 else 0
 h = enc_a(torch.randn(M, W, device=dev))
 x = torch.randn(M, W, device=dev)
-w_qkv, w_out = enc_w(torch.randn(3 * W, W, device=dev) * 0.03), enc_w(torch.randn(W, W, device=dev) * 0.03)
+# out_proj keeps bf16 hi/lo operands in every mode (csrc/vit.cu)
+w_qkv, w_out = enc_w(torch.randn(3 * W, W, device=dev) * 0.03), ops.split(torch.randn(W, W, device=dev) * 0.03)
 w_fc, w_proj = enc_w(torch.randn(4 * W, W, device=dev) * 0.03), enc_w(torch.randn(W, 4 * W, device=dev) * 0.03)
 b3, b1, b4 = torch.randn(3 * W, device=dev), torch.randn(W, device=dev), torch.randn(4 * W, device=dev)
 g, be = torch.ones(W, device=dev), torch.zeros(W, device=dev)
@@ -31,8 +32,8 @@ fc = ops.F16F8(M, 4 * W, dev) if PASSES == 2 else torch.empty(2, M, 4 * W, dtype
 
 def block():
     ops.gemm(h, w_qkv, bias=b3, out_split=qkv, passes=PASSES)
-    o = ops.vit_attention(qkv, B, L, 12, out_enc=ENC)
-    ops.gemm(o, w_out, bias=b1, residual=x, out_f32=x, passes=PASSES)
+    o = ops.vit_attention(qkv, B, L, 12)
+    ops.gemm(o, w_out, bias=b1, residual=x, out_f32=x, passes=3)
     hh = ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC)
     ops.gemm(hh, w_fc, bias=b4, act=ops.ACT_QUICKGELU, out_split=fc, passes=PASSES, out_enc=ENC)
     ops.gemm(fc, w_proj, bias=b1, residual=x, out_f32=x, passes=PASSES)
