@@ -179,8 +179,9 @@ __global__ void __launch_bounds__(ATT_THREADS, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                         const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p) {
   extern __shared__ uint8_t att_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(att_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
+  // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
+  uint8_t* smem = att_raw + ((1024u - (ptx::smem_u32(att_raw) & 1023u)) & 1023u);
   const int kv_plane = p.LP * 128;            // bytes of one plane of K (or V)
   uint8_t* sK = smem;                         // [2 planes][LP][128 B]
   uint8_t* sV = sK + 2 * kv_plane;

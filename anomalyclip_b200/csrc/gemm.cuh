@@ -224,8 +224,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
+  // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -402,8 +403,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
+  // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
@@ -604,8 +606,9 @@ gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   static_assert(PASSES == 2 || PASSES == 3, "the four-CTA kernel carries two operand planes");
 
   extern __shared__ uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>(
-      (reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~static_cast<uintptr_t>(1023));
+  // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
+  // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
+  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
   uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
   uint64_t* empty_bar = full_bar + STAGES;
   uint64_t* tfull_bar = empty_bar + STAGES;
