@@ -42,8 +42,11 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
                  __nv_bfloat16* __restrict__ out_split, long long ld_split,
                  long long plane_stride) {
   const int lane = threadIdx.x & 31;
-  const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
-  if (row >= rows) return;
+  // Rows are walked from the LAST to the first: the GEMM that produced x wrote its highest rows
+  // last, so they are the ones still resident in L2 (x is larger than L2 at the bench's micro-batch),
+  // and the rows written last here are the first ones the consuming GEMM reads.
+  const long long row = rows - 1 - (static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5));
+  if (row < 0) return;
   const int nvec = D >> 2;
   const float4* xr = reinterpret_cast<const float4*>(x + row * ldx);
   float4 v[kMaxVec];
