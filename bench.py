@@ -361,9 +361,9 @@ def run_b200(args) -> None:
         "frac": achieved / peaks["tf_sustained"],
         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
         # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT-block GEMM
-        # launches (in_proj 576 MB, out_proj 421 MB, c_fc 736 MB, c_proj 1002 MB) in the ncu --set full
-        # capture profiles/r1_ncu_full_block_final.json; the algorithmic figure is next to it
-        "traffic": 684e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
+        # launches (in_proj 577 MB, out_proj 424 MB, c_fc 739 MB, c_proj 1005 MB) in the ncu --set full
+        # capture profiles/r1_ncu_full_block_f16f8.json; the algorithmic figure is next to it
+        "traffic": 686e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(gemm["launches"], 1),
         "passes": args.passes, "tensor_pipe_issued_tflops": args.passes * achieved,
         "tensor_pipe_issued_frac": args.passes * achieved / peaks["tf_sustained"],

@@ -223,3 +223,36 @@ def test_text_features_are_computed_once_from_checkpoint_buffers():
         net.prompt_learner.ctx.add_(0.01)
     b = net.get_text_features()
     assert b is not a and not torch.allclose(a, b)           # recomputed after the context changed
+
+
+def test_f16f8_encoding_identity_on_the_host():
+    """The exponent rules of the f16f8 operand encoding (csrc/split.cuh, ops.weight_exponent),
+    restated in torch: x_H w_H + x_L w_C + x_C w_L = 2^(ex + ew) x w to ~1e-5, the weight's main
+    plane stays finite, and the coarse / residual planes stay inside e4m3's range."""
+    from anomalyclip_b200 import ops
+    torch.manual_seed(0)
+    x = torch.randn(96, 256) * 1.5
+    for scale in (0.02, 1.0, 37.0):
+        w = torch.randn(64, 256) * scale
+        ew = ops.weight_exponent(w)
+        assert 2 ** 14 < float(w.abs().max()) * 2.0 ** ew <= 2 ** 15
+        ex, rx, cx = ops.ACT_EXP
+        rw, cw = ops.WGT_EXP_RES, ew - rx
+        assert cx == ex - rw            # both cross terms carry 2^(ex + ew), like the main product
+
+        def planes(v, e, r, c):
+            vm = v.double() * 2.0 ** e
+            h = vm.float().clamp(-65504, 65504).half().double()
+            res, coarse = (vm - h) * 2.0 ** r, v.double() * 2.0 ** c
+            assert res.abs().max() <= 448 and coarse.abs().max() <= 448
+            return h, res.float().to(torch.float8_e4m3fn).double(), coarse.float().to(torch.float8_e4m3fn).double()
+
+        xh, xl, xc = planes(x, ex, rx, cx)
+        wh, wl, wc = planes(w, ew, rw, cw)
+        acc = (xh @ wh.T + xl @ wc.T + xc @ wl.T) * 2.0 ** -(ex + ew)
+        ref = x.double() @ w.double().T
+        err = ((acc - ref).norm() / ref.norm()).item()
+        assert err < 3e-5, err
+        # without the cross terms the same product is only fp16-accurate
+        err16 = ((xh @ wh.T * 2.0 ** -(ex + ew) - ref).norm() / ref.norm()).item()
+        assert err16 > 10 * err
