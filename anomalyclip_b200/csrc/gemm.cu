@@ -276,10 +276,14 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.out_scale = g.out_scale > 0.0f ? g.out_scale : 1.0f;
   p.out_enc = g.out_enc;
   {
-    // profiling experiments (results wrong by construction) only with the environment switch
-    const char* allow = getenv("ACLIP_PROFILING_EXPERIMENTS");
-    const char* dbg = getenv("ACLIP_GEMM_DEBUG");
-    p.debug = (allow != nullptr && allow[0] == '1' && dbg != nullptr) ? atoi(dbg) : 0;
+    // profiling experiments (results wrong by construction) only with the environment switch;
+    // read once per process
+    static const int debug_mask = [] {
+      const char* allow = getenv("ACLIP_PROFILING_EXPERIMENTS");
+      const char* dbg = getenv("ACLIP_GEMM_DEBUG");
+      return (allow != nullptr && allow[0] == '1' && dbg != nullptr) ? atoi(dbg) : 0;
+    }();
+    p.debug = debug_mask;
   }
   ACLIP_REQUIRE(g.out_enc == 0 || g.out_split == nullptr ||
                     (p.ld_split % 16 == 0 && g.split_plane_stride % 16 == 0),
