@@ -20,6 +20,7 @@
 #include <cuda_bf16.h>
 
 #include <mutex>
+#include <type_traits>
 
 #include "common.h"
 #include "ptx.cuh"
@@ -174,7 +175,11 @@ __device__ __forceinline__ float softmax_group(uint32_t (&v)[16], int key0, int 
   return sum;
 }
 
-template <int ENC>  // output encoding: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes
+// ENC: output encoding, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes.
+// GROUPS: number of 16-key groups when known at compile time (13 for the ViT-B/16's 197 tokens: the
+// per-group tests of the softmax loop then fold away, about a quarter of its instructions), 0 = read
+// it from the parameters.
+template <int ENC, int GROUPS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
                         const __grid_constant__ CUtensorMap tmKV, const AttnTcParams p) {
@@ -400,6 +405,11 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       }
     };
 
+    // The tile loop, instantiated per (group count, first group) of this warp's half of the keys:
+    // GC = 0 reads both from g_count / g_begin at run time.
+    auto softmax_tiles = [&](auto gc_tag, auto gb_tag) {
+    constexpr int GC = decltype(gc_tag)::value;
+    constexpr int GB = decltype(gb_tag)::value;
     for (int J = 0; J < my_tiles; ++J) {
       const int slot = J & 1;
       const uint32_t s_addr = tmem_base + slot * S_STRIDE + lane_off;
@@ -409,14 +419,15 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       uint32_t v[HALF_GROUPS][16];
 #pragma unroll
       for (int gi = 0; gi < HALF_GROUPS; ++gi)
-        if (gi < g_count) tmem_ld_x16(s_addr + 16 * (g_begin + gi), v[gi]);
+        if (GC ? gi < GC : gi < g_count) tmem_ld_x16(s_addr + 16 * ((GC ? GB : g_begin) + gi), v[gi]);
       ptx::tmem_ld_wait();
       float mx = -INFINITY;
 #pragma unroll
       for (int gi = 0; gi < HALF_GROUPS; ++gi)
-        if (gi < g_count) {
-          const int key0 = 16 * (g_begin + gi);
-          if (key0 + 16 <= p.L) {  // warp-uniform: only the last group straddles L
+        if (GC ? gi < GC : gi < g_count) {
+          const int key0 = 16 * ((GC ? GB : g_begin) + gi);
+          // only the last group of the row can straddle L (warp-uniform; known when GROUPS is)
+          if (GC ? (GB + gi < GROUPS - 1) : (key0 + 16 <= p.L)) {
 #pragma unroll
             for (int j = 0; j < 16; ++j) mx = fmaxf(mx, __uint_as_float(v[gi][j]));
           } else {
@@ -435,11 +446,12 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       float sum = 0.f;
 #pragma unroll
       for (int gi = 0; gi < HALF_GROUPS; ++gi)
-        if (gi < g_count) {
-          const int g = g_begin + gi;
+        if (GC ? gi < GC : gi < g_count) {
+          const int g = (GC ? GB : g_begin) + gi;
           if (!(p.debug & 1))
-            sum += (16 * g + 16 <= p.L) ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
-                                        : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+            sum += (GC ? (GB + gi < GROUPS - 1) : (16 * g + 16 <= p.L))
+                       ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
+                       : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
           if (!(p.debug & 4)) {
             tmem_st_x8(s_addr + 8 * g, &v[gi][0]);             // hi plane, packed
             tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
@@ -453,6 +465,15 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       // the previous tile's output is ready by now: normalise and store it.  (Its row sums were
       // written before the barrier above by both halves.)
       if (J > 0) write_output(J - 1);
+    }
+    };
+    using std::integral_constant;
+    if (GROUPS > 0) {
+      constexpr int G0 = (GROUPS + 1) / 2;
+      if (half == 0) softmax_tiles(integral_constant<int, G0>{}, integral_constant<int, 0>{});
+      else softmax_tiles(integral_constant<int, (GROUPS > 0 ? GROUPS - G0 : 1)>{}, integral_constant<int, G0>{});
+    } else {
+      softmax_tiles(integral_constant<int, 0>{}, integral_constant<int, 0>{});
     }
     if (my_tiles > 0) {
       asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
@@ -537,19 +558,29 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   int once_dev;
   if (once.need(once_dev)) {
     constexpr int kMaxSmem = 4 * MAX_LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
-    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<0>,
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<0, 0>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
-    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<1>,
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<1, 0>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<0, 13>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<1, 13>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     once.mark(once_dev);
   }
   int ctas = sm_count();
   if (ctas > p.items) ctas = p.items;
   timing_begin(KIND_VIT_ATTENTION, stream);
-  if (out_enc == 1)
-    vit_attention_tc_kernel<1><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
-  else
-    vit_attention_tc_kernel<0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  // 13 key groups (193..208 tokens, the ViT-B/16 case) have a specialised instantiation; debug & 8
+  // (profiling experiments) forces the generic one
+  const bool fixed13 = LP == 208 && !(debug & 8);
+  if (out_enc == 1) {
+    if (fixed13) vit_attention_tc_kernel<1, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else vit_attention_tc_kernel<1, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  } else {
+    if (fixed13) vit_attention_tc_kernel<0, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else vit_attention_tc_kernel<0, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  }
   timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
              (double)B * L * heads * HD * (3 * 4.0 + 4.0));
   ACLIP_CHECK_LAUNCH();
