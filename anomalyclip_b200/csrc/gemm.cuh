@@ -2,21 +2,25 @@
 //
 //   C[M,N] = epilogue( A[M,K] * W[N,K]^T )
 //
-// Operands are "split-bf16": every fp32 value x is carried as two bf16 planes
-// hi = bf16(x), lo = bf16(x - hi).  With PASSES == 3 the kernel issues
-// hi*hi + lo*hi + hi*lo into one fp32 TMEM accumulator, which reproduces an fp32 GEMM to
-// ~2^-16 relative error per product (the reference path is fp32 end to end, see
-// /root/reference/src/models/components/anomaly_clip.py:66-67).  PASSES == 1 is the plain
-// bf16 GEMM (hi plane only).
+// The reference path is fp32 end to end (/root/reference/src/models/components/anomaly_clip.py:66-67),
+// so every fp32 operand value travels in a narrow encoding whose products reproduce the fp32 product
+// (split.cuh), accumulated in one fp32 TMEM accumulator:
+//   PASSES == 3  "split-bf16": hi = bf16(x), lo = bf16(x - hi); hi*hi + lo*hi + hi*lo, three
+//                kind::f16 MMAs per K step, ~2^-16 relative error per product
+//   PASSES == 2  "f16f8": fp16 main plane + e4m3 residual and coarse planes; one kind::f16 MMA
+//                (K = 16) per K step plus two kind::f8f6f4 MMAs (K = 32, twice the rate) for the
+//                cross terms: two bf16-pass equivalents, ~2^-16 as well (CTA-pair kernels only)
+//   PASSES == 1  plain bf16 (hi plane only)
 //
-// Two kernels share the producer / issuer / epilogue code:
-//   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile            (192 threads)
-//   gemm2_tcgen05_kernel  a CTA pair (cta_group::2) per 256 x 256 tile   (320 threads per CTA)
+// Three kernels share the producer / issuer / epilogue code:
+//   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile                    (192 threads)
+//   gemm2_tcgen05_kernel  a CTA pair (cta_group::2) per 256 x 256 tile           (320 threads per CTA)
+//   gemm4_tcgen05_kernel  two CTA pairs on M-adjacent tiles sharing the W tile by TMA multicast
 // Roles:
-//   warp 0  lane 0 : TMA producer   (A and W tiles, 128-byte swizzle, mbarrier complete_tx)
-//   warp 1  lane 0 : MMA issuer     (tcgen05.mma, K=16 per instruction)
-//   other warps    : epilogue       (tcgen05.ld -> bias / activation -> smem transpose ->
-//                                    residual -> row-contiguous fp32 / split-bf16 stores)
+//   warp 0  lane 0 : TMA producer   (A and W tiles, swizzled boxes, mbarrier complete_tx)
+//   warp 1  lane 0 : MMA issuer     (tcgen05.mma)
+//   other warps    : epilogue       (tcgen05.ld -> scale + bias / activation -> smem transpose ->
+//                                    residual -> row-contiguous fp32 / encoded stores)
 // Pipelines: smem ring full/empty (TMA <-> MMA) and a double-buffered TMEM accumulator
 // full/empty (MMA <-> epilogue), so the epilogue of tile i overlaps the MMAs of tile i+1.
 //
@@ -49,8 +53,9 @@ struct GemmParams {
   int ldr;
   int act;
   float* out_f32;            // fp32 [*, ldc] or nullptr
-  __nv_bfloat16* out_split;  // bf16 [2][split_rows][ldc] or nullptr (hi plane, lo plane)
-  long long split_plane_stride;  // elements between the hi and lo plane
+  __nv_bfloat16* out_split;  // encoded output (out_enc) or nullptr: bf16 [2][rows][ld_split] planes
+                             // hi, lo, or f16f8 planes H | L | C (split.cuh)
+  long long split_plane_stride;  // plane stride in elements
   int ldc;
   int ld_split;  // pitch of out_split (elements)
   // output row remap: out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset

@@ -7,6 +7,7 @@ A "split" tensor is a bf16 tensor of shape [2, rows, ld]: plane 0 = hi, plane 1 
 from __future__ import annotations
 
 import ctypes as C
+import math
 from typing import Optional
 
 import torch
@@ -79,7 +80,6 @@ class F16F8:
 
 def weight_exponent(w: torch.Tensor) -> int:
     """e_main of a weight tensor: max|w| * 2^e in (2^14, 2^15]  (fp16 main plane stays finite)."""
-    import math
     m = float(w.abs().max())
     return 15 - math.ceil(math.log2(m)) if m > 0 else 0
 
@@ -118,31 +118,29 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if passes == 2:
         if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
             raise TypeError("gemm(passes=2) needs F16F8 operands")
-        N, M = w.rows, a.rows
+        if conv is not None:
+            raise ValueError("gemm(passes=2) has no conv mode")
+        M, N = a.rows, w.rows
         Kk = K if K is not None else a.ld
         g.lda, g.ldw = a.ld, w.ld
         g.a_plane_stride, g.w_plane_stride = a.plane_stride, w.plane_stride
         g.out_scale = 2.0 ** -(a.exp + w.exp)
         dev = a.buf.device
     else:
-        N = w.shape[1]
-        dev = a.device
-    if passes == 2:
-        pass
-    elif conv is not None:
-        S, H, Wd, Cc = conv
-        M, Kk = S * H * Wd, 9 * Cc
-        g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
-        g.lda = Cc
-    else:
-        M = a.shape[1]
-        Kk = K if K is not None else a.shape[2]
-        g.lda = a.stride(1)
-    g.a, g.w = a.data_ptr(), w.data_ptr()
-    g.M, g.N, g.K = M, N, Kk
-    if passes != 2:
+        N, dev = w.shape[1], a.device
         g.ldw = w.stride(1)
         g.a_plane_stride, g.w_plane_stride = a.stride(0), w.stride(0)
+        if conv is not None:
+            S, H, Wd, Cc = conv
+            M, Kk = S * H * Wd, 9 * Cc
+            g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
+            g.lda = Cc
+        else:
+            M = a.shape[1]
+            Kk = K if K is not None else a.shape[2]
+            g.lda = a.stride(1)
+    g.a, g.w = a.data_ptr(), w.data_ptr()
+    g.M, g.N, g.K = M, N, Kk
     g.passes = passes
     g.out_enc = out_enc
     g.bias = _ptr(bias)
