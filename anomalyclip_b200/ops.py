@@ -81,7 +81,9 @@ class F16F8:
 def weight_exponent(w: torch.Tensor) -> int:
     """e_main of a weight tensor: max|w| * 2^e in (2^14, 2^15]  (fp16 main plane stays finite)."""
     m = float(w.abs().max())
-    return 15 - math.ceil(math.log2(m)) if m > 0 else 0
+    if not (m > 0 and math.isfinite(m)):
+        return 0
+    return max(-30, min(30, 15 - math.ceil(math.log2(m))))   # the range aclip_encode_f16f8 accepts
 
 
 def encode_f16f8(x: torch.Tensor, *, weight: bool = False, ld_out: Optional[int] = None) -> F16F8:
