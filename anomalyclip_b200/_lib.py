@@ -59,7 +59,9 @@ class AxialAttnWeights(C.Structure):
 
 
 class ConvFFWeights(C.Structure):
-    _fields_ = [(n, vp) for n in ("g", "b", "conv1_w", "conv1_b", "conv2_w", "conv2_b")]
+    _fields_ = [(n, vp) for n in ("g", "b", "conv1_w", "conv1_b", "conv2_w", "conv2_b",
+                                  "conv1_w8", "conv2_w8")] + \
+               [("conv1_s", C.c_float), ("conv2_s", C.c_float)]
 
 
 class TemporalWeights(C.Structure):

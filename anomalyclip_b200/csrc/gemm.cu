@@ -201,9 +201,10 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.passes >= 1 && g.passes <= 3, "gemm: passes must be 1, 2 or 3 (got %d)", g.passes);
   ACLIP_REQUIRE(g.out_enc == 0 || g.out_enc == 1, "gemm: out_enc must be 0 (bf16 hi/lo) or 1 (f16f8)");
   if (g.passes == 2) {
-    // f16f8 operands (split.cuh): CTA-pair kernel, linear A only
-    ACLIP_REQUIRE(g.a_mode == 0 && g.N % 256 == 0 && g.kernel != 1,
-                  "gemm: passes=2 (f16f8 operands) needs a linear A operand and N %% 256 == 0 (N=%d)", g.N);
+    // f16f8 operands (split.cuh): CTA-pair kernels only (the four-CTA one: linear A only)
+    ACLIP_REQUIRE(g.a_mode == 0 || g.a_mode == 1, "gemm: unknown a_mode %d", g.a_mode);
+    ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1 && (g.a_mode == 0 || g.kernel != 4),
+                  "gemm: passes=2 (f16f8 operands) runs on the CTA-pair kernel: N %% 256 == 0 (N=%d)", g.N);
     ACLIP_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.a_plane_stride % 16 == 0 &&
                       g.w_plane_stride % 16 == 0,
                   "gemm: passes=2 needs pitches and plane strides that are multiples of 16");
@@ -293,7 +294,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   if (g.passes == 2) {
     // fp16 plane: [1][rows][ld] (128-byte swizzle rows of 64 values); e4m3 planes L, C: one
     // [2][rows][ld] byte tensor starting 2 * plane_stride bytes in (64-byte swizzle rows)
-    for (int op = 0; op < 2; ++op) {
+    for (int op = (g.a_mode == 1 ? 1 : 0); op < 2; ++op) {
       const void* base = op == 0 ? g.a : g.w;
       const cuuint64_t rows = op == 0 ? g.M : g.N, ld = op == 0 ? g.lda : g.ldw;
       const cuuint64_t ps = op == 0 ? g.a_plane_stride : g.w_plane_stride;
@@ -311,6 +312,31 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
       ACLIP_TRY(make_tmap(op == 0 ? &tmA8 : &tmB8, static_cast<const uint8_t*>(base) + 2 * ps, 3,
                           dims_8, str_8, box_8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
                           CU_TENSOR_MAP_SWIZZLE_64B));
+    }
+    if (g.a_mode == 1) {
+      // conv3x3 over an f16f8 NHWC grid: 5-D maps {C, W, H, S, plane} for the fp16 plane and for
+      // the two e4m3 planes; a box is 64 channels x one 128-row block of the grid (x both planes)
+      ACLIP_REQUIRE(g.conv_c % 64 == 0, "conv3x3: C=%d must be a multiple of 64", g.conv_c);
+      ACLIP_REQUIRE(g.conv_w > 0 && 128 % g.conv_w == 0 && (g.conv_h * g.conv_w) % 128 == 0,
+                    "conv3x3: grid %dx%d unsupported (need W | 128 and 128 | H*W)", g.conv_h, g.conv_w);
+      ACLIP_REQUIRE(g.M == g.conv_s * g.conv_h * g.conv_w && g.K == 9 * g.conv_c,
+                    "conv3x3: M/K inconsistent with the grid");
+      p.conv_cin_kb = g.conv_c / 64;
+      p.conv_w = g.conv_w;
+      p.conv_h = g.conv_h;
+      const cuuint64_t C = g.conv_c, W = g.conv_w, H = g.conv_h, S = g.conv_s;
+      const cuuint64_t ps = g.a_plane_stride;
+      ACLIP_REQUIRE(ps >= S * H * W * C, "gemm: plane stride smaller than the operand");
+      cuuint64_t dims_h[5] = {C, W, H, S, 1};
+      cuuint64_t str_h[4] = {C * 2, W * C * 2, H * W * C * 2, S * H * W * C * 2};
+      cuuint32_t box_h[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(128 / g.conv_w), 1, 1};
+      ACLIP_TRY(make_tmap(&tmA, g.a, 5, dims_h, str_h, box_h, CU_TENSOR_MAP_DATA_TYPE_FLOAT16,
+                          CU_TENSOR_MAP_SWIZZLE_128B));
+      cuuint64_t dims_8[5] = {C, W, H, S, 2};
+      cuuint64_t str_8[4] = {C, W * C, H * W * C, ps};
+      cuuint32_t box_8[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(128 / g.conv_w), 1, 2};
+      ACLIP_TRY(make_tmap(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * ps, 5, dims_8, str_8, box_8,
+                          CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_64B));
     }
     return quad ? launch_quad<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
                 : launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);

@@ -475,8 +475,16 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (PASSES == 2) {
             // f16f8 operands: fp16 plane (128 B rows, SWIZZLE_128B) + the two e4m3 planes in one
             // box (64 B rows, SWIZZLE_64B); same bytes per stage as two bf16 planes
-            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            if (p.a_mode == 0) {
+              ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+              ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            } else {  // conv3x3: the same shifted, zero-filled boxes for the fp16 and the e4m3 planes
+              const int tap = kb / p.conv_cin_kb;
+              const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
+              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
+              ptx::tma_load_5d_pair(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+              ptx::tma_load_5d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+            }
             ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
             ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
             if (++stage == STAGES) { stage = 0; phase ^= 1; }

@@ -223,8 +223,8 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
               void* out_split, long long ld_split, long long plane_stride, int out_enc,
               cudaStream_t stream) {
   ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
-  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && mode == 0 && ld_split % 16 == 0 && plane_stride % 16 == 0),
-                "layernorm: out_enc=%d unsupported here (f16f8 needs mode 0 and 16-element pitches)", out_enc);
+  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0),
+                "layernorm: out_enc=%d unsupported (f16f8 needs 16-element pitches)", out_enc);
   ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
   ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
                     (out_split == nullptr || ld_split % 4 == 0),
@@ -240,6 +240,9 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   else if (mode == 0)
     layernorm_kernel<0, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
+        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  else if (out_enc == 1)
+    layernorm_kernel<1, 1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
         x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
   else
     layernorm_kernel<1, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(

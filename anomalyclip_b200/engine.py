@@ -246,10 +246,16 @@ class PackedTemporal:
                 q = f"{pre}axial_attn.layers.blocks.{2 * d + 1}.{fg}.net."
                 c = self.ff[2 * d + j]
                 c.g, c.b = f32t(sd[q + "0.g"].reshape(E)), f32t(sd[q + "0.b"].reshape(E))
-                c.conv1_w = spl(sd[q + "1.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(4 * E, 9 * E))
-                c.conv1_b = f32t(sd[q + "1.bias"])
-                c.conv2_w = spl(sd[q + "3.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(E, 36 * E))
-                c.conv2_b = f32t(sd[q + "3.bias"])
+                w1 = sd[q + "1.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(4 * E, 9 * E)
+                w2 = sd[q + "3.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(E, 36 * E)
+                c.conv1_w, c.conv1_b = spl(w1), f32t(sd[q + "1.bias"])
+                c.conv2_w, c.conv2_b = spl(w2), f32t(sd[q + "3.bias"])
+                if E % 256 == 0:  # f16f8 copies for passes = 2 calls on large chunks (CTA-pair kernel)
+                    for name, wt in (("conv1", w1), ("conv2", w2)):
+                        e8 = ops.encode_f16f8(_dev_f32(wt, device), weight=True)
+                        keep.append(e8)
+                        setattr(c, name + "_w8", e8.data_ptr())
+                        setattr(c, name + "_s", 2.0 ** -(ops.ACT_EXP[0] + e8.exp))
         w.attn = C.cast(self.attn, C.POINTER(_lib.AxialAttnWeights))
         w.ff = C.cast(self.ff, C.POINTER(_lib.ConvFFWeights))
         w.head_ln_g = f32t(sd[pre + "classifier.layer_norm.weight"])

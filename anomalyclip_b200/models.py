@@ -410,9 +410,9 @@ class AnomalyCLIP(nn.Module):
                 emb_size=self.emb_size, depth=self.depth, heads=self.heads,
                 num_segments=self.num_segments, seg_length=self.seg_length,
                 concat_features=self.concat_features, feature_dim=ARCHS[self.arch]["embed_dim"])
-            # passes = 2 (f16f8 operands) exists for the image encoder's GEMMs only; the temporal
-            # stage (0.1 % of the work) then runs its fp32-faithful three-pass mode
-            self._scorer = engine.TemporalScorer(packed, passes=3 if self.passes == 2 else self.passes)
+            # passes = 2: the temporal stage runs its conv GEMMs on f16f8 operands for large chunks
+            # (>= 8 sub-videos) and three passes otherwise
+            self._scorer = engine.TemporalScorer(packed, passes=self.passes)
             self._scorer_key = key
         return self._scorer
 

@@ -120,11 +120,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if passes == 2:
         if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
             raise TypeError("gemm(passes=2) needs F16F8 operands")
-        if conv is not None:
-            raise ValueError("gemm(passes=2) has no conv mode")
         M, N = a.rows, w.rows
         Kk = K if K is not None else a.ld
         g.lda, g.ldw = a.ld, w.ld
+        if conv is not None:   # a: rows = S*H*W grid cells of C channels (NHWC)
+            S, H, Wd, Cc = conv
+            if a.rows != S * H * Wd or a.ld != Cc:
+                raise ValueError("gemm(passes=2, conv): the F16F8 grid must be [S*H*W, C]")
+            Kk = 9 * Cc
+            g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
         g.a_plane_stride, g.w_plane_stride = a.plane_stride, w.plane_stride
         g.out_scale = 2.0 ** -(a.exp + w.exp)
         dev = a.buf.device

@@ -217,6 +217,10 @@ typedef struct AclipConvFFWeights {   /* ChanLayerNorm -> conv3x3 -> LeakyReLU -
   const float *g, *b;                 /* [E] */
   const void* conv1_w; const float* conv1_b; /* split [2][4E][9*E], k = (ky*3+kx)*E + c */
   const void* conv2_w; const float* conv2_b; /* split [2][E][9*4E] */
+  /* optional (NULL = absent): the same two weights as f16f8 planes and their accumulator scales
+   * 2^-(4 + e_weight); used by passes = 2 calls whose chunk has >= 4096 rows and E % 256 == 0 */
+  const void* conv1_w8; const void* conv2_w8;
+  float conv1_s, conv2_s;
 } AclipConvFFWeights;
 
 typedef struct AclipTemporalWeights { /* SelectorModel (test branch) + TemporalModel + head */
@@ -268,7 +272,9 @@ int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch, vo
  * features: fp32 [N][feature_dim], rows in the caller's "(b n s l)" order, N = sub_videos*n*l with
  * sub_videos = b*segment_size.  Outputs in the same row order: similarity_out [N][num_dirs],
  * scores_out [N], class_probs_out [N][num_dirs] (may be NULL).  Sub-videos are processed in as
- * large chunks as `workspace` allows. */
+ * large chunks as `workspace` allows.  passes: 3 (split-bf16) or 1 (bf16) for every GEMM; 2 runs the
+ * 3x3 conv GEMMs (94 % of the work) on f16f8 operands where AclipConvFFWeights carries them and the
+ * chunk is large enough for the CTA-pair kernel, everything else as passes = 3. */
 int aclip_temporal_forward(const AclipTemporalWeights* w, const float* features,
                            long long sub_videos, int segment_size, float* similarity_out,
                            float* scores_out, float* class_probs_out, void* workspace,

@@ -275,3 +275,25 @@ def test_gemm_four_cta_kernel_is_bit_identical_to_the_pair_kernel(ops, M, N, K, 
     torch.cuda.synchronize()
     assert torch.equal(out, ref)
     assert _rel(out, a.double() @ w.double().T + bias.double()) < 3e-5
+
+
+@pytest.mark.parametrize("S,Cin,Cout", [(1, 64, 256), (3, 256, 1024), (2, 1024, 256), (9, 256, 256)])
+def test_conv3x3_implicit_gemm_f16f8(ops, S, Cin, Cout):
+    """The 3x3 "same" convolution over an f16f8 NHWC grid (5-D TMA maps for the fp16 plane and for
+    the two e4m3 planes, hardware zero fill at the borders), LeakyReLU epilogue, f16f8 output."""
+    torch.manual_seed(3)
+    H, W = 32, 16
+    x = torch.randn(S, Cin, H, W, device="cuda")
+    wt = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.02
+    b = torch.randn(Cout, device="cuda")
+    ref = torch.nn.functional.conv2d(x.double(), wt.double(), b.double(), padding=1)
+    ref = ref.permute(0, 2, 3, 1).reshape(S * H * W, Cout)
+    a = ops.encode_f16f8(x.permute(0, 2, 3, 1).contiguous().reshape(S * H * W, Cin))
+    wk = ops.encode_f16f8(wt.permute(0, 2, 3, 1).contiguous().reshape(Cout, 9 * Cin), weight=True)
+    out = ops.gemm(a, wk, bias=b, conv=(S, H, W, Cin), passes=2)
+    err = _rel(out, ref)
+    print(f"conv3x3 f16f8 S={S} {Cin}->{Cout}: rel err {err:.3e}")
+    assert err < 3e-5
+    enc = ops.gemm(a, wk, bias=b, act=ops.ACT_LEAKYRELU, conv=(S, H, W, Cin), passes=2,
+                   want_split=True, out_enc=1)
+    assert _rel(enc.decode(), torch.nn.functional.leaky_relu(ref, 0.01)) < 3e-5

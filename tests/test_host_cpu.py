@@ -34,14 +34,14 @@ def test_invalid_arguments_return_status_not_crash():
     assert lib.aclip_temporal_forward(None, None, 0, 1, None, None, None, None, 0, 3, None) == -1
     assert lib.aclip_vit_workspace_bytes(None, 4) == 0
     assert lib.aclip_encode_f16f8(None, 4, 16, 16, None, 16, 64, 4, 7, 0, None) == -1
-    # a passes = 2 GEMM without its accumulator scale / with a conv operand is refused before any launch
+    # a passes = 2 GEMM without its accumulator scale / with N % 256 != 0 is refused before any launch
     g = _lib.GemmArgs()
     g.a, g.w, g.M, g.N, g.K, g.lda, g.ldw = 1024, 2048, 128, 256, 64, 64, 64
     g.a_plane_stride, g.w_plane_stride, g.passes, g.out_f32, g.ldc = 128 * 64, 256 * 64, 2, 4096, 256
     import ctypes as C
     assert lib.aclip_gemm(C.byref(g), None) == -1 and b"out_scale" in lib.aclip_last_error()
-    g.out_scale, g.a_mode = 1.0, 1
-    assert lib.aclip_gemm(C.byref(g), None) == -1 and b"linear" in lib.aclip_last_error()
+    g.out_scale, g.N = 1.0, 128
+    assert lib.aclip_gemm(C.byref(g), None) == -1 and b"CTA-pair" in lib.aclip_last_error()
 
 
 def test_no_cpu_fallback():

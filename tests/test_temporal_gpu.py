@@ -93,3 +93,30 @@ def test_rows_must_fill_whole_sub_videos():
     scorer.packed.set_directions(make_text_features(cfg), make_ncentroid(cfg))
     with pytest.raises(ValueError):
         scorer(torch.zeros(100, 512, device="cuda"), 1)
+
+
+@pytest.mark.parametrize("name", ["ucfcrime", "shanghaitech"])
+def test_f16f8_conv_mode_on_a_large_chunk_matches_oracle(name):
+    """passes=2: with >= 8 sub-videos per chunk (4096 rows) the conv feed-forward GEMMs run on f16f8
+    operands (ChanLayerNorm emits the planes, conv1 writes its hidden in them); smaller chunks and
+    every other GEMM keep three passes.  Same parity bar either way."""
+    cfg = PRESETS[name]
+    sd = make_state_dict(cfg, with_vit=False)
+    text, m = make_text_features(cfg), make_ncentroid(cfg)
+    feats = make_features(cfg, 8, seed=21).reshape(8, 1, cfg.unit, 512)       # 8 videos x 1 sub-video
+    sim_ref, sc_ref = _oracle(cfg, sd, feats, text, m, 1)
+    probs_ref, _ = oracle.test_step_postprocess(sim_ref, sc_ref)
+    for max_chunk in (512, 4):      # f16f8 conv path / three-pass fallback (chunks of 2048 rows)
+        scorer = _scorer(cfg, sd, passes=2, max_chunk=max_chunk)
+        scorer.packed.set_directions(text, m)
+        sim, sc, probs = scorer(feats.cuda(), 1)
+        assert_parity(sim, sim_ref, f"{name} similarity (passes=2, chunk {max_chunk})")
+        assert_parity(sc, sc_ref, f"{name} scores (passes=2, chunk {max_chunk})")
+        assert_parity(probs, probs_ref, f"{name} class probabilities (passes=2, chunk {max_chunk})")
+        assert torch.equal(probs.argmax(1).cpu(), probs_ref.argmax(1)), "argmax class differs"
+    # the two chunkings take different GEMM paths for the conv layers but agree to fp32 noise
+    a = _scorer(cfg, sd, passes=2, max_chunk=512); a.packed.set_directions(text, m)
+    b = _scorer(cfg, sd, passes=3, max_chunk=512); b.packed.set_directions(text, m)
+    sa, sb = a(feats.cuda(), 1)[1], b(feats.cuda(), 1)[1]
+    assert not torch.equal(sa, sb), "passes=2 did not take the f16f8 conv path on a 4096-row chunk"
+    assert_parity(sa, sb, "f16f8 vs three-pass scores", rtol=1e-4)
