@@ -52,9 +52,9 @@ def main():
         _lib.timing_enable(False)
         kinds = {k: round(v["ms"], 3) for k, v in _lib.timing_collect().items()}
         rows = B * cfg.unit
-        print(json.dumps({"preset": args.preset, "sub_videos": B, "ms": round(ms, 3),
+        print(json.dumps({"preset": args.preset, "passes": args.passes, "sub_videos": B, "ms": round(ms, 3),
                           "rows_per_s": round(rows / ms * 1e3),
-                          "algo_tflops": round(rows * MFLOP_PER_ROW[args.preset] / ms / 1e3 / 1e3, 1),
+                          "algo_tflops": round(rows * MFLOP_PER_ROW[args.preset] / ms / 1e3, 1),
                           "kernels_ms": kinds}), flush=True)
 
 
