@@ -101,6 +101,25 @@ class FeatureVideoDataset(torch.utils.data.Dataset):
         return self.assemble(feats, rec)
 
 
+def save_features(path: str, feats: torch.Tensor, ncrops: int = 1) -> str:
+    """Write encoder outputs in the on-disk format `FeatureVideoDataset` (and the reference's
+    feature_dataset.py:74,326-349) reads: `<path>.npy`, fp32 `[frames * ncrops, D]`, frame-major with
+    the crops of a frame adjacent.  `feats` is (frames, D), (frames, ncrops, D) or (ncrops, frames, D)
+    as returned by the dataset (crop-major); returns the file name."""
+    f = feats.detach().to(device="cpu", dtype=torch.float32)
+    if f.dim() == 3:
+        if f.shape[0] == ncrops and f.shape[1] != ncrops:      # (ncrops, frames, D) -> frame-major
+            f = f.permute(1, 0, 2)
+        if f.shape[1] != ncrops:
+            raise ValueError(f"save_features: {tuple(feats.shape)} does not hold {ncrops} crops per frame")
+        f = f.reshape(-1, f.shape[-1])
+    elif f.dim() != 2 or f.shape[0] % ncrops != 0:
+        raise ValueError(f"save_features: expected (frames*ncrops, D) rows, got {tuple(feats.shape)}")
+    name = path if path.endswith(".npy") else path + ".npy"
+    np.save(name, f.contiguous().numpy())
+    return name
+
+
 def gather_test_frames(frames: torch.Tensor, num_segments: int, seg_length: int, stride: int = 1
                        ) -> Tuple[torch.Tensor, int]:
     """Raw-frame variant (video_dataset.py:331-346) for frames already decoded to a

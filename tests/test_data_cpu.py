@@ -58,3 +58,25 @@ def test_resize_crop_plan_is_bit_exact_with_pillow(h, w):
     got = oracle.resize_center_crop_u8(frame, plan)
     assert got.shape == (3, 224, 224)
     assert np.array_equal(got, ref)
+
+
+def test_feature_file_roundtrip(tmp_path):
+    """save_features writes the `.npy` layout the feature dataset reads back (frame-major rows,
+    crops adjacent), for 1 and 10 crops; the dataset then pads / wraps the frames as in test mode."""
+    import torch
+    from anomalyclip_b200.data import FeatureVideoDataset, VideoRecord, save_features, test_mode_indices
+    torch.manual_seed(0)
+    for ncrops, frames in ((1, 700), (10, 37)):
+        feats = torch.randn(frames, ncrops, 512)
+        name = save_features(str(tmp_path / f"video_{ncrops}"), feats, ncrops=ncrops)
+        assert name.endswith(".npy")
+        ds = FeatureVideoDataset([VideoRecord(name, 1, frames, 3)], num_segments=32, seg_length=16,
+                                 ncrops=ncrops, normal_id=7)
+        x, labels, label, segment_size, path = ds[0]
+        idx, s = test_mode_indices(frames, 32, 16)
+        assert segment_size == s and x.shape == (ncrops, len(idx), 512) and labels.shape[0] == frames
+        assert torch.equal(x, feats[torch.from_numpy(idx)].permute(1, 0, 2))
+        # the crop-major tensor the dataset returns can be written back unchanged
+        again = save_features(str(tmp_path / f"again_{ncrops}"), feats.permute(1, 0, 2), ncrops=ncrops)
+        import numpy as np
+        assert np.array_equal(np.load(again), np.load(name))
