@@ -265,3 +265,33 @@ def test_f16f8_encoding_identity_on_the_host():
         # without the cross terms the same product is only fp16-accurate
         err16 = ((xh @ wh.T * 2.0 ** -(ex + ew) - ref).norm() / ref.norm()).item()
         assert err16 > 10 * err
+
+
+def test_f16f8_emulated_through_a_small_vit_stays_fp32_faithful():
+    """End-to-end numerics of the f16f8 GEMM operands without a GPU: every linear layer of a small
+    ViT (oracle arithmetic) is replaced by the emulated encoding (scripts/numerics_f16f8.py); the
+    features stay within 1e-4 of the fp32 oracle (bar 1e-3) while plain fp16 / bf16 operands do not
+    get anywhere near that."""
+    import importlib.util
+    import torch.nn.functional as F
+    from anomalyclip_b200 import synthetic as syn
+    from oracle import anomalyclip_oracle as oracle
+    spec = importlib.util.spec_from_file_location("numerics_f16f8", ROOT / "scripts" / "numerics_f16f8.py")
+    study = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(study)
+    w = syn.make_vit_weights(width=256, layers=3, patch=16, resolution=64, output_dim=256, seed=5)
+    torch.manual_seed(1)
+    frames = torch.randn(4, 3, 64, 64)
+    real = F.linear
+    errs = {}
+    with torch.no_grad():
+        ref = oracle.vit_forward(w, frames).double()
+        for mode in ("bf16x1", "fp16x1", "bf16x3", "f16f8"):
+            F.linear = study.make_linear(mode)
+            try:
+                out = oracle.vit_forward(w, frames).double()
+            finally:
+                F.linear = real
+            errs[mode] = ((out - ref).norm() / ref.norm()).item()
+    assert errs["f16f8"] < 1e-4 and errs["bf16x3"] < 1e-4, errs
+    assert errs["fp16x1"] > 5 * errs["f16f8"] and errs["bf16x1"] > 50 * errs["f16f8"], errs
