@@ -295,3 +295,15 @@ def test_f16f8_emulated_through_a_small_vit_stays_fp32_faithful():
             errs[mode] = ((out - ref).norm() / ref.norm()).item()
     assert errs["f16f8"] < 1e-4 and errs["bf16x3"] < 1e-4, errs
     assert errs["fp16x1"] > 5 * errs["f16f8"] and errs["bf16x1"] > 50 * errs["f16f8"], errs
+
+
+def test_header_is_plain_c():
+    """The drop-in boundary is a C ABI: include/aclip_b200.h must compile as C99 on its own."""
+    import shutil
+    import subprocess
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror",
+                          str(ROOT / "include" / "aclip_b200.h")], capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
