@@ -76,12 +76,7 @@ class FeatureVideoDataset(torch.utils.data.Dataset):
 
     @classmethod
     def from_annotation_file(cls, annotation_file: str, root: str, **kw) -> "FeatureVideoDataset":
-        recs = []
-        for line in Path(annotation_file).read_text().splitlines():
-            p = line.strip().split()
-            if len(p) >= 4:
-                recs.append(VideoRecord(str(Path(root) / p[0]), int(p[1]), int(p[2]), int(p[3])))
-        return cls(recs, **kw)
+        return cls(read_annotation_file(annotation_file, root), **kw)
 
     def __len__(self) -> int:
         return len(self.records)
@@ -97,8 +92,108 @@ class FeatureVideoDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, i: int):
         rec = self.records[i]
+        # the reference's annotation rows name the video without the suffix (feature_dataset.py:74)
+        if not rec.path.endswith(".npy"):
+            rec = VideoRecord(rec.path + ".npy", rec.start_frame, rec.end_frame, rec.label)
         feats = torch.from_numpy(np.load(rec.path, allow_pickle=True)).to(torch.float32)
         return self.assemble(feats, rec)
+
+
+def read_annotation_file(annotation_file: str, root: str) -> List[VideoRecord]:
+    """One `VIDEO_PATH START_FRAME END_FRAME LABEL` row per video (video_dataset.py:195-199)."""
+    recs = []
+    for line in Path(annotation_file).read_text().splitlines():
+        p = line.strip().split()
+        if len(p) >= 4:
+            recs.append(VideoRecord(str(Path(root) / p[0]), int(p[1]), int(p[2]), int(p[3])))
+    return recs
+
+
+def read_temporal_annotations(path: Optional[str]) -> Dict[str, List[int]]:
+    """`NAME LABEL START END [START END ...]` rows -> {stem: [start, end, ...]}
+    (video_dataset.py:201-211, feature_dataset.py the same)."""
+    out: Dict[str, List[int]] = {}
+    if path:
+        for line in Path(path).read_text().splitlines():
+            p = line.strip().split()
+            if len(p) >= 2:
+                out[Path(p[0]).stem] = [int(v) for v in p[2:]]
+    return out
+
+
+class FrameVideoDataset(torch.utils.data.Dataset):
+    """Raw-frame videos in test mode (data.load_from_features=False): the reference's
+    `VideoFrameDataset(test_mode=True)` (video_dataset.py:237-244, 293-351) with the test transform of
+    src/utils/augmentations.py:21-34.  Same constructor keywords; `__getitem__` returns the same
+    5-tuple (frames (T, 3, S, S), labels [frames], label, segment_size, path).
+
+    `output` selects how far the reference's transform runs on the host:
+      "uint8"       PIL bicubic resize of the shorter edge to `input_size` + centre crop (exactly
+                    GroupScale + GroupCenterCrop), frames stay uint8: ToTensor + Normalize happen on
+                    the GPU inside the patchify kernel (4x less host->device traffic).  Default.
+      "normalised"  the reference's full transform: fp32, /255, mean/std normalised.
+      "raw"         decoded frames (T, H, W, 3) uint8 untouched, for `GpuFrameIngest` (resize + crop
+                    on the GPU as well); all frames of a video must have one size.
+    Frames that the wrap-around padding repeats are decoded once."""
+
+    MEAN = (0.48145466, 0.4578275, 0.40821073)
+    STD = (0.26862954, 0.26130258, 0.27577711)
+
+    def __init__(self, root_path: str, annotationfile_path: str, normal_id: int, num_segments: int = 32,
+                 frames_per_segment: int = 16, imagefile_template: str = "{:06d}.jpg", transform=None,
+                 test_mode: bool = True, val_mode: bool = False, ncrops: int = 1,
+                 temporal_annotation_file: Optional[str] = None, labels_file: Optional[str] = None,
+                 stride: int = 1, spatialannotationdir_path: Optional[str] = None,
+                 input_size: int = 224, output: str = "uint8") -> None:
+        if not test_mode or val_mode:
+            raise NotImplementedError("FrameVideoDataset: only test_mode=True (the inference path) exists; "
+                                      "the random training sampler is out of scope")
+        if output not in ("uint8", "normalised", "raw"):
+            raise ValueError(f"FrameVideoDataset: unknown output '{output}'")
+        if ncrops != 1:
+            raise NotImplementedError("FrameVideoDataset: the reference's raw-frame test transform has one crop")
+        self.root_path, self.annotationfile_path = root_path, annotationfile_path
+        self.normal_id, self.num_segments, self.frames_per_segment = normal_id, num_segments, frames_per_segment
+        self.imagefile_template, self.transform, self.stride, self.ncrops = imagefile_template, transform, stride, ncrops
+        self.input_size, self.output = input_size, output
+        self.labels_file = labels_file
+        self.video_list = read_annotation_file(annotationfile_path, root_path)
+        self.annotations = read_temporal_annotations(temporal_annotation_file)
+
+    def __len__(self) -> int:
+        return len(self.video_list)
+
+    def _load(self, directory: str, frame: int) -> np.ndarray:
+        from PIL import Image
+        img = Image.open(str(Path(directory) / self.imagefile_template.format(frame))).convert("RGB")
+        if self.output != "raw":
+            w, h = img.size
+            s = self.input_size
+            ow, oh = (s, int(s * h / w)) if w <= h else (int(s * w / h), s)   # torchvision Resize(int)
+            img = img.resize((ow, oh), Image.BICUBIC)
+            top, left = int(round((oh - s) / 2.0)), int(round((ow - s) / 2.0))  # torchvision CenterCrop
+            img = img.crop((left, top, left + s, top + s))
+        return np.asarray(img)
+
+    def __getitem__(self, i: int):
+        rec = self.video_list[i]
+        labels = frame_labels(rec.num_frames, rec.start_frame, rec.label, self.normal_id,
+                              self.annotations.get(Path(rec.path).stem, ()))
+        idx, segment_size = test_mode_indices(rec.num_frames, self.num_segments,
+                                              self.frames_per_segment, self.stride)
+        uniq, inverse = np.unique(idx, return_inverse=True)
+        decoded = np.stack([self._load(rec.path, int(f) + rec.start_frame) for f in uniq])  # (U, H, W, 3)
+        frames = torch.from_numpy(decoded)
+        if self.output != "raw":
+            frames = frames.permute(0, 3, 1, 2)                                       # (U, 3, S, S)
+            if self.output == "normalised":
+                mean = torch.tensor(self.MEAN).view(1, 3, 1, 1)
+                std = torch.tensor(self.STD).view(1, 3, 1, 1)
+                frames = (frames.to(torch.float32).div(255.0) - mean) / std
+        frames = frames.index_select(0, torch.from_numpy(inverse.astype(np.int64))).contiguous()
+        if self.transform is not None:
+            frames = self.transform(frames)
+        return frames, labels, rec.label, segment_size, rec.path
 
 
 def save_features(path: str, feats: torch.Tensor, ncrops: int = 1) -> str:

@@ -1,0 +1,161 @@
+"""The test-mode data path (reference: src/data/anomaly_clip_datamodule.py, video_dataset.py,
+feature_dataset.py, src/utils/augmentations.py) on small synthetic videos written to a temp dir.
+
+Checked three ways: against the oracle's restatement of the reference loops, against the
+torchvision/PIL transform the reference composes, and -- when /root/reference is present (the build
+container) -- against the reference's own dataset classes loaded from their files."""
+import importlib.util
+from pathlib import Path
+
+import numpy as np
+import pytest
+import torch
+import torchvision.transforms as T
+from PIL import Image
+
+from anomalyclip_b200 import data
+from anomalyclip_b200.datamodule import AnomalyCLIPDataModule
+from oracle import anomalyclip_oracle as oracle
+
+REF = Path("/root/reference/src/data/components")
+MEAN, STD = [0.48145466, 0.4578275, 0.40821073], [0.26862954, 0.26130258, 0.27577711]
+
+
+def _reference_transform():
+    """get_augmentations(224, 1) of src/utils/augmentations.py:21-34, composed from torchvision."""
+    per_frame = T.Compose([T.Resize(224, interpolation=T.InterpolationMode.BICUBIC), T.CenterCrop(224),
+                           T.ToTensor(), T.Normalize(MEAN, STD)])
+    return lambda imgs: torch.stack([per_frame(im) for im in imgs])
+
+
+def _load_reference(name):
+    path = REF / f"{name}.py"
+    if not path.exists():
+        return None
+    spec = importlib.util.spec_from_file_location(f"_ref_{name}", path)
+    mod = importlib.util.module_from_spec(spec)
+    try:
+        spec.loader.exec_module(mod)
+    except ImportError:   # feature_dataset.py pulls in src.utils (Lightning / Hydra), absent here
+        return None
+    return mod
+
+
+@pytest.fixture()
+def frame_videos(tmp_path):
+    """Two videos of PNG frames (lossless, so decoding is exact): 40 frames 60x80 starting at frame
+    id 1, 23 frames 90x70 starting at frame id 5; plus annotation files."""
+    rng = np.random.default_rng(0)
+    spec = {"Abuse/Abuse001_x264": (1, 40, 3, (60, 80)), "Normal/Normal007_x264": (5, 27, 7, (90, 70))}
+    for name, (start, end, _, (h, w)) in spec.items():
+        d = tmp_path / "frames" / name
+        d.mkdir(parents=True)
+        for f in range(start, end + 1):
+            Image.fromarray(rng.integers(0, 256, (h, w, 3), dtype=np.uint8)).save(d / f"{f:06d}.png")
+    (tmp_path / "test.txt").write_text("".join(f"{n} {s} {e} {c}\n" for n, (s, e, c, _) in spec.items()))
+    (tmp_path / "normal.txt").write_text("Normal/Normal007_x264 5 27 7\n")
+    (tmp_path / "temporal.txt").write_text("Abuse001_x264.mp4 Abuse 10 20 33 36\nNormal007_x264.mp4 Normal\n")
+    return tmp_path, spec
+
+
+def test_frame_dataset_matches_the_reference_transform_and_loops(frame_videos):
+    root, spec = frame_videos
+    kw = dict(root_path=str(root / "frames"), annotationfile_path=str(root / "test.txt"), normal_id=7,
+              num_segments=2, frames_per_segment=4, imagefile_template="{:06d}.png", test_mode=True,
+              temporal_annotation_file=str(root / "temporal.txt"))
+    ds_n = data.FrameVideoDataset(output="normalised", **kw)
+    ds_u = data.FrameVideoDataset(output="uint8", **kw)
+    ds_r = data.FrameVideoDataset(output="raw", **kw)
+    transform = _reference_transform()
+    ref_mod = _load_reference("video_dataset")
+    ref_ds = ref_mod.VideoFrameDataset(transform=transform, **kw) if ref_mod is not None else None
+    assert len(ds_n) == 2
+    for i, (name, (start, end, label, (h, w))) in enumerate(spec.items()):
+        frames = end - start + 1
+        idx, seg = oracle.test_mode_frame_indices(frames, 2, 4, 1)
+        imgs = [Image.open(root / "frames" / name / f"{f + start:06d}.png").convert("RGB") for f in idx]
+        want = transform(imgs)
+        x, labels, lab, segment_size, path = ds_n[i]
+        assert x.dtype == torch.float32 and torch.equal(x, want)
+        assert lab == label and segment_size == seg and path == str(root / "frames" / name)
+        intervals = [10, 20, 33, 36] if label == 3 else []
+        assert labels.tolist() == oracle.frame_labels(frames, start, label, 7, intervals)
+        # uint8 frames: the same pixels before ToTensor + Normalize (those run on the GPU)
+        u = ds_u[i][0]
+        assert u.dtype == torch.uint8 and u.shape == (len(idx), 3, 224, 224)
+        assert torch.equal((u.float() / 255 - torch.tensor(MEAN).view(1, 3, 1, 1)) / torch.tensor(STD).view(1, 3, 1, 1), want)
+        r = ds_r[i][0]
+        assert r.shape == (len(idx), h, w, 3) and np.array_equal(r[0].numpy(), np.asarray(imgs[0]))
+        if ref_ds is not None:  # the reference's own class on the same files
+            rx, rlabels, rlab, rseg, rpath = ref_ds[i]
+            assert torch.equal(x, rx) and labels.tolist() == rlabels.tolist()
+            assert (rlab, rseg, rpath) == (lab, segment_size, path)
+
+
+def test_frame_dataset_refuses_what_is_out_of_scope(frame_videos):
+    root, _ = frame_videos
+    kw = dict(root_path=str(root / "frames"), annotationfile_path=str(root / "test.txt"), normal_id=7)
+    with pytest.raises(NotImplementedError):
+        data.FrameVideoDataset(test_mode=False, **kw)
+    with pytest.raises(ValueError):
+        data.FrameVideoDataset(output="jpeg", **kw)
+
+
+def test_datamodule_feature_mode(tmp_path):
+    rng = np.random.default_rng(1)
+    (tmp_path / "feats" / "Abuse").mkdir(parents=True)
+    f1 = rng.standard_normal((700, 512)).astype(np.float32)
+    f2 = rng.standard_normal((100, 512)).astype(np.float32)
+    np.save(tmp_path / "feats" / "Abuse" / "Abuse001_x264.npy", f1)
+    np.save(tmp_path / "feats" / "Normal_100.npy", f2)
+    (tmp_path / "test.txt").write_text("Abuse/Abuse001_x264 0 699 3\nNormal_100 0 99 7\n")   # no suffix, as in the reference
+    (tmp_path / "normal.txt").write_text("Normal_100 0 99 7\n")
+    (tmp_path / "temporal.txt").write_text("Abuse001_x264.mp4 Abuse 100 200\nNormal_100.mp4 Normal\n")
+    dm = AnomalyCLIPDataModule(
+        num_workers=0, pin_memory=False, num_segments=32, seg_length=16, batch_size=64, batch_size_test=1,
+        num_classes=14, input_size=224, load_from_features=True, frames_root=str(tmp_path / "feats"),
+        normal_id=7, image_tmpl="{:06d}.jpg", stride=1, ncrops=1,
+        annotation_file_normal=str(tmp_path / "normal.txt"), annotation_file_test=str(tmp_path / "test.txt"),
+        annotation_file_temporal_test=str(tmp_path / "temporal.txt"), labels_file=None, visualize=False)
+    assert dm.num_classes == 14
+    with pytest.raises(RuntimeError):
+        dm.test_dataloader()
+    dm.setup("test")
+    batches = list(dm.test_dataloader())
+    assert len(batches) == 2 and len(list(dm.train_dataloader_test_mode())) == 1
+    x, labels, label, segment_size, path = batches[0]
+    assert x.shape == (1, 1, 1024, 512) and int(segment_size[0]) == 2 and int(label[0]) == 3
+    assert labels.shape == (1, 700) and labels[0, 100:201].eq(3).all() and int(labels.sum()) == 3 * 101 + 7 * 599
+    assert path[0].endswith("Abuse001_x264.npy")
+    idx, _ = oracle.test_mode_frame_indices(700, 32, 16, 1)
+    assert torch.equal(x[0, 0], torch.from_numpy(f1)[idx])
+    with pytest.raises(NotImplementedError):
+        dm.train_dataloader()
+    ref_mod = _load_reference("feature_dataset")
+    if ref_mod is not None:   # the reference's own feature dataset on the same files
+        ref = ref_mod.VideoFrameDataset(root_path=str(tmp_path / "feats"), annotationfile_path=str(tmp_path / "test.txt"),
+                                        normal_id=7, num_segments=32, frames_per_segment=16, test_mode=True,
+                                        ncrops=1, temporal_annotation_file=str(tmp_path / "temporal.txt"))
+        for i in range(2):
+            rx, rlabels, rlab, rseg, rpath = ref[i]
+            ox, olabels, olab, oseg, opath = dm.test_data[i]
+            assert torch.equal(ox, rx) and olabels.tolist() == rlabels.tolist()
+            assert (olab, oseg, opath) == (rlab, rseg, rpath)
+
+
+def test_datamodule_frame_mode_and_target_path(frame_videos):
+    import importlib
+    root, spec = frame_videos
+    cls = getattr(importlib.import_module("src.data.anomaly_clip_datamodule"), "AnomalyCLIPDataModule")
+    assert cls is AnomalyCLIPDataModule     # configs/data/*.yaml:1 `_target_`
+    dm = cls(num_segments=2, seg_length=4, batch_size_test=1, num_classes=14, input_size=224,
+             load_from_features=False, frames_root=str(root / "frames"), normal_id=7,
+             image_tmpl="{:06d}.png", stride=1, ncrops=1, annotation_file_normal=str(root / "normal.txt"),
+             annotation_file_test=str(root / "test.txt"),
+             annotation_file_temporal_test=str(root / "temporal.txt"))
+    dm.setup()
+    frames, labels, label, segment_size, path = next(iter(dm.test_dataloader()))
+    assert frames.dtype == torch.uint8 and frames.shape == (1, 40, 3, 224, 224)   # 40 frames = 5 x (2*4)
+    assert int(segment_size[0]) == 5 and labels.shape == (1, 40)
+    normal = next(iter(dm.train_dataloader_test_mode()))
+    assert normal[0].shape == (1, 24, 3, 224, 224) and int(normal[2][0]) == 7      # 23 frames padded to 24
