@@ -159,3 +159,71 @@ def test_datamodule_frame_mode_and_target_path(frame_videos):
     assert int(segment_size[0]) == 5 and labels.shape == (1, 40)
     normal = next(iter(dm.train_dataloader_test_mode()))
     assert normal[0].shape == (1, 24, 3, 224, 224) and int(normal[2][0]) == 7      # 23 frames padded to 24
+
+
+def test_evaluate_runs_the_reference_test_sequence(tmp_path):
+    """`evaluate(module, datamodule)` = datamodule.setup -> ncentroid from the normal training videos
+    -> one test_step per video (padded rows trimmed to the real frames) -> test_epoch_end metrics.
+    The net is a small CPU stand-in with the AnomalyCLIP call signature: this checks the host flow,
+    not the kernels."""
+    from torch import nn
+    from anomalyclip_b200.eval import evaluate
+    from anomalyclip_b200.metrics import frame_metrics
+    from anomalyclip_b200.module import AnomalyCLIPModule
+
+    rng = np.random.default_rng(2)
+    (tmp_path / "feats").mkdir()
+    vids = {"Abuse001": (600, 3, [50, 300]), "Fight002": (90, 5, [10, 60]), "Normal003": (130, 7, [])}
+    feats = {}
+    for name, (frames, label, iv) in vids.items():
+        f = rng.standard_normal((frames, 512)).astype(np.float32)
+        if iv:
+            f[iv[0]:iv[1] + 1, :8] += 3.0 * label        # make the anomalous frames separable
+        feats[name] = f
+        np.save(tmp_path / "feats" / f"{name}.npy", f)
+    (tmp_path / "test.txt").write_text("".join(f"{n} 0 {v[0] - 1} {v[1]}\n" for n, v in vids.items()))
+    (tmp_path / "normal.txt").write_text("Normal003 0 129 7\n")
+    (tmp_path / "temporal.txt").write_text("".join(
+        f"{n}.mp4 x {' '.join(map(str, v[2]))}\n" for n, v in vids.items()))
+
+    class Net(nn.Module):
+        embedding_dim, normal_id = 512, 7
+
+        def __init__(self):
+            super().__init__()
+            self.temporal_model = nn.Linear(1, 1)      # gives the module its device
+            self.class_probs = None
+            self.calls = []
+
+        def forward(self, x, labels, ncentroid, segment_size, test_mode):
+            assert test_mode and x.shape[-2] == 512 * segment_size
+            self.calls.append((tuple(x.shape), int(labels.shape[0]), segment_size))
+            z = x.reshape(-1, 512) - ncentroid
+            scores = torch.sigmoid(z[:, :8].mean(1))
+            sim = z[:, :13]
+            self.class_probs = torch.softmax(sim, 1) * scores[:, None]
+            return sim, scores
+
+    dm = AnomalyCLIPDataModule(num_segments=32, seg_length=16, batch_size_test=1, num_classes=14,
+                               load_from_features=True, frames_root=str(tmp_path / "feats"), normal_id=7,
+                               annotation_file_normal=str(tmp_path / "normal.txt"),
+                               annotation_file_test=str(tmp_path / "test.txt"),
+                               annotation_file_temporal_test=str(tmp_path / "temporal.txt"))
+    net = Net()
+    module = AnomalyCLIPModule(net, num_classes=14, save_dir=str(tmp_path / "out"))
+    metrics = evaluate(module, dm)
+    want_centroid = torch.from_numpy(feats["Normal003"]).double().mean(0)
+    assert torch.allclose(module.ncentroid.double().cpu(), want_centroid, atol=1e-6)
+    assert [c[1:] for c in net.calls] == [(600, 2), (90, 1), (130, 1)]     # real frames, segment_size
+    # metrics equal frame_metrics on the trimmed, concatenated outputs computed directly
+    scores, probs, labels = [], [], []
+    for name, (frames, label, iv) in vids.items():
+        z = torch.from_numpy(feats[name]) - module.ncentroid.float().cpu()
+        s = torch.sigmoid(z[:, :8].mean(1))
+        scores.append(s); probs.append(torch.softmax(z[:, :13], 1) * s[:, None])
+        labels.append(torch.from_numpy(data.frame_labels(frames, 0, label, 7, iv)))
+    ref = frame_metrics(torch.cat(scores), torch.cat(probs), torch.cat(labels), 7)
+    assert set(metrics) == {f"test/{k}" for k in ref}
+    for k, v in ref.items():
+        assert abs(metrics[f"test/{k}"] - v) < 1e-6, k
+    assert metrics["test/AUC"] > 0.9 and (tmp_path / "out" / "metrics.json").is_file()
