@@ -21,7 +21,17 @@ def evaluate(module, datamodule, ncentroid: Optional[torch.Tensor] = None,
 
     checkpoint: optional Lightning `.ckpt` (or plain state_dict file); its `state_dict` is loaded
     into the module first, as `Trainer.test(ckpt_path=...)` does.
-    ncentroid: use this centroid instead of the side-car / the normal training videos."""
+    ncentroid: use this centroid instead of the side-car / the normal training videos.
+
+    Under `torch.distributed` (one process per GPU) the videos are dealt round-robin to the ranks,
+    every rank runs `test_step` on its own videos and the per-frame outputs are exchanged once at the
+    end, so every rank returns the metrics of the WHOLE test set (the reference's test path is
+    `@rank_zero_only`, anomaly_clip_module.py:458,500: one GPU does all the work)."""
+    import torch.distributed as dist
+    from torch.utils.data import DataLoader, Subset
+
+    world = dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+    rank = dist.get_rank() if world > 1 else 0
     if checkpoint is not None:
         state = torch.load(checkpoint, map_location="cpu")
         module.load_state_dict(state.get("state_dict", state), strict=False)
@@ -33,8 +43,30 @@ def evaluate(module, datamodule, ncentroid: Optional[torch.Tensor] = None,
         try:
             module.on_test_start()                      # side-car file, if the run directory has one
         except RuntimeError:
-            module.ncentroid = module.compute_ncentroid(datamodule.train_dataloader_test_mode(),
-                                                        datamodule.hparams.load_from_features)
-    for i, batch in enumerate(datamodule.test_dataloader()):
+            loader = datamodule.train_dataloader_test_mode()
+            if world > 1:                               # each rank streams its share; sharded_mean combines
+                mine = list(range(rank, len(loader.dataset), world))
+                loader = DataLoader(Subset(loader.dataset, mine), batch_size=loader.batch_size,
+                                    num_workers=loader.num_workers, pin_memory=loader.pin_memory)
+            module.ncentroid = module.compute_ncentroid(loader, datamodule.hparams.load_from_features)
+    loader = datamodule.test_dataloader()
+    if world == 1:
+        for i, batch in enumerate(loader):
+            module.test_step(batch, i)
+        return module.test_epoch_end()
+
+    mine = list(range(rank, len(loader.dataset), world))
+    shard = DataLoader(Subset(loader.dataset, mine), batch_size=loader.batch_size,
+                       num_workers=loader.num_workers, pin_memory=loader.pin_memory)
+    for i, batch in enumerate(shard):
         module.test_step(batch, i)
+    # one exchange of the per-video outputs; then the lists are put back in dataset order so that
+    # every rank computes exactly what a single process would
+    local = list(zip(mine, module.labels, module.abnormal_scores, module.class_probs))
+    gathered = [None] * world
+    dist.all_gather_object(gathered, local)
+    merged = sorted((item for part in gathered for item in part), key=lambda t: t[0])
+    module.labels = [t[1] for t in merged]
+    module.abnormal_scores = [t[2] for t in merged]
+    module.class_probs = [t[3] for t in merged]
     return module.test_epoch_end()

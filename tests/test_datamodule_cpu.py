@@ -161,30 +161,30 @@ def test_datamodule_frame_mode_and_target_path(frame_videos):
     assert normal[0].shape == (1, 24, 3, 224, 224) and int(normal[2][0]) == 7      # 23 frames padded to 24
 
 
-def test_evaluate_runs_the_reference_test_sequence(tmp_path):
-    """`evaluate(module, datamodule)` = datamodule.setup -> ncentroid from the normal training videos
-    -> one test_step per video (padded rows trimmed to the real frames) -> test_epoch_end metrics.
-    The net is a small CPU stand-in with the AnomalyCLIP call signature: this checks the host flow,
-    not the kernels."""
-    from torch import nn
-    from anomalyclip_b200.eval import evaluate
-    from anomalyclip_b200.metrics import frame_metrics
-    from anomalyclip_b200.module import AnomalyCLIPModule
-
+def _write_feature_videos(root: Path):
     rng = np.random.default_rng(2)
-    (tmp_path / "feats").mkdir()
-    vids = {"Abuse001": (600, 3, [50, 300]), "Fight002": (90, 5, [10, 60]), "Normal003": (130, 7, [])}
+    (root / "feats").mkdir(exist_ok=True)
+    vids = {"Abuse001": (600, 3, [50, 300]), "Fight002": (90, 5, [10, 60]), "Normal003": (130, 7, []),
+            "Normal004": (75, 7, [])}
     feats = {}
     for name, (frames, label, iv) in vids.items():
         f = rng.standard_normal((frames, 512)).astype(np.float32)
         if iv:
             f[iv[0]:iv[1] + 1, :8] += 3.0 * label        # make the anomalous frames separable
         feats[name] = f
-        np.save(tmp_path / "feats" / f"{name}.npy", f)
-    (tmp_path / "test.txt").write_text("".join(f"{n} 0 {v[0] - 1} {v[1]}\n" for n, v in vids.items()))
-    (tmp_path / "normal.txt").write_text("Normal003 0 129 7\n")
-    (tmp_path / "temporal.txt").write_text("".join(
+        np.save(root / "feats" / f"{name}.npy", f)
+    (root / "test.txt").write_text("".join(f"{n} 0 {v[0] - 1} {v[1]}\n" for n, v in vids.items()))
+    (root / "normal.txt").write_text("Normal003 0 129 7\nNormal004 0 74 7\n")
+    (root / "temporal.txt").write_text("".join(
         f"{n}.mp4 x {' '.join(map(str, v[2]))}\n" for n, v in vids.items()))
+    return vids, feats
+
+
+def _stub_module_and_datamodule(root: Path):
+    """A small CPU stand-in with the AnomalyCLIP call signature: the tests below check the host
+    flow (datasets, centroid, trimming, sharding, metrics), not the kernels."""
+    from torch import nn
+    from anomalyclip_b200.module import AnomalyCLIPModule
 
     class Net(nn.Module):
         embedding_dim, normal_id = 512, 7
@@ -198,32 +198,86 @@ def test_evaluate_runs_the_reference_test_sequence(tmp_path):
         def forward(self, x, labels, ncentroid, segment_size, test_mode):
             assert test_mode and x.shape[-2] == 512 * segment_size
             self.calls.append((tuple(x.shape), int(labels.shape[0]), segment_size))
-            z = x.reshape(-1, 512) - ncentroid
+            z = x.reshape(-1, 512) - ncentroid.to(x.dtype)
             scores = torch.sigmoid(z[:, :8].mean(1))
             sim = z[:, :13]
             self.class_probs = torch.softmax(sim, 1) * scores[:, None]
             return sim, scores
 
     dm = AnomalyCLIPDataModule(num_segments=32, seg_length=16, batch_size_test=1, num_classes=14,
-                               load_from_features=True, frames_root=str(tmp_path / "feats"), normal_id=7,
-                               annotation_file_normal=str(tmp_path / "normal.txt"),
-                               annotation_file_test=str(tmp_path / "test.txt"),
-                               annotation_file_temporal_test=str(tmp_path / "temporal.txt"))
+                               load_from_features=True, frames_root=str(root / "feats"), normal_id=7,
+                               annotation_file_normal=str(root / "normal.txt"),
+                               annotation_file_test=str(root / "test.txt"),
+                               annotation_file_temporal_test=str(root / "temporal.txt"))
     net = Net()
-    module = AnomalyCLIPModule(net, num_classes=14, save_dir=str(tmp_path / "out"))
-    metrics = evaluate(module, dm)
-    want_centroid = torch.from_numpy(feats["Normal003"]).double().mean(0)
-    assert torch.allclose(module.ncentroid.double().cpu(), want_centroid, atol=1e-6)
-    assert [c[1:] for c in net.calls] == [(600, 2), (90, 1), (130, 1)]     # real frames, segment_size
-    # metrics equal frame_metrics on the trimmed, concatenated outputs computed directly
+    return AnomalyCLIPModule(net, num_classes=14, save_dir=str(root / "out")), dm, net
+
+
+def _direct_metrics(vids, feats, centroid):
+    from anomalyclip_b200.metrics import frame_metrics
     scores, probs, labels = [], [], []
     for name, (frames, label, iv) in vids.items():
-        z = torch.from_numpy(feats[name]) - module.ncentroid.float().cpu()
+        z = torch.from_numpy(feats[name]) - centroid.float()
         s = torch.sigmoid(z[:, :8].mean(1))
         scores.append(s); probs.append(torch.softmax(z[:, :13], 1) * s[:, None])
         labels.append(torch.from_numpy(data.frame_labels(frames, 0, label, 7, iv)))
-    ref = frame_metrics(torch.cat(scores), torch.cat(probs), torch.cat(labels), 7)
+    return frame_metrics(torch.cat(scores), torch.cat(probs), torch.cat(labels), 7)
+
+
+def test_evaluate_runs_the_reference_test_sequence(tmp_path):
+    """`evaluate(module, datamodule)` = datamodule.setup -> ncentroid from the normal training videos
+    -> one test_step per video (padded rows trimmed to the real frames) -> test_epoch_end metrics."""
+    from anomalyclip_b200.eval import evaluate
+    vids, feats = _write_feature_videos(tmp_path)
+    module, dm, net = _stub_module_and_datamodule(tmp_path)
+    metrics = evaluate(module, dm)
+    normal = torch.from_numpy(np.concatenate([feats["Normal003"], feats["Normal004"]])).double()
+    assert torch.allclose(module.ncentroid.double().cpu(), normal.mean(0), atol=1e-6)
+    assert [c[1:] for c in net.calls] == [(600, 2), (90, 1), (130, 1), (75, 1)]   # real frames, segment_size
+    ref = _direct_metrics(vids, feats, module.ncentroid.cpu())
     assert set(metrics) == {f"test/{k}" for k in ref}
     for k, v in ref.items():
         assert abs(metrics[f"test/{k}"] - v) < 1e-6, k
     assert metrics["test/AUC"] > 0.9 and (tmp_path / "out" / "metrics.json").is_file()
+
+
+def _eval_worker(rank, world, port, root, q):
+    import os
+    import torch.distributed as dist
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anomalyclip_b200.eval import evaluate
+    module, dm, net = _stub_module_and_datamodule(Path(root))
+    metrics = evaluate(module, dm)
+    q.put((rank, metrics, module.ncentroid.double().tolist(), [c[1] for c in net.calls]))
+    dist.destroy_process_group()
+
+
+def test_evaluate_shards_the_videos_over_ranks_gloo(tmp_path):
+    """world_size 2 on CPU: videos are dealt round-robin, the centroid is the all-reduced mean, and both
+    ranks end up with the metrics of the whole test set, identical to the single-process run."""
+    import socket
+    import torch.multiprocessing as mp
+    from anomalyclip_b200.eval import evaluate
+    vids, feats = _write_feature_videos(tmp_path)
+    module, dm, _ = _stub_module_and_datamodule(tmp_path)
+    single = evaluate(module, dm)
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_eval_worker, args=(r, 2, port, str(tmp_path), q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    got = {r: (m, c, calls) for r, m, c, calls in (q.get(timeout=180) for _ in range(2))}
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    # rank 0 saw videos 0 and 2 (the two test_step calls after its one centroid video), rank 1 videos 1 and 3
+    assert got[0][2] == [600, 130] and got[1][2] == [90, 75]
+    for r in (0, 1):
+        assert torch.allclose(torch.tensor(got[r][1], dtype=torch.float64), module.ncentroid.double().cpu(), atol=1e-6)
+        assert set(got[r][0]) == set(single)
+        for k, v in single.items():
+            assert abs(got[r][0][k] - v) < 1e-6, (r, k)
