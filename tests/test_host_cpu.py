@@ -307,3 +307,42 @@ def test_header_is_plain_c():
     res = subprocess.run([gcc, "-fsyntax-only", "-x", "c", "-std=c99", "-Wall", "-Werror",
                           str(ROOT / "include" / "aclip_b200.h")], capture_output=True, text=True)
     assert res.returncode == 0, res.stderr
+
+
+def test_training_side_targets_resolve_and_the_schedule_is_the_reference_curve():
+    """`loss._target_` and `scheduler._target_` of configs/model/*.yaml must import (Hydra builds
+    them for an evaluation run too); the schedule is checked against the reference's own class when
+    /root/reference is present."""
+    import importlib
+    import importlib.util
+    import math
+    import pickle
+    Loss = getattr(importlib.import_module("src.models.components.loss"), "ComputeLoss")
+    Sched = getattr(importlib.import_module("src.models.components.scheduler"), "WarmupCosineAnnealingLR")
+    loss = Loss(normal_id=7, num_topk=3, lambda_dir_abn=1.0, lambda_dir_nor=1.0, lambda_topk_abn=1.0,
+                lambda_bottomk_abn=1.0, lambda_topk_nor=1.0, lambda_smooth=8e-4, lambda_sparse=8e-3,
+                frames_per_segment=16, num_segments=32)
+    assert pickle.loads(pickle.dumps(loss)).lambda_smooth == 8e-4        # hyper_parameters round-trip
+    with pytest.raises(NotImplementedError):
+        loss(None)
+
+    def curve(cls):
+        p = torch.nn.Parameter(torch.zeros(1))
+        opt = torch.optim.SGD([{"params": [p], "lr": 0.1}, {"params": [torch.nn.Parameter(torch.zeros(1))], "lr": 0.02}])
+        sched = cls(opt, total_epoch=50, warmup_epochs=5)
+        out = []
+        for _ in range(60):
+            out.append([g["lr"] for g in opt.param_groups])
+            opt.step()
+            sched.step()
+        return out
+    mine = curve(Sched)
+    assert mine[0] == [0.0, 0.0] and abs(mine[5][0] - 0.1) < 1e-12 and abs(mine[55][0]) < 1e-12
+    assert abs(mine[27][0] - 0.1 * (1 + math.cos(math.pi * 22 / 45)) / 2) < 1e-12
+    ref_file = Path("/root/reference/src/models/components/scheduler.py")
+    if ref_file.exists():
+        spec = importlib.util.spec_from_file_location("_ref_scheduler", ref_file)
+        ref = importlib.util.module_from_spec(spec)
+        spec.loader.exec_module(ref)
+        want = curve(ref.WarmupCosineAnnealingLR)
+        assert all(abs(a - b) < 1e-12 for x, y in zip(mine, want) for a, b in zip(x, y))
