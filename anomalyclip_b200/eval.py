@@ -70,3 +70,32 @@ def evaluate(module, datamodule, ncentroid: Optional[torch.Tensor] = None,
     module.abnormal_scores = [t[2] for t in merged]
     module.class_probs = [t[3] for t in merged]
     return module.test_epoch_end()
+
+
+def main(argv=None) -> Dict[str, float]:
+    """`python -m anomalyclip_b200.eval --configs <AnomalyCLIP>/configs --data ucfcrime --model
+    anomaly_clip_ucfcrime --ckpt last.ckpt [key.path=value ...]`: the reference's `python src/eval.py
+    data=... model=... ckpt_path=...` without Hydra / Lightning (config.py composes the same files)."""
+    import argparse
+    import json
+
+    from .config import instantiate, load_eval_config
+
+    ap = argparse.ArgumentParser(description=main.__doc__)
+    ap.add_argument("--configs", required=True, help="the reference's configs/ directory")
+    ap.add_argument("--data", default="ucfcrime")
+    ap.add_argument("--model", default="anomaly_clip_ucfcrime")
+    ap.add_argument("--ckpt", default=None, help="Lightning checkpoint (state_dict with the reference's key names)")
+    ap.add_argument("--device", default="cuda")
+    ap.add_argument("overrides", nargs="*", help="key.path=value, e.g. data.frames_root=/data/UCF/features")
+    args = ap.parse_args(argv)
+    cfg = load_eval_config(args.configs, args.data, args.model, args.overrides)
+    datamodule, module = instantiate(cfg["data"]), instantiate(cfg["model"])
+    module.to(args.device)
+    metrics = evaluate(module, datamodule, checkpoint=args.ckpt)
+    print(json.dumps(metrics, indent=2, sort_keys=True))
+    return metrics
+
+
+if __name__ == "__main__":
+    main()

@@ -281,3 +281,39 @@ def test_evaluate_shards_the_videos_over_ranks_gloo(tmp_path):
         assert set(got[r][0]) == set(single)
         for k, v in single.items():
             assert abs(got[r][0][k] - v) < 1e-6, (r, k)
+
+
+@pytest.mark.skipif(not Path("/root/reference/configs").is_dir(),
+                    reason="reads the reference's own YAML files (present in the build container)")
+@pytest.mark.parametrize("data_name,model_name,classes,emb,depth,concat", [
+    ("ucfcrime", "anomaly_clip_ucfcrime", 14, 256, 1, False),
+    ("shanghaitech", "anomaly_clip_shanghaitech", None, 256, 2, True),
+    ("xdviolence", "anomaly_clip_xdviolence", 7, 128, 1, False)])
+def test_reference_yaml_configs_instantiate_the_b200_classes(tmp_path, data_name, model_name, classes, emb,
+                                                             depth, concat):
+    """The reference's config files, composed without Hydra, build this repository's datamodule and
+    module: every key is accepted verbatim, `${data.x}` interpolations resolve, partials stay partials."""
+    import functools
+    from anomalyclip_b200.config import instantiate, load_eval_config
+    from anomalyclip_b200.models import AnomalyCLIP
+    from anomalyclip_b200.module import AnomalyCLIPModule
+    from anomalyclip_b200.training_stubs import ComputeLoss, WarmupCosineAnnealingLR
+    labels = {"ucfcrime": "ucf_labels.csv", "shanghaitech": "sht_labels.csv", "xdviolence": "xd_labels.csv"}
+    cfg = load_eval_config("/root/reference/configs", data=data_name, model=model_name, overrides=[
+        f"data.labels_file=/root/reference/data/{labels[data_name]}", f"data.frames_root={tmp_path}",
+        "data.num_workers=0", "model.net.build_text_tower=false"])
+    assert cfg["model"]["net"]["normal_id"] == cfg["data"]["normal_id"]          # ${data.normal_id}
+    assert cfg["model"]["net"]["labels_file"].endswith(labels[data_name])
+    dm = instantiate(cfg["data"])
+    assert isinstance(dm, AnomalyCLIPDataModule) and dm.hparams.num_segments == 32
+    module = instantiate(cfg["model"])
+    assert isinstance(module, AnomalyCLIPModule) and isinstance(module.net, AnomalyCLIP)
+    assert isinstance(module.criterion, ComputeLoss)
+    assert isinstance(module.optimizer, functools.partial) and module.optimizer.func is torch.optim.AdamW
+    assert module.scheduler.func is WarmupCosineAnnealingLR
+    net = module.net
+    assert (net.emb_size, net.depth, bool(net.concat_features)) == (emb, depth, concat)
+    assert net.normal_id == cfg["data"]["normal_id"] and len(net.classnames) == cfg["data"]["num_classes"]
+    if classes is not None:
+        assert len(net.classnames) == classes
+    assert module.num_classes == cfg["data"]["num_classes"]
