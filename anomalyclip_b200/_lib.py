@@ -37,13 +37,15 @@ class GemmArgs(C.Structure):
         ("row_group", C.c_int), ("row_group_stride", C.c_int), ("row_offset", C.c_int),
         ("max_ctas", C.c_int), ("kernel", C.c_int),
         ("out_scale", C.c_float), ("out_enc", C.c_int),
+        ("gather", vp), ("gather_signal", C.c_int), ("gather_row0", C.c_longlong),
     ]
 
 
 class VitBlock(C.Structure):
     _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w",
                                   "out_b", "fc_w", "fc_b", "proj_w", "proj_b")] + \
-               [(n, C.c_float) for n in ("qkv_s", "out_s", "fc_s", "proj_s")]
+               [(n, C.c_float) for n in ("qkv_s", "out_s", "fc_s", "proj_s")] + \
+               [("out_w16", vp)]
 
 
 class VitWeights(C.Structure):
@@ -89,6 +91,7 @@ SIGNATURES = {
     "aclip_version": (C.c_int, []),
     "aclip_last_error": (C.c_char_p, []),
     "aclip_launch_count": (C.c_longlong, []),
+    "aclip_saturation_count": (C.c_longlong, [C.c_int]),
     "aclip_timing_enable": (C.c_int, [C.c_int]),
     "aclip_timing_collect": (C.c_int, [C.POINTER(TimingRow), C.c_int]),
     "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),
@@ -112,6 +115,9 @@ SIGNATURES = {
     "aclip_vit_forward": (C.c_int, [C.POINTER(VitWeights), vp, C.c_int, C.c_longlong, C.c_int,
                                     C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
                                     C.c_size_t, C.c_int, vp]),
+    "aclip_vit_forward_ex": (C.c_int, [C.POINTER(VitWeights), vp, C.c_int, C.c_longlong, C.c_int,
+                                       C.POINTER(C.c_float), C.POINTER(C.c_float), vp, vp,
+                                       C.c_size_t, C.c_int, vp, vp]),
     "aclip_temporal_workspace_bytes": (C.c_size_t, [C.POINTER(TemporalWeights), C.c_longlong]),
     "aclip_temporal_forward": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
                                          vp, vp, vp, C.c_size_t, C.c_int, vp]),
@@ -120,6 +126,7 @@ SIGNATURES = {
     "aclip_temporal_core_forward": (C.c_int, [C.POINTER(TemporalWeights), vp, C.c_longlong, C.c_int, vp,
                                               vp, C.c_size_t, C.c_int, vp]),
     "aclip_peer_wait": (C.c_int, [vp, C.c_int, C.c_uint, vp]),
+    "aclip_peer_signal": (C.c_int, [vp, vp]),
 }
 
 _lib = None
@@ -156,6 +163,15 @@ def check(rc: int) -> None:
 
 def launch_count() -> int:
     return int(load().aclip_launch_count())
+
+
+def saturation_count(reset: bool = False) -> int:
+    """Threads that stored an activation beyond the fp16 range of the f16f8 / f16 encodings on the
+    current CUDA device since the last reset (synchronises the device).  0 on a healthy run."""
+    n = int(load().aclip_saturation_count(int(reset)))
+    if n < 0:
+        check(n)
+    return n
 
 
 def timing_enable(on: bool) -> None:

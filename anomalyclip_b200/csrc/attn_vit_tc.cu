@@ -1,4 +1,7 @@
-// ViT self-attention on the 5th-generation tensor cores (tcgen05 + TMEM), split-bf16 x3.
+// ViT self-attention on the 5th-generation tensor cores (tcgen05 + TMEM): split-bf16 x3, or
+// fp16 operands in one pass (ENC == 2: q | k | v arrive as fp16(x * 2^4) from the in_proj GEMM of the
+// "f16" operand mode, P is rounded to fp16, the output leaves as fp16(o * 2^4); K and V are then
+// double buffered across items because a single plane leaves the room).
 //
 //   softmax(Q K^T / 8) V per (frame, head), L = 197 tokens, head dim 64, no mask
 //   (nn.MultiheadAttention inside ResidualAttentionBlock.attention, clip/model.py:206-212).
@@ -53,6 +56,7 @@ struct AttnTcParams {
   int width;                // heads * 64: column offset of K (and 2x for V) inside a qkv row
   int debug;                // profiling experiments only (0 in production)
   int out_enc;              // 0 = bf16 hi/lo output planes, 1 = f16f8 activation planes (split.cuh)
+  unsigned int* sat;        // fp16 saturation counter (split.cuh) or nullptr
 };
 
 __device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, uint32_t (&v)[16]) {
@@ -175,7 +179,31 @@ __device__ __forceinline__ float softmax_group(uint32_t (&v)[16], int key0, int 
   return sum;
 }
 
-// ENC: output encoding, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes.
+// fp16 variant: v[0..8) = packed fp16 probabilities (one plane); the row sum is taken from the
+// unrounded values.
+template <bool MASK>
+__device__ __forceinline__ float softmax_group_f16(uint32_t (&v)[16], int key0, int L, float sl2, float mb) {
+  float sum = 0.f;
+  uint32_t h[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    float p0 = fast_exp2(fmaf(__uint_as_float(v[2 * j]), sl2, -mb));
+    float p1 = fast_exp2(fmaf(__uint_as_float(v[2 * j + 1]), sl2, -mb));
+    if (MASK) {
+      const int k = key0 + 2 * j;
+      if (k >= L) p0 = 0.f;
+      if (k + 1 >= L) p1 = 0.f;
+    }
+    sum += p0 + p1;
+    asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(p1), "f"(p0));
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) v[j] = h[j];
+  return sum;
+}
+
+// ENC: output encoding, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes, 2 = fp16 in AND out
+// (one operand plane, one MMA pass).
 // GROUPS: number of 16-key groups when known at compile time (13 for the ViT-B/16's 197 tokens: the
 // per-group tests of the softmax loop then fold away, about a quarter of its instructions), 0 = read
 // it from the parameters.
@@ -187,18 +215,21 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
   // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
   uint8_t* smem = att_raw + ((1024u - (ptx::smem_u32(att_raw) & 1023u)) & 1023u);
+  constexpr bool F16 = ENC == 2;
+  constexpr int NPL = F16 ? 1 : 2;            // operand planes
+  constexpr int KVS = F16 ? 2 : 1;            // K / V buffers (items in flight)
   const int kv_plane = p.LP * 128;            // bytes of one plane of K (or V)
-  uint8_t* sK = smem;                         // [2 planes][LP][128 B]
-  uint8_t* sV = sK + 2 * kv_plane;
-  uint8_t* sQ = sV + 2 * kv_plane;            // [2 slots][2 planes][128][128 B]
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + 2 * 2 * Q_PLANE);
-  uint64_t* k_full = bars + 0;  uint64_t* k_empty = bars + 1;
-  uint64_t* v_full = bars + 2;  uint64_t* v_empty = bars + 3;
-  uint64_t* q_full = bars + 4;  uint64_t* q_empty = bars + 6;   // [2]
-  uint64_t* s_full = bars + 8;  uint64_t* p_full = bars + 10;   // [2]
-  uint64_t* o_full = bars + 12; uint64_t* o_empty = bars + 13;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 14);
-  float* max_buf = reinterpret_cast<float*>(bars + 16);   // [2 slots][2 halves][128 rows]
+  uint8_t* sK = smem;                         // [KVS][NPL planes][LP][128 B]
+  uint8_t* sV = sK + KVS * NPL * kv_plane;
+  uint8_t* sQ = sV + KVS * NPL * kv_plane;    // [2 slots][NPL planes][128][128 B]
+  uint64_t* bars = reinterpret_cast<uint64_t*>(sQ + 2 * NPL * Q_PLANE);
+  uint64_t* k_full = bars + 0;  uint64_t* k_empty = bars + 2;   // [KVS]
+  uint64_t* v_full = bars + 4;  uint64_t* v_empty = bars + 6;   // [KVS]
+  uint64_t* q_full = bars + 8;  uint64_t* q_empty = bars + 10;  // [2]
+  uint64_t* s_full = bars + 12; uint64_t* p_full = bars + 14;   // [2]
+  uint64_t* o_full = bars + 16; uint64_t* o_empty = bars + 17;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 18);
+  float* max_buf = reinterpret_cast<float*>(bars + 20);   // [2 slots][2 halves][128 rows]
   float* sum_buf = max_buf + 4 * TILE_Q;                  // [2 slots][2 halves][128 rows]
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(sum_buf + 4 * TILE_Q);  // [4 quarters][2 planes][32][128 B]
 
@@ -206,8 +237,10 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   if (warp == PRODUCER_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
-    ptx::mbar_init(k_full, 1);  ptx::mbar_init(k_empty, 1);
-    ptx::mbar_init(v_full, 1);  ptx::mbar_init(v_empty, 1);
+    for (int i = 0; i < KVS; ++i) {
+      ptx::mbar_init(&k_full[i], 1);  ptx::mbar_init(&k_empty[i], 1);
+      ptx::mbar_init(&v_full[i], 1);  ptx::mbar_init(&v_empty[i], 1);
+    }
     for (int i = 0; i < 2; ++i) {
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);  ptx::mbar_init(&p_full[i], SOFTMAX_WARPS);
@@ -235,17 +268,19 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
         const int item = blockIdx.x + it * gridDim.x;
         const int b = item / p.heads, h = item - b * p.heads;
         const int row0 = b * p.L;
-        ptx::mbar_wait(k_empty, (it & 1) ^ 1);
-        ptx::mbar_expect_tx(k_full, 2 * kv_plane);
-        ptx::tma_load_3d(sK, &tmKV, k_full, p.width + h * HD, row0, 0);
+        const int ks = it % KVS;                      // K / V buffer of this item
+        const uint32_t kph = (it / KVS) & 1;
+        ptx::mbar_wait(&k_empty[ks], kph ^ 1);
+        ptx::mbar_expect_tx(&k_full[ks], NPL * kv_plane);
+        ptx::tma_load_3d(sK + ks * NPL * kv_plane, &tmKV, &k_full[ks], p.width + h * HD, row0, 0);
         for (int q = 0; q < 2; ++q) {
           ptx::mbar_wait(&q_empty[q], (it & 1) ^ 1);
-          ptx::mbar_expect_tx(&q_full[q], 2 * Q_PLANE);
-          ptx::tma_load_3d(sQ + q * 2 * Q_PLANE, &tmQ, &q_full[q], h * HD, row0 + q * TILE_Q, 0);
+          ptx::mbar_expect_tx(&q_full[q], NPL * Q_PLANE);
+          ptx::tma_load_3d(sQ + q * NPL * Q_PLANE, &tmQ, &q_full[q], h * HD, row0 + q * TILE_Q, 0);
         }
-        ptx::mbar_wait(v_empty, (it & 1) ^ 1);
-        ptx::mbar_expect_tx(v_full, 2 * kv_plane);
-        ptx::tma_load_3d(sV, &tmKV, v_full, 2 * p.width + h * HD, row0, 0);
+        ptx::mbar_wait(&v_empty[ks], kph ^ 1);
+        ptx::mbar_expect_tx(&v_full[ks], NPL * kv_plane);
+        ptx::tma_load_3d(sV + ks * NPL * kv_plane, &tmKV, &v_full[ks], 2 * p.width + h * HD, row0, 0);
       }
     }
   } else if (warp == MMA_WARP) {
@@ -253,53 +288,63 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     // The whole warp stays converged; one elected lane issues (see mma_ss_if).
     {
       const bool leader = ptx::elect_one();
-      const uint32_t idesc_qk = ptx::make_idesc_bf16_f32(TILE_Q, p.LP);
-      const uint32_t idesc_pv = ptx::make_idesc_bf16_f32(TILE_Q, HD) | (1u << 16);  // B is MN-major
+      // operand format code 0 = fp16 under kind::f16 (ptx::make_idesc_fmt0_f32), else bf16
+      const uint32_t idesc_qk = F16 ? ptx::make_idesc_fmt0_f32(TILE_Q, p.LP)
+                                    : ptx::make_idesc_bf16_f32(TILE_Q, p.LP);
+      const uint32_t idesc_pv = (F16 ? ptx::make_idesc_fmt0_f32(TILE_Q, HD)
+                                     : ptx::make_idesc_bf16_f32(TILE_Q, HD)) | (1u << 16);  // B is MN-major
       const uint32_t k_base = ptx::smem_u32(sK), v_base = ptx::smem_u32(sV);
       const int ksteps = p.LP >> 4;
       // descriptors advance by a constant in their low word: +2 (32 bytes >> 4) per 16-wide K step
       // of a K-major operand, +128 (2048 bytes >> 4) per 16 keys of the MN-major V operand
-      const uint64_t kd_hi = ptx::make_kmajor_sw128_desc(k_base);
-      const uint64_t kd_lo = ptx::make_kmajor_sw128_desc(k_base + kv_plane);
-      const uint64_t vd_hi = make_mnmajor_sw128_desc(v_base);
-      const uint64_t vd_lo = make_mnmajor_sw128_desc(v_base + kv_plane);
+      const uint64_t kd_hi0 = ptx::make_kmajor_sw128_desc(k_base);
+      const uint64_t vd_hi0 = make_mnmajor_sw128_desc(v_base);
+      const uint64_t lo_off = static_cast<uint64_t>(kv_plane >> 4);    // hi -> lo plane (NPL == 2)
+      const uint64_t slot_off = static_cast<uint64_t>((NPL * kv_plane) >> 4);  // K / V buffer stride
 
       auto issue_qk = [&](int J) {  // S[J % 2] = Q_J K^T
         const int it = J >> 1, q = J & 1;
-        if (q == 0) { ptx::mbar_wait(k_full, it & 1); }
+        const int ks = it % KVS;
+        if (q == 0) { ptx::mbar_wait(&k_full[ks], (it / KVS) & 1); }
         ptx::mbar_wait(&q_full[q], it & 1);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + q * S_STRIDE;
-        const uint32_t q_base = ptx::smem_u32(sQ + q * 2 * Q_PLANE);
+        const uint32_t q_base = ptx::smem_u32(sQ + q * NPL * Q_PLANE);
         const uint64_t qd_hi = ptx::make_kmajor_sw128_desc(q_base);
-        const uint64_t qd_lo = ptx::make_kmajor_sw128_desc(q_base + Q_PLANE);
+        const uint64_t kd_hi = kd_hi0 + ks * slot_off;
 #pragma unroll
         for (int k = 0; k < HD / 16; ++k) {
           mma_ss_if(leader, d, qd_hi + 2 * k, kd_hi + 2 * k, idesc_qk, k != 0 ? 1u : 0u);
-          mma_ss_if(leader, d, qd_lo + 2 * k, kd_hi + 2 * k, idesc_qk, 1u);
-          mma_ss_if(leader, d, qd_hi + 2 * k, kd_lo + 2 * k, idesc_qk, 1u);
+          if (!F16) {
+            mma_ss_if(leader, d, qd_hi + (Q_PLANE >> 4) + 2 * k, kd_hi + 2 * k, idesc_qk, 1u);
+            mma_ss_if(leader, d, qd_hi + 2 * k, kd_hi + lo_off + 2 * k, idesc_qk, 1u);
+          }
         }
         commit_if(leader, &s_full[q]);
         commit_if(leader, &q_empty[q]);
-        if (q == 1) commit_if(leader, k_empty);
+        if (q == 1) commit_if(leader, &k_empty[ks]);
       };
       auto issue_pv = [&](int J) {  // O = P_J V
         const int it = J >> 1, q = J & 1;
-        if (q == 0) { ptx::mbar_wait(v_full, it & 1); }
+        const int ks = it % KVS;
+        if (q == 0) { ptx::mbar_wait(&v_full[ks], (it / KVS) & 1); }
         ptx::mbar_wait(&p_full[q], it & 1);
         ptx::mbar_wait(o_empty, (J & 1) ^ 1);
         ptx::tc_fence_after();
         const uint32_t d = tmem_base + O_COL;
         const uint32_t a_hi0 = tmem_base + q * S_STRIDE;
         const uint32_t a_lo0 = a_hi0 + PLO_OFF;
+        const uint64_t vd_hi = vd_hi0 + ks * slot_off;
 #pragma unroll 1
         for (int k = 0; k < ksteps; ++k) {
           mma_ts_if(leader, d, a_hi0 + 8 * k, vd_hi + 128 * k, idesc_pv, k != 0 ? 1u : 0u);
-          mma_ts_if(leader, d, a_lo0 + 8 * k, vd_hi + 128 * k, idesc_pv, 1u);
-          mma_ts_if(leader, d, a_hi0 + 8 * k, vd_lo + 128 * k, idesc_pv, 1u);
+          if (!F16) {
+            mma_ts_if(leader, d, a_lo0 + 8 * k, vd_hi + 128 * k, idesc_pv, 1u);
+            mma_ts_if(leader, d, a_hi0 + 8 * k, vd_hi + lo_off + 128 * k, idesc_pv, 1u);
+          }
         }
         commit_if(leader, o_full);
-        if (q == 1) commit_if(leader, v_empty);
+        if (q == 1) commit_if(leader, &v_empty[ks]);
       };
 
       if (my_tiles > 0) issue_qk(0);
@@ -337,6 +382,40 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       // 32 dims, then write whole 128-byte rows: 4 rows per store instruction instead of 32
       // scattered 16-byte pieces.  16-byte chunks are XOR-swizzled by the row to avoid conflicts.
       uint8_t* stage = out_stage + quarter * (2 * 32 * 128);
+      if (ENC == 2) {
+        // fp16 rows: the accumulator already carries the 2^4 of the V operand, so o / rowsum is the
+        // encoded value; this warp's 32 dims are 64 bytes of the 128-byte row
+        float amax = 0.f;
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          uint32_t h[4];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float a = __uint_as_float(o[8 * c + 2 * j]) * inv_sum;
+            const float bb = __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum;
+            amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(bb)));
+            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(bb), "f"(a));
+          }
+          const int chunk = (half * 4 + c) ^ (lane & 7);
+          *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
+        }
+        if (p.sat != nullptr && !(amax <= 65504.0f)) atomicAdd(p.sat, 1u);
+        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
+        const int row_base = q * TILE_Q + quarter * 32;
+        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
+        const long long off0 = (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const int row = half * 16 + i * 4 + (lane >> 3);
+          const int chunk = lane & 7;
+          if (row_base + row < p.L) {
+            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
+            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) =
+                *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) * 16));
+          }
+        }
+        return;
+      }
       if (ENC == 1) {
         // f16f8: buffer 0 holds the fp16 rows (128 B), buffer 1 the e4m3 rows [L 64 B | C 64 B]
 #pragma unroll
@@ -448,13 +527,18 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       for (int gi = 0; gi < HALF_GROUPS; ++gi)
         if (GC ? gi < GC : gi < g_count) {
           const int g = (GC ? GB : g_begin) + gi;
-          if (!(p.debug & 1))
-            sum += (GC ? (GB + gi < GROUPS - 1) : (16 * g + 16 <= p.L))
-                       ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
-                       : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+          if (!(p.debug & 1)) {
+            const bool whole = GC ? (GB + gi < GROUPS - 1) : (16 * g + 16 <= p.L);
+            if (F16)
+              sum += whole ? softmax_group_f16<false>(v[gi], 16 * g, p.L, p.sl2, mb)
+                           : softmax_group_f16<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+            else
+              sum += whole ? softmax_group<false>(v[gi], 16 * g, p.L, p.sl2, mb)
+                           : softmax_group<true>(v[gi], 16 * g, p.L, p.sl2, mb);
+          }
           if (!(p.debug & 4)) {
-            tmem_st_x8(s_addr + 8 * g, &v[gi][0]);             // hi plane, packed
-            tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
+            tmem_st_x8(s_addr + 8 * g, &v[gi][0]);                       // hi (or fp16) plane, packed
+            if (!F16) tmem_st_x8(s_addr + PLO_OFF + 8 * g, &v[gi][8]);   // lo plane, packed
           }
         }
       sum_buf[slot * 2 * TILE_Q + half * TILE_Q + row_in_tile] = sum;
@@ -513,8 +597,11 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
                      int heads, void* out_split, long long out_plane_stride, int ld_out,
                      cudaStream_t stream, int debug, int out_enc) {
   ACLIP_REQUIRE(qkv_split != nullptr && out_split != nullptr, "vit_attention: null pointer");
-  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && ld_out % 16 == 0 && out_plane_stride % 16 == 0),
+  ACLIP_REQUIRE(out_enc == 0 || out_enc == 2 ||
+                    (out_enc == 1 && ld_out % 16 == 0 && out_plane_stride % 16 == 0),
                 "vit_attention: out_enc=%d unsupported (f16f8 needs 16-element pitches)", out_enc);
+  const bool f16 = out_enc == 2;   // fp16 q | k | v in, fp16 out, one MMA pass
+  const int npl = f16 ? 1 : 2;
   ACLIP_REQUIRE(B > 0 && heads > 0 && L > 0, "vit_attention: empty problem");
   const int LP = (L + 15) / 16 * 16;
   ACLIP_REQUIRE(LP <= MAX_LP, "vit_attention: L=%d exceeds the %d-token limit", L, MAX_LP);
@@ -530,15 +617,17 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   const long long rows = static_cast<long long>(B) * L;
   CUtensorMap tmQ, tmKV;
   {
-    cuuint64_t dims[3] = {(cuuint64_t)ld_in, (cuuint64_t)rows, 2};
-    cuuint64_t strides[2] = {(cuuint64_t)ld_in * 2, (cuuint64_t)in_plane_stride * 2};
+    cuuint64_t dims[3] = {(cuuint64_t)ld_in, (cuuint64_t)rows, (cuuint64_t)npl};
+    cuuint64_t strides[2] = {(cuuint64_t)ld_in * 2,
+                             f16 ? (cuuint64_t)ld_in * 2 * (cuuint64_t)rows : (cuuint64_t)in_plane_stride * 2};
     cuuint32_t estr[3] = {1, 1, 1};
-    cuuint32_t box_q[3] = {64, TILE_Q, 2};
-    cuuint32_t box_kv[3] = {64, (cuuint32_t)LP, 2};
-    CUresult r1 = enc(&tmQ, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv_split), dims,
+    cuuint32_t box_q[3] = {64, TILE_Q, (cuuint32_t)npl};
+    cuuint32_t box_kv[3] = {64, (cuuint32_t)LP, (cuuint32_t)npl};
+    const CUtensorMapDataType dt = f16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+    CUresult r1 = enc(&tmQ, dt, 3, const_cast<void*>(qkv_split), dims,
                       strides, box_q, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-    CUresult r2 = enc(&tmKV, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 3, const_cast<void*>(qkv_split), dims,
+    CUresult r2 = enc(&tmKV, dt, 3, const_cast<void*>(qkv_split), dims,
                       strides, box_kv, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
                       CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r1 != CUDA_SUCCESS || r2 != CUDA_SUCCESS)
@@ -547,13 +636,16 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   AttnTcParams p{};
   p.L = L; p.LP = LP; p.heads = heads; p.items = B * heads;
   p.sl2 = 1.4426950408889634f / sqrtf(static_cast<float>(HD));
+  if (f16) p.sl2 /= kActScaleMain * kActScaleMain;   // S = (2^4 q) . (2^4 k)
+  p.sat = f16 ? saturation_counter() : nullptr;
   p.out = static_cast<__nv_bfloat16*>(out_split);
   p.out_plane_stride = out_plane_stride;
   p.ld_out = ld_out;
   p.width = heads * HD;
   p.debug = debug;
   p.out_enc = out_enc;
-  const int smem = 4 * LP * 128 + 4 * Q_PLANE + 8192 + 32768 + 1024;
+  // K and V: two planes, or (fp16) one plane in two buffers: 4 * LP * 128 either way
+  const int smem = 4 * LP * 128 + 2 * npl * Q_PLANE + 8192 + 32768 + 1024;
   static PerDeviceOnce once;
   int once_dev;
   if (once.need(once_dev)) {
@@ -566,6 +658,10 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<1, 13>,
                                        cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<2, 0>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
+    ACLIP_CUDA_OK(cudaFuncSetAttribute(vit_attention_tc_kernel<2, 13>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, kMaxSmem));
     once.mark(once_dev);
   }
   int ctas = sm_count();
@@ -574,7 +670,10 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   // 13 key groups (193..208 tokens, the ViT-B/16 case) have a specialised instantiation; debug & 8
   // (profiling experiments) forces the generic one
   const bool fixed13 = LP == 208 && !(debug & 8);
-  if (out_enc == 1) {
+  if (out_enc == 2) {
+    if (fixed13) vit_attention_tc_kernel<2, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    else vit_attention_tc_kernel<2, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+  } else if (out_enc == 1) {
     if (fixed13) vit_attention_tc_kernel<1, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
     else vit_attention_tc_kernel<1, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
   } else {
@@ -582,10 +681,38 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
     else vit_attention_tc_kernel<0, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
   }
   timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
-             (double)B * L * heads * HD * (3 * 4.0 + 4.0));
+             (double)B * L * heads * HD * (f16 ? 3 * 2.0 + 2.0 : 3 * 4.0 + 4.0));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
 }
 
 }  // namespace aclip
+
+namespace aclip {
+// kernel: 0 / 2 = the tcgen05 kernel above (the warp-level mma.sync kernel of round 1 is gone);
+// kernel >= 16 = profiling experiments, only with ACLIP_PROFILING_EXPERIMENTS=1 in the environment
+// (16 + mask: skip softmax math / output stores / TMEM stores; results WRONG by construction).
+int vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
+                  int heads, void* out_split, long long out_plane_stride, int ld_out, int kernel,
+                  int out_enc, cudaStream_t stream) {
+  if (kernel >= 16) {
+    const char* allow = getenv("ACLIP_PROFILING_EXPERIMENTS");
+    ACLIP_REQUIRE(allow != nullptr && allow[0] == '1',
+                  "vit_attention: kernel must be 0 or 2 (got %d)", kernel);
+    return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                            out_plane_stride, ld_out, stream, kernel - 16, out_enc);
+  }
+  ACLIP_REQUIRE(kernel == 0 || kernel == 2, "vit_attention: kernel must be 0 or 2 (got %d)", kernel);
+  return vit_attention_tc(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                          out_plane_stride, ld_out, stream, 0, out_enc);
+}
+}  // namespace aclip
+
+extern "C" int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in,
+                                   int B, int L, int heads, void* out_split,
+                                   long long out_plane_stride, int ld_out, int kernel,
+                                   int out_enc, void* stream) {
+  return aclip::vit_attention(qkv_split, in_plane_stride, ld_in, B, L, heads, out_split,
+                              out_plane_stride, ld_out, kernel, out_enc, aclip::as_stream(stream));
+}

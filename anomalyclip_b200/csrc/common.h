@@ -14,6 +14,8 @@ namespace aclip {
 std::string& last_error();
 int fail(int code, const char* fmt, ...);
 int sm_count();
+// Device address of this device's fp16 saturation counter (split.cuh), nullptr if unavailable.
+unsigned int* saturation_counter();
 extern std::atomic<long long> g_launches;  // kernels launched by this library
 int gemm(const AclipGemmArgs& g, cudaStream_t stream);
 struct RowMap;

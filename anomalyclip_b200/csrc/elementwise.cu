@@ -12,6 +12,29 @@ __device__ __forceinline__ void split2(float a, float b, uint32_t& hi, uint32_t&
   split_pack2(a, b, hi, lo);
 }
 
+// ------------------------------------------------------------------------------ saturation guard
+// Per-device counter of threads that stored a value beyond the fp16 range of the activation
+// encodings (split.cuh: sat_track / sat_report).  Kernels of other translation units receive its
+// device address as a parameter.
+__device__ unsigned int g_f16_saturations = 0;
+
+unsigned int* saturation_counter() {
+  static std::atomic<unsigned int*> cached[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+  unsigned int* ptr = cached[dev].load(std::memory_order_acquire);
+  if (ptr == nullptr) {
+    void* sym = nullptr;
+    if (cudaGetSymbolAddress(&sym, g_f16_saturations) != cudaSuccess) {
+      cudaGetLastError();
+      return nullptr;
+    }
+    ptr = static_cast<unsigned int*>(sym);
+    cached[dev].store(ptr, std::memory_order_release);
+  }
+  return ptr;
+}
+
 // ------------------------------------------------------------------------------ split
 __global__ void __launch_bounds__(256)
 split_kernel(const float* __restrict__ in, long long rows, int cols, int ld_in,
@@ -141,11 +164,13 @@ struct Norm3 { float mean[3]; float std[3]; };
 template <bool U8, int ENC>
 __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
-                __nv_bfloat16* __restrict__ out, long long plane_stride) {
+                __nv_bfloat16* __restrict__ out, long long plane_stride,
+                unsigned int* __restrict__ sat) {
   const int G = R / P;
   const int K = 3 * P * P;
   const int groups_per_row = K >> 3;
   const long long total = static_cast<long long>(B) * G * G * groups_per_row;
+  float amax = 0.f;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long row = i / groups_per_row;
@@ -172,9 +197,18 @@ patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
       v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w;
       v[4] = bb.x; v[5] = bb.y; v[6] = bb.z; v[7] = bb.w;
     }
+    if (ENC != 0) amax = sat_track(sat_track(amax, v[0], v[1], v[2], v[3]), v[4], v[5], v[6], v[7]);
     if (ENC == 1) {
       f16f8_store4_act(out, plane_stride, row * K + k, v[0], v[1], v[2], v[3]);
       f16f8_store4_act(out, plane_stride, row * K + k + 4, v[4], v[5], v[6], v[7]);
+      continue;
+    }
+    if (ENC == 2) {
+      uint2 h0, h1;
+      f16_pack4(v[0], v[1], v[2], v[3], h0);
+      f16_pack4(v[4], v[5], v[6], v[7], h1);
+      *reinterpret_cast<uint4*>(reinterpret_cast<uint8_t*>(out) + 2 * (row * K + k)) =
+          make_uint4(h0.x, h0.y, h1.x, h1.y);
       continue;
     }
     uint32_t hi[4], lo[4];
@@ -184,13 +218,15 @@ patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
     *reinterpret_cast<uint4*>(dst) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(dst + plane_stride) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
+  if (ENC != 0) sat_report(sat, amax);
 }
 
 int patchify(const void* frames, int is_u8, int B, int R, int P, const float* mean3,
              const float* std3, void* out_split, long long plane_stride, int out_enc,
              cudaStream_t stream) {
   ACLIP_REQUIRE(frames != nullptr && out_split != nullptr, "patchify: null pointer");
-  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && plane_stride % 16 == 0 && (3 * P * P) % 16 == 0),
+  ACLIP_REQUIRE(out_enc == 0 || out_enc == 2 ||
+                    (out_enc == 1 && plane_stride % 16 == 0 && (3 * P * P) % 16 == 0),
                 "patchify: out_enc=%d unsupported", out_enc);
   ACLIP_REQUIRE(B > 0 && P % 8 == 0 && R % P == 0, "patchify: B=%d R=%d P=%d unsupported", B, R, P);
   ACLIP_REQUIRE((reinterpret_cast<uintptr_t>(frames) & 15) == 0, "patchify: frames must be 16-byte aligned");
@@ -204,15 +240,21 @@ int patchify(const void* frames, int is_u8, int B, int R, int P, const float* me
   auto* o = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_PATCHIFY, stream);
   const int grid = grid_for(total, 256);
-  if (is_u8 && out_enc == 1)
-    patchify_kernel<true, 1><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
-  else if (is_u8)
-    patchify_kernel<true, 0><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
-  else if (out_enc == 1)
-    patchify_kernel<false, 1><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
-  else
-    patchify_kernel<false, 0><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride);
-  timing_end(KIND_PATCHIFY, stream, 0.0, (double)B * 3 * R * R * ((is_u8 ? 1.0 : 4.0) + 4.0));
+  unsigned int* sat = out_enc != 0 ? saturation_counter() : nullptr;
+#define ACLIP_PATCHIFY(U8, ENC) \
+  patchify_kernel<U8, ENC><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride, sat)
+  if (is_u8) {
+    if (out_enc == 2) ACLIP_PATCHIFY(true, 2);
+    else if (out_enc == 1) ACLIP_PATCHIFY(true, 1);
+    else ACLIP_PATCHIFY(true, 0);
+  } else {
+    if (out_enc == 2) ACLIP_PATCHIFY(false, 2);
+    else if (out_enc == 1) ACLIP_PATCHIFY(false, 1);
+    else ACLIP_PATCHIFY(false, 0);
+  }
+#undef ACLIP_PATCHIFY
+  timing_end(KIND_PATCHIFY, stream, 0.0,
+             (double)B * 3 * R * R * ((is_u8 ? 1.0 : 4.0) + (out_enc == 2 ? 2.0 : 4.0)));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -318,4 +360,18 @@ extern "C" int aclip_patchify(const void* frames, int frames_are_u8, int B, int 
                               long long plane_stride, int out_enc, void* stream) {
   return aclip::patchify(frames, frames_are_u8, B, R, P, mean3_host, std3_host, out_split,
                          plane_stride, out_enc, aclip::as_stream(stream));
+}
+
+extern "C" long long aclip_saturation_count(int reset) {
+  unsigned int* ptr = aclip::saturation_counter();
+  if (ptr == nullptr) return aclip::fail(ACLIP_ERR_CUDA, "saturation_count: no counter on this device");
+  unsigned int v = 0;
+  if (cudaMemcpy(&v, ptr, sizeof(v), cudaMemcpyDeviceToHost) != cudaSuccess)
+    return aclip::fail(ACLIP_ERR_CUDA, "saturation_count: cudaMemcpy failed");
+  if (reset != 0 && v != 0) {
+    const unsigned int zero = 0;
+    if (cudaMemcpy(ptr, &zero, sizeof(zero), cudaMemcpyHostToDevice) != cudaSuccess)
+      return aclip::fail(ACLIP_ERR_CUDA, "saturation_count: reset failed");
+  }
+  return static_cast<long long>(v);
 }

@@ -130,8 +130,9 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   timing_begin(KIND_GEMM, stream);
   kernel<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA8, tmB8, p);
   {
-    const double planes = PASSES == 1 ? 1.0 : 2.0;
-    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
+    const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : 2.0;
+    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? (p.out_enc == 2 ? 2.0 : 4.0) : 0.0) +
+                         (p.residual ? 4.0 : 0.0);
     const double a_elems = p.a_mode == 1 ? (double)p.M * (p.K / 9) : (double)p.M * p.K;
     timing_end(KIND_GEMM, stream, 2.0 * p.M * (double)p.N * p.K,
                planes * 2.0 * (a_elems + (double)p.N * p.K) + out_b * (double)p.M * p.N);
@@ -141,69 +142,23 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   return ACLIP_OK;
 }
 
-template <int PASSES>
-static int launch_quad(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA8,
-                       const CUtensorMap& tmB8, const GemmParams& p, int max_ctas,
-                       cudaStream_t stream) {
-  using Cfg = Gemm2Cfg<PASSES>;
-  auto kernel = gemm4_tcgen05_kernel<PASSES>;
-  static PerDeviceOnce once;
-  int once_dev;
-  if (once.need(once_dev)) {
-    ACLIP_CUDA_OK(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       Cfg::SMEM_BYTES));
-    once.mark(once_dev);
-  }
-  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
-  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
-  const int super_tiles = ((m_tiles + 1) / 2) * n_tiles;
-  // A persistent grid must be fully co-resident: clusters of four only fit where a GPC has four
-  // free SMs, so ask the driver how many can be active at once (per device, cached).
-  static std::atomic<int> max_clusters[64];
-  int cap = 0;
-  if (once_dev >= 0 && once_dev < 64) cap = max_clusters[once_dev].load(std::memory_order_relaxed);
-  if (cap == 0) {
-    cudaLaunchConfig_t cfg{};
-    cfg.gridDim = dim3(4 * (sm_count() / 4));
-    cfg.blockDim = dim3(Cfg::THREADS);
-    cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
-    cudaLaunchAttribute attr{};
-    attr.id = cudaLaunchAttributeClusterDimension;
-    attr.val.clusterDim.x = 4; attr.val.clusterDim.y = 1; attr.val.clusterDim.z = 1;
-    cfg.attrs = &attr;
-    cfg.numAttrs = 1;
-    if (cudaOccupancyMaxActiveClusters(&cap, kernel, &cfg) != cudaSuccess || cap <= 0) {
-      cudaGetLastError();
-      cap = sm_count() / 4;
-    }
-    if (getenv("ACLIP_DEBUG") != nullptr) fprintf(stderr, "[aclip] four-CTA clusters co-resident: %d\n", cap);
-    if (once_dev >= 0 && once_dev < 64) max_clusters[once_dev].store(cap, std::memory_order_relaxed);
-  }
-  int clusters = max_ctas > 0 ? max_ctas / 4 : cap;
-  if (clusters > cap) clusters = cap;
-  if (clusters > super_tiles) clusters = super_tiles;
-  if (clusters < 1) clusters = 1;
-  timing_begin(KIND_GEMM, stream);
-  kernel<<<4 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA8, tmB8, p);
-  {
-    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
-    timing_end(KIND_GEMM, stream, 2.0 * p.M * (double)p.N * p.K,
-               4.0 * ((double)p.M * p.K + (double)p.N * p.K) + out_b * (double)p.M * p.N);
-  }
-  ACLIP_CHECK_LAUNCH();
-  g_launches.fetch_add(1, std::memory_order_relaxed);
-  return ACLIP_OK;
-}
-
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  ACLIP_REQUIRE(g.passes >= 1 && g.passes <= 3, "gemm: passes must be 1, 2 or 3 (got %d)", g.passes);
-  ACLIP_REQUIRE(g.out_enc == 0 || g.out_enc == 1, "gemm: out_enc must be 0 (bf16 hi/lo) or 1 (f16f8)");
+  ACLIP_REQUIRE(g.passes >= 1 && g.passes <= 4, "gemm: passes must be 1, 2, 3 or 4 (got %d)", g.passes);
+  ACLIP_REQUIRE(g.out_enc >= 0 && g.out_enc <= 2,
+                "gemm: out_enc must be 0 (bf16 hi/lo), 1 (f16f8) or 2 (fp16 plane)");
+  if (g.passes == 4) {
+    // fp16 operands, one pass: A is an fp16 matrix [M][lda] (or NHWC grid), W the fp16 plane of a
+    // weight packed with aclip_encode_f16f8; CTA-pair kernel only
+    ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1,
+                  "gemm: passes=4 (fp16 operands) runs on the CTA-pair kernel: N %% 256 == 0 (N=%d)", g.N);
+    ACLIP_REQUIRE(g.out_scale > 0.0f, "gemm: passes=4 needs out_scale = 2^-(e_act + e_weight)");
+  }
   if (g.passes == 2) {
-    // f16f8 operands (split.cuh): CTA-pair kernels only (the four-CTA one: linear A only)
+    // f16f8 operands (split.cuh): CTA-pair kernel only
     ACLIP_REQUIRE(g.a_mode == 0 || g.a_mode == 1, "gemm: unknown a_mode %d", g.a_mode);
-    ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1 && (g.a_mode == 0 || g.kernel != 4),
+    ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1,
                   "gemm: passes=2 (f16f8 operands) runs on the CTA-pair kernel: N %% 256 == 0 (N=%d)", g.N);
     ACLIP_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.a_plane_stride % 16 == 0 &&
                       g.w_plane_stride % 16 == 0,
@@ -229,18 +184,16 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.residual == nullptr || (g.ldr % 4 == 0 && g.ldr >= g.N), "gemm: ldr=%d invalid",
                 g.ldr);
   ACLIP_REQUIRE(g.act >= 0 && g.act <= 2, "gemm: unknown activation %d", g.act);
-  const int planes = g.passes == 1 ? 1 : 2;
+  const int planes = (g.passes == 1 || g.passes == 4) ? 1 : 2;
+  const CUtensorMapDataType op_dtype =
+      g.passes == 4 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
   // 128-wide tiles when they waste fewer padded columns than 256-wide ones (e.g. N = 128, 384)
   // CTA-pair kernel (256 x 256 tiles over two SMs) whenever N tiles evenly and there is enough
   // work to fill the machine; kernel = 1 / 2 forces the single-CTA / pair kernel (tests).
-  ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2 || g.kernel == 4,
-                "gemm: kernel must be 0 (auto), 1 (single CTA), 2 (CTA pair) or 4 (two pairs sharing W)");
-  ACLIP_REQUIRE((g.kernel != 2 && g.kernel != 4) || g.N % 256 == 0,
-                "gemm: the CTA-pair kernels need N %% 256 == 0");
-  ACLIP_REQUIRE(g.kernel != 4 || (g.passes != 1 && g.a_mode == 0),
-                "gemm: the four-CTA kernel needs passes 2 or 3 and a linear A operand");
-  const bool quad = g.kernel == 4;
-  const bool pair = quad || g.kernel == 2 || g.passes == 2 ||
+  ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2,
+                "gemm: kernel must be 0 (auto), 1 (single CTA) or 2 (CTA pair)");
+  ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
+  const bool pair = g.kernel == 2 || g.passes == 2 || g.passes == 4 ||
                     (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
@@ -276,6 +229,23 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   p.row_offset = g.row_offset;
   p.out_scale = g.out_scale > 0.0f ? g.out_scale : 1.0f;
   p.out_enc = g.out_enc;
+  p.sat = (g.out_split != nullptr && g.out_enc != 0) ? saturation_counter() : nullptr;
+  if (g.gather != nullptr) {
+    // fused all-gather of the fp32 output rows (frame-sharded image encoder, SURVEY 8e option 1)
+    const AclipPeerGather& pg = *g.gather;
+    ACLIP_REQUIRE(g.out_f32 != nullptr && pg.world >= 1 && pg.world <= 8 && pg.rank >= 0 &&
+                      pg.rank < pg.world && pg.width == g.ldc && pg.epoch > 0 && pg.counter != nullptr &&
+                      g.gather_row0 >= 0 && g.gather_row0 + g.M <= pg.rows_per_rank,
+                  "gemm: bad peer-gather descriptor (needs an fp32 output of pitch == width, rows inside "
+                  "this rank's block)");
+    p.peer_world = pg.world; p.peer_rank = pg.rank; p.peer_signal = g.gather_signal;
+    p.peer_epoch = pg.epoch; p.peer_counter = pg.counter;
+    for (int r = 0; r < pg.world; ++r) {
+      ACLIP_REQUIRE(pg.rows[r] != nullptr && pg.flags[r] != nullptr, "gemm: null peer pointer %d", r);
+      p.peer_out[r] = pg.rows[r] + (pg.rank * pg.rows_per_rank + g.gather_row0) * pg.width;
+      p.peer_flags[r] = pg.flags[r];
+    }
+  }
   {
     // profiling experiments (results wrong by construction) only with the environment switch;
     // read once per process
@@ -301,14 +271,12 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
       ACLIP_REQUIRE(ps >= rows * ld, "gemm: plane stride smaller than the operand");
       cuuint64_t dims_h[3] = {(cuuint64_t)g.K, rows, 1};
       cuuint64_t str_h[2] = {ld * 2, ld * 2 * rows};
-      // the four-CTA kernel fetches W in quarters of 64 rows, one plane per TMA box
-      const bool quarter = quad && op == 1;
-      cuuint32_t box_h[3] = {64, quarter ? 64u : 128u, 1};
+      cuuint32_t box_h[3] = {64, 128u, 1};
       ACLIP_TRY(make_tmap(op == 0 ? &tmA : &tmB, base, 3, dims_h, str_h, box_h,
                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
       cuuint64_t dims_8[3] = {(cuuint64_t)g.K, rows, 2};
       cuuint64_t str_8[2] = {ld, ps};
-      cuuint32_t box_8[3] = {64, quarter ? 64u : 128u, quarter ? 1u : 2u};
+      cuuint32_t box_8[3] = {64, 128u, 2u};
       ACLIP_TRY(make_tmap(op == 0 ? &tmA8 : &tmB8, static_cast<const uint8_t*>(base) + 2 * ps, 3,
                           dims_8, str_8, box_8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
                           CU_TENSOR_MAP_SWIZZLE_64B));
@@ -338,8 +306,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
       ACLIP_TRY(make_tmap(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * ps, 5, dims_8, str_8, box_8,
                           CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_64B));
     }
-    return quad ? launch_quad<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
-                : launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
+    return launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
   }
   if (g.a_mode == 0) {
     ACLIP_REQUIRE(g.lda % 8 == 0 && g.lda >= g.K, "gemm: lda=%d invalid for K=%d", g.lda, g.K);
@@ -349,7 +316,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     cuuint32_t box[3] = {64, 128, (cuuint32_t)planes};
     ACLIP_REQUIRE(planes == 1 || (g.a_plane_stride % 8 == 0 && g.a_plane_stride > 0),
                   "gemm: a_plane_stride must be a positive multiple of 8");
-    ACLIP_TRY(make_tmap(&tmA, g.a, 3, dims, strides, box));
+    ACLIP_TRY(make_tmap(&tmA, g.a, 3, dims, strides, box, op_dtype));
   } else if (g.a_mode == 1) {
     ACLIP_REQUIRE(g.conv_c % 64 == 0, "conv3x3: C=%d must be a multiple of 64", g.conv_c);
     ACLIP_REQUIRE(g.conv_w > 0 && 128 % g.conv_w == 0 && (g.conv_h * g.conv_w) % 128 == 0,
@@ -366,7 +333,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                              planes == 1 ? S * H * W * C * 2 : (cuuint64_t)g.a_plane_stride * 2};
     cuuint32_t box[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(128 / g.conv_w), 1,
                          (cuuint32_t)planes};
-    ACLIP_TRY(make_tmap(&tmA, g.a, 5, dims, strides, box));
+    ACLIP_TRY(make_tmap(&tmA, g.a, 5, dims, strides, box, op_dtype));
   } else {
     return fail(ACLIP_ERR_INVALID, "gemm: unknown a_mode %d", g.a_mode);
   }
@@ -375,16 +342,15 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     cuuint64_t strides[2] = {(cuuint64_t)g.ldw * 2, planes == 1 ? (cuuint64_t)g.ldw * 2 * g.N
                                                                 : (cuuint64_t)g.w_plane_stride * 2};
     cuuint32_t box[3] = {64, (cuuint32_t)block_n, (cuuint32_t)planes};
-    if (quad) { box[1] = 64; box[2] = 1; }
     ACLIP_REQUIRE(planes == 1 || (g.w_plane_stride % 8 == 0 && g.w_plane_stride > 0),
                   "gemm: w_plane_stride must be a positive multiple of 8");
-    ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box));
+    ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box, op_dtype));
   }
 
-  if (quad) return launch_quad<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
   if (pair)
-    return g.passes == 3 ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
-                         : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+    return g.passes == 3   ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+           : g.passes == 4 ? launch_pair<4>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+                           : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
   if (block_n == 256) {
     return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
                          : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);

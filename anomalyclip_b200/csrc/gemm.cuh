@@ -11,11 +11,14 @@
 //                (K = 16) per K step plus two kind::f8f6f4 MMAs (K = 32, twice the rate) for the
 //                cross terms: two bf16-pass equivalents, ~2^-16 as well (CTA-pair kernels only)
 //   PASSES == 1  plain bf16 (hi plane only)
+//   PASSES == 4  "f16": the fp16 main plane only, one kind::f16 MMA per K step (CTA-pair kernel);
+//                ~2^-12 relative per product, selected by the host after calibration (split.cuh)
 //
-// Three kernels share the producer / issuer / epilogue code:
+// Two kernels share the producer / issuer / epilogue code:
 //   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile                    (192 threads)
 //   gemm2_tcgen05_kernel  a CTA pair (cta_group::2) per 256 x 256 tile           (320 threads per CTA)
-//   gemm4_tcgen05_kernel  two CTA pairs on M-adjacent tiles sharing the W tile by TMA multicast
+// (A four-CTA variant sharing the W tile by TMA multicast was measured in round 1: ~8 % faster per
+// SM but only 33 clusters of four are co-resident on 148 SMs, a net loss; removed.)
 // Roles:
 //   warp 0  lane 0 : TMA producer   (A and W tiles, swizzled boxes, mbarrier complete_tx)
 //   warp 1  lane 0 : MMA issuer     (tcgen05.mma)
@@ -61,7 +64,19 @@ struct GemmParams {
   // output row remap: out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset
   int row_group, row_group_stride, row_offset;
   float out_scale;  // multiplies the accumulator before bias (f16f8 operands: 2^-(ex + ew)), else 1
-  int out_enc;      // encoding of out_split: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes
+  int out_enc;      // encoding of out_split: 0 = bf16 hi/lo planes, 1 = f16f8 activation planes,
+                    // 2 = fp16 plane only
+  unsigned int* sat;  // fp16 saturation counter of this device (split.cuh) or nullptr
+  // Fused all-gather of the fp32 output over NVLink peer memory (peer_world > 0): every row this
+  // GEMM stores to out_f32 is also stored to peer_out[r] (same pitch, same row remap) for every
+  // rank r of the group -- peer-mapped buffers, the local rank's own is one of them -- and, when
+  // peer_signal is set, the last CTA publishes peer_flags[r][peer_rank] = peer_epoch on every rank
+  // (system-scope release) once all CTAs have fenced their stores.  aclip_peer_wait is the consumer.
+  int peer_world, peer_rank, peer_signal;
+  unsigned int peer_epoch;
+  unsigned int* peer_counter;
+  float* peer_out[8];
+  unsigned int* peer_flags[8];
   int debug;        // profiling experiments only (ACLIP_PROFILING_EXPERIMENTS=1): 1 = issue no MMAs
                     // (operand feed + epilogue only; results are wrong by construction)
 };
@@ -109,19 +124,27 @@ __device__ __forceinline__ float quick_gelu(float x) {
 // once per row.
 constexpr int EPI_STAGE_BYTES = 32 * 128;
 
-// SPLIT: 0 = no split output, 1 = bf16 hi/lo planes, 2 = f16f8 activation planes
+// SPLIT: 0 = no split output, 1 = bf16 hi/lo planes, 2 = f16f8 activation planes, 3 = fp16 plane
 template <bool F32, int SPLIT>
 __device__ __forceinline__ void epilogue_store(const GemmParams& p, const int (&orow)[8],
                                                const float4 (&val)[8], int col, int lane,
                                                const uint8_t* stage) {
   const int piece = lane & 7;
+  float amax = 0.f;  // max |value| stored in an fp16-based encoding (saturation guard)
 #pragma unroll
   for (int i = 0; i < 8; ++i) {
     const int row = i * 4 + (lane >> 3);
     if (orow[i] >= 0) {
       const float4 a = *reinterpret_cast<const float4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
       const float4 v4 = make_float4(a.x + val[i].x, a.y + val[i].y, a.z + val[i].z, a.w + val[i].w);
-      if (F32) *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(orow[i]) * p.ldc + col) = v4;
+      if (F32) {
+        *reinterpret_cast<float4*>(p.out_f32 + static_cast<long long>(orow[i]) * p.ldc + col) = v4;
+        if (p.peer_world > 0) {
+#pragma unroll 1
+          for (int r = 0; r < p.peer_world; ++r)
+            *reinterpret_cast<float4*>(p.peer_out[r] + static_cast<long long>(orow[i]) * p.ldc + col) = v4;
+        }
+      }
       if (SPLIT == 1) {
         uint32_t h0, l0, h1, l1;
         split_pack2(v4.x, v4.y, h0, l0);
@@ -132,9 +155,15 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, const int (&
       } else if (SPLIT == 2) {
         f16f8_store4_act(p.out_split, p.split_plane_stride,
                          static_cast<long long>(orow[i]) * p.ld_split + col, v4.x, v4.y, v4.z, v4.w);
+        amax = sat_track(amax, v4.x, v4.y, v4.z, v4.w);
+      } else if (SPLIT == 3) {
+        f16_store4_act(p.out_split, static_cast<long long>(orow[i]) * p.ld_split + col, v4.x, v4.y,
+                       v4.z, v4.w);
+        amax = sat_track(amax, v4.x, v4.y, v4.z, v4.w);
       }
     }
   }
+  if (SPLIT >= 2) sat_report(p.sat, amax);
 }
 
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
@@ -214,10 +243,32 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
   if (p.out_f32 != nullptr) {
     if (kind == 0) epilogue_store<true, 0>(p, orow, val, col, lane, stage);
     else if (kind == 1) epilogue_store<true, 1>(p, orow, val, col, lane, stage);
-    else epilogue_store<true, 2>(p, orow, val, col, lane, stage);
+    else if (kind == 2) epilogue_store<true, 2>(p, orow, val, col, lane, stage);
+    else epilogue_store<true, 3>(p, orow, val, col, lane, stage);
   } else {
     if (kind == 1) epilogue_store<false, 1>(p, orow, val, col, lane, stage);
     else if (kind == 2) epilogue_store<false, 2>(p, orow, val, col, lane, stage);
+    else if (kind == 3) epilogue_store<false, 3>(p, orow, val, col, lane, stage);
+  }
+}
+
+// End of a GEMM whose epilogue stored into peer memory: called by every thread after its last
+// store; the block-level barrier that follows in the kernels orders the fences before the count.
+__device__ __forceinline__ void peer_fence(const GemmParams& p) {
+  if (p.peer_world > 0) __threadfence_system();
+}
+// One thread per CTA, after the barrier: the last CTA to arrive raises this rank's flag everywhere.
+__device__ __forceinline__ void peer_publish(const GemmParams& p) {
+  if (p.peer_world > 0 && p.peer_signal) {
+    const unsigned int done = atomicAdd(p.peer_counter, 1u);
+    if (done == gridDim.x - 1) {
+      *p.peer_counter = 0u;  // ready for the next launch
+      __threadfence_system();
+      for (int r = 0; r < p.peer_world; ++r)
+        asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(p.peer_flags[r] + p.peer_rank),
+                     "r"(p.peer_epoch)
+                     : "memory");
+    }
   }
 }
 
@@ -361,8 +412,10 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   }
 
+  peer_fence(p);
   ptx::tc_fence_before();
   __syncthreads();
+  if (threadIdx.x == 0) peer_publish(p);
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc(tmem_base, Cfg::TMEM_COLS);
@@ -386,7 +439,7 @@ struct Gemm2Cfg {
   static constexpr int BLOCK_K = 64;
   static constexpr int UMMA_K = 16;
   static constexpr int PASSES = PASSES_;
-  static constexpr int PLANES = PASSES_ == 1 ? 1 : 2;
+  static constexpr int PLANES = (PASSES_ == 1 || PASSES_ == 4) ? 1 : 2;
   static constexpr int A_PLANE_BYTES = CTA_M * 128;
   static constexpr int B_PLANE_BYTES = CTA_N * 128;
   static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
@@ -509,8 +562,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (rank == 0) {
       const bool leader = ptx::elect_one();
       // kind::f16 with fp16 operands and kind::f8f6f4 with e4m3 operands both encode format 0
-      constexpr uint32_t idesc = PASSES == 2 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
-                                             : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
+      constexpr uint32_t idesc = (PASSES == 2 || PASSES == 4)
+                                     ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
+                                     : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
       const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
       const uint64_t desc8 = ptx::make_kmajor_sw64_desc(ptx::smem_u32(smem));
       uint32_t stage = 0, phase = 0;
@@ -591,194 +645,10 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   }
 
+  peer_fence(p);
   ptx::tc_fence_before();
   ptx::cluster_sync();  // nobody leaves while the pair may still touch its smem / TMEM / barriers
-  if (warp == 1) {
-    ptx::tc_fence_after();
-    ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);
-  }
-}
-
-// ------------------------------------------------------------------------------------------
-// Four-CTA variant: a cluster of two CTA pairs computes two M-adjacent 256 x 256 tiles against the
-// SAME W tile.  Each of the four CTAs fetches a quarter (64 rows) of the W tile per K block and
-// multicasts it to the CTA at its position in the other pair, so the W operand crosses the
-// L2 -> SM fabric once per cluster instead of once per pair: 96 KB instead of 128 KB of L2 reads per
-// pair and K block.  (The pair kernel at three stages is bound by the L2 -> SM throughput of
-// ~6300 B/clk as much as by the tensor pipe.)  Everything else -- roles, TMEM double buffering,
-// epilogue -- is the pair kernel's; the shared-memory slot of a stage is released only when BOTH
-// pairs' MMAs have consumed it (empty barriers count two multicast commits).
-template <int PASSES>
-__global__ void __cluster_dims__(4, 1, 1) __launch_bounds__(320, 1)
-gemm4_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
-                     const __grid_constant__ CUtensorMap tmB,
-                     const __grid_constant__ CUtensorMap tmA8,
-                     const __grid_constant__ CUtensorMap tmB8, const GemmParams p) {
-  using Cfg = Gemm2Cfg<PASSES>;
-  constexpr int STAGES = Cfg::STAGES;
-  static_assert(PASSES == 2 || PASSES == 3, "the four-CTA kernel carries two operand planes");
-
-  extern __shared__ uint8_t smem_raw[];
-  // 1024-byte alignment as an OFFSET into the __shared__ array: the pointer keeps its address
-  // space, so plain C++ accesses compile to LDS/STS instead of generic LD/ST
-  uint8_t* smem = smem_raw + ((1024u - (ptx::smem_u32(smem_raw) & 1023u)) & 1023u);
-  uint64_t* full_bar = reinterpret_cast<uint64_t*>(smem + STAGES * Cfg::STAGE_BYTES);
-  uint64_t* empty_bar = full_bar + STAGES;
-  uint64_t* tfull_bar = empty_bar + STAGES;
-  uint64_t* tempty_bar = tfull_bar + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(tempty_bar + 2);
-
-  const int warp = threadIdx.x >> 5;
-  const int lane = threadIdx.x & 31;
-  const uint32_t crank = ptx::cluster_ctarank();   // 0..3
-  const int pair = static_cast<int>(crank >> 1);    // which of the two M tiles
-  const int rank = static_cast<int>(crank & 1);     // position inside the pair, 0 = pair leader
-  const int cluster_id = blockIdx.x >> 2;
-  const int num_clusters = gridDim.x >> 2;
-  const uint16_t pair_mask = static_cast<uint16_t>(0x3u << (2 * pair));
-  const uint16_t w_mask = static_cast<uint16_t>(0x5u << rank);  // this position in both pairs
-
-  if (warp == 0 && lane == 0) {
-    ptx::prefetch_tmap(&tmA);
-    ptx::prefetch_tmap(&tmB);
-    if (PASSES == 2) {
-      ptx::prefetch_tmap(&tmA8);
-      ptx::prefetch_tmap(&tmB8);
-    }
-    for (int s = 0; s < STAGES; ++s) {
-      ptx::mbar_init(&full_bar[s], 1);   // pair leader's producer (arrive.expect_tx)
-      ptx::mbar_init(&empty_bar[s], 2);  // one multicast tcgen05.commit from each pair
-    }
-    for (int a = 0; a < 2; ++a) {
-      ptx::mbar_init(&tfull_bar[a], 1);
-      ptx::mbar_init(&tempty_bar[a], 2 * Cfg::EPI_WARPS);
-    }
-    ptx::fence_mbar_init();
-  }
-  if (warp == 1) {
-    ptx::tmem_alloc_pair(tmem_slot, Cfg::TMEM_COLS);
-    ptx::tmem_relinquish_pair();
-  }
-  ptx::tc_fence_before();
-  ptx::cluster_sync();
-  ptx::tc_fence_after();
-  const uint32_t tmem_base = *tmem_slot;
-
-  const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
-  const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
-  const int total_tiles = ((m_tiles + 1) >> 1) * n_tiles;   // super-tiles of two M tiles
-
-  if (warp == 0) {
-    // ------------------------------------------------------------ TMA producer (all four CTAs)
-    if (lane == 0) {
-      uint32_t stage = 0, phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        // W rows of this CTA's position in the pair; this CTA fetches quarter `pair` of them
-        const int n0 = (t % n_tiles) * Cfg::BLOCK_N + rank * Cfg::CTA_N;
-        const int nq = n0 + pair * (Cfg::CTA_N / 2);
-        const int m0 = (((t / n_tiles) * 2 + pair) * 2 + rank) * Cfg::CTA_M;  // may lie beyond M: zero fill
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          const int k0 = kb * Cfg::BLOCK_K;
-          if (PASSES == 2) {
-            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
-            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], k0, m0, 0);
-            ptx::tma_load_3d_pair_mc(sb + pair * (Cfg::B_PLANE_BYTES / 2), &tmB, &full_bar[stage], k0, nq, 0, w_mask);
-            uint8_t* s8 = sb + Cfg::B_PLANE_BYTES + pair * (Cfg::B_PLANE_BYTES / 4);
-            ptx::tma_load_3d_pair_mc(s8, &tmB8, &full_bar[stage], k0, nq, 0, w_mask);
-            ptx::tma_load_3d_pair_mc(s8 + Cfg::B_PLANE_BYTES / 2, &tmB8, &full_bar[stage], k0, nq, 1, w_mask);
-          } else {
-            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
-            uint8_t* sq = sb + pair * (Cfg::B_PLANE_BYTES / 2);
-            ptx::tma_load_3d_pair_mc(sq, &tmB, &full_bar[stage], k0, nq, 0, w_mask);
-            ptx::tma_load_3d_pair_mc(sq + Cfg::B_PLANE_BYTES, &tmB, &full_bar[stage], k0, nq, 1, w_mask);
-          }
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-      }
-    }
-  } else if (warp == 1) {
-    // ------------------------------------------------------------ MMA issuer (pair leaders)
-    if (rank == 0) {
-      const bool leader = ptx::elect_one();
-      constexpr uint32_t idesc = PASSES == 2 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
-                                             : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
-      const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
-      const uint64_t desc8 = ptx::make_kmajor_sw64_desc(ptx::smem_u32(smem));
-      uint32_t stage = 0, phase = 0;
-      uint32_t acc = 0, acc_phase = 0;
-      for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-        ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
-        ptx::tc_fence_after();
-        const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
-          ptx::mbar_wait(&full_bar[stage], phase);
-          ptx::tc_fence_after();
-          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
-          if (p.debug & 1) {
-          } else if (PASSES == 2) {
-#pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
-            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
-            const uint64_t b_l0 = a_l0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
-            constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
-#pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
-              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
-              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + kCoarse + 2 * k, b_l0 + 2 * k, idesc, 1u);
-            }
-          } else {
-#pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-              const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
-            }
-          }
-          ptx::mma_commit_pair_if(leader, &empty_bar[stage], 0xF);  // one of two arrivals, all four CTAs
-          if (++stage == STAGES) { stage = 0; phase ^= 1; }
-        }
-        ptx::mma_commit_pair_if(leader, &tfull_bar[acc], pair_mask);
-        acc ^= 1;
-        if (acc == 0) acc_phase ^= 1;
-      }
-    }
-  } else {
-    // ------------------------------------------------------------ epilogue (warps 2..9)
-    const int quarter = warp & 3;
-    const int col_half = (warp - 2) >> 2;
-    uint8_t* stage = smem + STAGES * Cfg::STAGE_BYTES + 256 + (warp - 2) * EPI_STAGE_BYTES;
-    uint32_t acc = 0, acc_phase = 0;
-    for (int t = cluster_id; t < total_tiles; t += num_clusters) {
-      const int n0 = (t % n_tiles) * Cfg::BLOCK_N + col_half * 128;
-      const int m_base = (((t / n_tiles) * 2 + pair) * 2 + rank) * Cfg::CTA_M + quarter * 32;
-      ptx::mbar_wait(&tfull_bar[acc], acc_phase);
-      ptx::tc_fence_after();
-      const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
-                             (static_cast<uint32_t>(quarter * 32) << 16);
-#pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;
-        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
-      }
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive_remote(&tempty_bar[acc], static_cast<uint32_t>(2 * pair));
-      acc ^= 1;
-      if (acc == 0) acc_phase ^= 1;
-    }
-  }
-
-  ptx::tc_fence_before();
-  ptx::cluster_sync();
+  if (threadIdx.x == 0) peer_publish(p);
   if (warp == 1) {
     ptx::tc_fence_after();
     ptx::tmem_dealloc_pair(tmem_base, Cfg::TMEM_COLS);

@@ -33,14 +33,15 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 
 // mode 0: (x - mean) / sqrt(var + eps) * g + b      nn.LayerNorm (clip/model.py:174-180)
 // mode 1: (x - mean) / (sqrt(var) + eps) * g + b    ChanLayerNorm of axial_attention (eps on std)
-// ENC: encoding of out_split, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes (split.cuh)
+// ENC: encoding of out_split, 0 = bf16 hi/lo planes, 1 = f16f8 activation planes, 2 = fp16 plane
+// (split.cuh)
 template <int MODE, int ENC>
 __global__ void __launch_bounds__(kWarpsPerCta * 32)
 layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long ldx,
                  const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
                  float* __restrict__ out_f32, long long ld_f32,
                  __nv_bfloat16* __restrict__ out_split, long long ld_split,
-                 long long plane_stride) {
+                 long long plane_stride, unsigned int* __restrict__ sat) {
   const int lane = threadIdx.x & 31;
   // Rows are walked from the LAST to the first: the GEMM that produced x wrote its highest rows
   // last, so they are the ones still resident in L2 (x is larger than L2 at the bench's micro-batch),
@@ -71,6 +72,7 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
   }
   const float var = warp_sum(q) / static_cast<float>(D);
   const float rstd = MODE == 0 ? rsqrtf(var + eps) : 1.0f / (sqrtf(var) + eps);
+  float amax = 0.f;
 #pragma unroll
   for (int i = 0; i < kMaxVec; ++i) {
     const int c = lane + i * 32;
@@ -91,12 +93,17 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
           __nv_bfloat16* dst = out_split + row * ld_split + 4 * c;
           *reinterpret_cast<uint2*>(dst) = make_uint2(h01, h23);
           *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(l01, l23);
-        } else {
+        } else if (ENC == 1) {
           f16f8_store4_act(out_split, plane_stride, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
+          amax = sat_track(amax, y.x, y.y, y.z, y.w);
+        } else {
+          f16_store4_act(out_split, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
+          amax = sat_track(amax, y.x, y.y, y.z, y.w);
         }
       }
     }
   }
+  if (ENC != 0) sat_report(sat, amax);
 }
 
 struct PeerDev {            // device-side copy of AclipPeerGather for one head launch
@@ -216,6 +223,15 @@ __global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, un
   }
 }
 
+__global__ void peer_signal_kernel(PeerDev pg) {
+  if (threadIdx.x == 0) {
+    __threadfence_system();
+    for (int r = 0; r < pg.world; ++r)
+      asm volatile("st.release.sys.global.u32 [%0], %1;" ::"l"(pg.flags[r] + pg.rank), "r"(pg.epoch)
+                   : "memory");
+  }
+}
+
 }  // namespace
 
 int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
@@ -223,7 +239,8 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
               void* out_split, long long ld_split, long long plane_stride, int out_enc,
               cudaStream_t stream) {
   ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
-  ACLIP_REQUIRE(out_enc == 0 || (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0),
+  ACLIP_REQUIRE(out_enc == 0 || out_enc == 2 ||
+                    (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0),
                 "layernorm: out_enc=%d unsupported (f16f8 needs 16-element pitches)", out_enc);
   ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
   ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
@@ -235,20 +252,22 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   auto* os = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_LAYERNORM, stream);
-  if (mode == 0 && out_enc == 1)
-    layernorm_kernel<0, 1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
-  else if (mode == 0)
-    layernorm_kernel<0, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
-  else if (out_enc == 1)
-    layernorm_kernel<1, 1><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
-  else
-    layernorm_kernel<1, 0><<<grid, kWarpsPerCta * 32, 0, stream>>>(
-        x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride);
+  unsigned int* sat = (out_split != nullptr && out_enc != 0) ? saturation_counter() : nullptr;
+#define ACLIP_LN(MODE, ENC)                                                      \
+  layernorm_kernel<MODE, ENC><<<grid, kWarpsPerCta * 32, 0, stream>>>(           \
+      x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat)
+  if (mode == 0) {
+    if (out_enc == 2) ACLIP_LN(0, 2);
+    else if (out_enc == 1) ACLIP_LN(0, 1);
+    else ACLIP_LN(0, 0);
+  } else {
+    if (out_enc == 2) ACLIP_LN(1, 2);
+    else if (out_enc == 1) ACLIP_LN(1, 1);
+    else ACLIP_LN(1, 0);
+  }
+#undef ACLIP_LN
   timing_end(KIND_LAYERNORM, stream, 8.0 * rows * D,
-             (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? 4.0 : 0.0)));
+             (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? (out_enc == 2 ? 2.0 : 4.0) : 0.0)));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;
@@ -310,4 +329,21 @@ extern "C" int aclip_layernorm(const float* x, long long rows, int D, long long 
 extern "C" int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch,
                                void* stream) {
   return aclip::peer_wait(local_flags, world, epoch, aclip::as_stream(stream));
+}
+
+extern "C" int aclip_peer_signal(const AclipPeerGather* gather, void* stream) {
+  using namespace aclip;
+  ACLIP_REQUIRE(gather != nullptr && gather->world >= 1 && gather->world <= 8 && gather->rank >= 0 &&
+                    gather->rank < gather->world && gather->epoch > 0,
+                "peer_signal: bad descriptor");
+  PeerDev pg{};
+  pg.world = gather->world; pg.rank = gather->rank; pg.epoch = gather->epoch;
+  for (int r = 0; r < gather->world; ++r) {
+    ACLIP_REQUIRE(gather->flags[r] != nullptr, "peer_signal: null flag pointer %d", r);
+    pg.flags[r] = gather->flags[r];
+  }
+  peer_signal_kernel<<<1, 32, 0, as_stream(stream)>>>(pg);
+  ACLIP_CHECK_LAUNCH();
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  return ACLIP_OK;
 }

@@ -74,4 +74,34 @@ __device__ __forceinline__ void f16f8_store4_act(void* base, long long plane_str
   *reinterpret_cast<uint32_t*>(b + 3 * plane_stride + off) = c;
 }
 
+// ---------------------------------------------------------------------------------------------
+// "f16" operand encoding (GEMM passes == 4): only the H plane of the encoding above,
+// H = fp16(v * 2^4), and ONE kind::f16 MMA pass per product.  Rounding both operands to 11
+// significant bits costs ~2.5e-4 relative on the ViT-B/16 features (scripts/numerics_passes.py):
+// inside the 1e-3 bar, but with far less margin than f16f8, so the host side selects it only after
+// a calibration run against the f16f8 mode on the same checkpoint (engine.VitEncoder "auto").
+// A tensor is a plain fp16 matrix [rows][ld]; weights reuse the H plane of their f16f8 pack.
+__device__ __forceinline__ void f16_pack4(float v0, float v1, float v2, float v3, uint2& h) {
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.x) : "f"(v1 * kActScaleMain), "f"(v0 * kActScaleMain));
+  asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h.y) : "f"(v3 * kActScaleMain), "f"(v2 * kActScaleMain));
+}
+__device__ __forceinline__ void f16_store4_act(void* base, long long off, float v0, float v1,
+                                               float v2, float v3) {
+  uint2 h;
+  f16_pack4(v0, v1, v2, v3, h);
+  *reinterpret_cast<uint2*>(static_cast<uint8_t*>(base) + 2 * off) = h;
+}
+
+// Saturation guard of the fp16-based activation encodings: the conversions above clamp
+// (cvt.satfinite), so a value with |v| * 2^4 > 65504 would be stored wrong without a trace.  Every
+// encoder keeps the running max |v| of what it stores (sat_track) and bumps a per-device counter
+// once per thread when it reached the fp16 range (sat_report); aclip_saturation_count() reads it.
+constexpr float kActF16Limit = 65504.0f / kActScaleMain;
+__device__ __forceinline__ float sat_track(float m, float v0, float v1, float v2, float v3) {
+  return fmaxf(fmaxf(m, fmaxf(fabsf(v0), fabsf(v1))), fmaxf(fabsf(v2), fabsf(v3)));
+}
+__device__ __forceinline__ void sat_report(unsigned int* counter, float m) {
+  if (counter != nullptr && !(m <= kActF16Limit)) atomicAdd(counter, 1u);   // also counts NaN
+}
+
 }  // namespace aclip

@@ -7,7 +7,9 @@
 //          LN2 -> GEMM(c_fc)+b+QuickGELU -> GEMM(c_proj)+b+residual ]
 //   ln_post on the CLS rows -> GEMM(proj)
 //
-// The residual stream X stays fp32; GEMM operands are split-bf16 (see gemm.cuh).  No allocation,
+// The residual stream X stays fp32; GEMM operands travel in the encoding of the requested mode
+// (gemm.cuh / split.cuh): passes = 3 split-bf16, 2 f16f8 (out_proj and the attention stay
+// split-bf16), 4 fp16 planes end to end (every GEMM and the attention in one pass).  No allocation,
 // no synchronisation: everything is enqueued on the caller's stream into the caller's workspace.
 #include "common.h"
 
@@ -47,7 +49,7 @@ VitPlan plan_vit(const AclipVitWeights& w, int mb) {
 AclipGemmArgs linear(const void* a, long long a_plane, int M, int K, int lda, const void* w, int N,
                      int passes, float w_scale = 0.0f) {
   AclipGemmArgs g{};
-  g.out_scale = passes == 2 ? w_scale : 0.0f;
+  g.out_scale = (passes == 2 || passes == 4) ? w_scale : 0.0f;
   g.a = a; g.w = w;
   g.M = M; g.N = N; g.K = K;
   g.lda = lda; g.ldw = K;
@@ -84,17 +86,32 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
                                  long long num_frames, int micro_batch, const float* mean3_host,
                                  const float* std3_host, float* features_out, void* workspace,
                                  size_t workspace_bytes, int passes, void* stream_) {
+  return aclip_vit_forward_ex(wp, frames, frames_are_u8, num_frames, micro_batch, mean3_host,
+                              std3_host, features_out, workspace, workspace_bytes, passes, nullptr,
+                              stream_);
+}
+
+extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frames, int frames_are_u8,
+                                    long long num_frames, int micro_batch, const float* mean3_host,
+                                    const float* std3_host, float* features_out, void* workspace,
+                                    size_t workspace_bytes, int passes,
+                                    const AclipPeerGather* gather, void* stream_) {
   using namespace aclip;
   ACLIP_REQUIRE(wp != nullptr, "vit_forward: weights are NULL");
   const AclipVitWeights& w = *wp;
   ACLIP_TRY(check_weights(w));
   ACLIP_REQUIRE(frames != nullptr && features_out != nullptr, "vit_forward: null frames/output");
   ACLIP_REQUIRE(num_frames >= 0 && micro_batch > 0, "vit_forward: bad frame count / micro-batch");
-  ACLIP_REQUIRE(passes >= 1 && passes <= 3, "vit_forward: passes must be 1, 2 or 3");
-  ACLIP_REQUIRE(passes != 2 || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
-                                (3 * w.patch * w.patch) % 16 == 0),
-                "vit_forward: passes=2 (f16f8 operands) needs width and output_dim multiples of 256");
-  const int enc = passes == 2 ? 1 : 0;  // encoding of every GEMM A operand on this path
+  ACLIP_REQUIRE(passes >= 1 && passes <= 4, "vit_forward: passes must be 1, 2, 3 or 4");
+  ACLIP_REQUIRE((passes != 2 && passes != 4) || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
+                                                 (3 * w.patch * w.patch) % 16 == 0),
+                "vit_forward: passes=%d (fp16-based operands) needs width and output_dim multiples of 256",
+                passes);
+  const bool f16 = passes == 4;
+  const int enc = f16 ? 2 : passes == 2 ? 1 : 0;  // encoding of every GEMM A operand on this path
+  ACLIP_REQUIRE(gather == nullptr || (gather->width == w.output_dim && num_frames == gather->rows_per_rank),
+                "vit_forward: the feature gather must be built for %lld rows of %d values", num_frames,
+                w.output_dim);
   if (num_frames == 0) return ACLIP_OK;
   if (micro_batch > num_frames) micro_batch = static_cast<int>(num_frames);
   const VitPlan pl = plan_vit(w, micro_batch);
@@ -135,7 +152,8 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
 
     for (int l = 0; l < w.layers; ++l) {  // :214-217
       const AclipVitBlock& b = w.blocks[l];
-      ACLIP_REQUIRE(b.ln1_g && b.ln1_b && b.ln2_g && b.ln2_b && b.qkv_w && b.qkv_b && b.out_w &&
+      ACLIP_REQUIRE(b.ln1_g && b.ln1_b && b.ln2_g && b.ln2_b && b.qkv_w && b.qkv_b &&
+                        (f16 ? b.out_w16 != nullptr : b.out_w != nullptr) &&
                         b.out_b && b.fc_w && b.fc_b && b.proj_w && b.proj_b,
                     "vit_forward: block %d has a null weight", l);
       ACLIP_TRY(layernorm(X, M, W, W, b.ln1_g, b.ln1_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc, stream));
@@ -143,14 +161,17 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
         AclipGemmArgs g = linear(H, hp, M, W, W, b.qkv_w, 3 * W, passes, b.qkv_s);
         g.bias = b.qkv_b;
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 3 * W;
+        g.out_enc = f16 ? 2 : 0;
         ACLIP_TRY(gemm(g, stream));
       }
       // q | k | v and the attention output stay bf16 hi/lo planes in every mode: out_proj is the
       // smallest GEMM of the block and runs the three-pass kernel also when passes = 2 (the f16f8
       // encode in the attention epilogue costs more than the two-pass out_proj saves)
-      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, 0, stream));
+      // (passes = 4: fp16 q | k | v in, fp16 out, one MMA pass, and out_proj on its fp16 weight)
+      ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, f16 ? 2 : 0, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.out_w, W, passes == 2 ? 3 : passes);
+        AclipGemmArgs g = f16 ? linear(H, hp, M, W, W, b.out_w16, W, 4, b.out_s)
+                              : linear(H, hp, M, W, W, b.out_w, W, passes == 2 ? 3 : passes);
         g.bias = b.out_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;
@@ -180,6 +201,11 @@ extern "C" int aclip_vit_forward(const AclipVitWeights* wp, const void* frames, 
       AclipGemmArgs g = linear(H, hp, Bm, W, W, w.proj_w, w.output_dim, passes, w.proj_s);
       g.out_f32 = features_out + f0 * w.output_dim;
       g.ldc = w.output_dim;
+      // frame-sharded encoder: the projection's epilogue stores the feature rows straight into
+      // every rank's gathered buffer; the launch of the last micro-batch raises this rank's flag
+      g.gather = gather;
+      g.gather_row0 = f0;
+      g.gather_signal = f0 + Bm >= num_frames ? 1 : 0;
       ACLIP_TRY(gemm(g, stream));
     }
   }

@@ -109,7 +109,10 @@ class PeerRowGather:
     its next-but-one call needs this rank's flag of the call in between."""
 
     def __init__(self, rows_per_rank: int, width: int, device: torch.device,
-                 group: Optional[dist.ProcessGroup] = None) -> None:
+                 group: Optional[dist.ProcessGroup] = None, extra_floats: int = 0) -> None:
+        """extra_floats: additional symmetric floats behind the flag words (`extra()`), for callers
+        that exchange a second payload through the same mapping (the feature rows of a
+        frame-sharded encoder, `PeerFeatureGather`)."""
         import torch.distributed._symmetric_memory as symm_mem
 
         from . import _lib
@@ -120,16 +123,21 @@ class PeerRowGather:
             raise ValueError("PeerRowGather supports up to 8 ranks (one NVSwitch domain)")
         self.rows_per_rank, self.width, self.device = rows_per_rank, width, device
         self.block = self.world * rows_per_rank * width             # floats per parity copy
-        self.buf = symm_mem.empty(2 * self.block + 64, dtype=torch.float32, device=device)
+        self.buf = symm_mem.empty(2 * self.block + 64 + extra_floats, dtype=torch.float32, device=device)
         self.buf.zero_()
+        self._marks_host = torch.zeros(self.world, dtype=torch.int32).pin_memory()
+        self._marks_event: Optional[torch.cuda.Event] = None
         self.handle = symm_mem.rendezvous(self.buf, group.group_name)
         self.counter = torch.zeros(1, dtype=torch.int32, device=device)
         self.epoch = 0
         torch.cuda.synchronize(device)
         dist.barrier(group)                                          # all buffers zeroed and mapped
 
-    def descriptor(self, n_rows: int, width: int):
-        if n_rows != self.rows_per_rank or width != self.width:
+    def descriptor(self, n_rows: int, width: int, partial: bool = False):
+        """Descriptor of the next call (advances the epoch).  partial: this rank may contribute
+        fewer than rows_per_rank rows (uneven unit counts); the tail of its block is then stale."""
+        if width != self.width or n_rows > self.rows_per_rank or \
+                (n_rows != self.rows_per_rank and not partial):
             raise ValueError("PeerRowGather: shape differs from the one it was built for")
         self.epoch += 1
         g = self._lib.PeerGather()
@@ -143,17 +151,151 @@ class PeerRowGather:
         g.counter = self.counter.data_ptr()
         return g
 
+    def _marks(self) -> torch.Tensor:
+        return self.buf[2 * self.block + self.world: 2 * self.block + 2 * self.world].view(torch.int32)
+
+    def _raise_if_marked(self, marks: List[int]) -> None:
+        late = [r for r, v in enumerate(marks) if v != 0]
+        if late:
+            self._marks().zero_()          # a later epoch starts clean
+            raise self._lib.AclipError(
+                f"PeerRowGather: the rows of rank(s) {late} did not arrive within the wait kernel's "
+                "bound (~5 s); the gathered buffer of that call was stale.  A peer stalled or died; "
+                "fall back to distributed.gather_rows (one NCCL all-gather)")
+
     def wait(self) -> torch.Tensor:
         """Gathered rows [world * rows_per_rank, width] of the latest call (a view of the local
-        symmetric buffer, valid until the call after next)."""
+        symmetric buffer, valid until the call after next).
+
+        The wait kernel gives up after a bounded time instead of hanging the device and marks the
+        late ranks; those marks are copied to pinned host memory behind it, and the NEXT wait()
+        (or check()) raises `AclipError` if any was set -- a timeout is never silent, and the
+        steady state costs no host synchronisation."""
+        if self._marks_event is not None and self._marks_event.query():
+            self._marks_event = None
+            self._raise_if_marked(self._marks_host.tolist())
         lib = self._lib.load()
-        self._lib.check(lib.aclip_peer_wait(self.buf.data_ptr() + 4 * 2 * self.block, self.world,
-                                            self.epoch, torch.cuda.current_stream(self.device).cuda_stream))
+        stream = torch.cuda.current_stream(self.device)
+        with torch.cuda.device(self.device):
+            self._lib.check(lib.aclip_peer_wait(self.buf.data_ptr() + 4 * 2 * self.block, self.world,
+                                                self.epoch, stream.cuda_stream))
+            if self._marks_event is None:      # previous copy consumed: take the next snapshot
+                self._marks_host.copy_(self._marks(), non_blocking=True)
+                self._marks_event = torch.cuda.Event()
+                self._marks_event.record(stream)
         parity = self.epoch & 1
         return self.buf[parity * self.block:(parity + 1) * self.block].view(
             self.world * self.rows_per_rank, self.width)
 
+    def signal(self) -> None:
+        """Take part in the next exchange without contributing rows (a rank with no unit in this
+        call): raises this rank's flag of the new epoch on every peer."""
+        g = self.descriptor(0, self.width, partial=True)
+        import ctypes as C
+        with torch.cuda.device(self.device):
+            self._lib.check(self._lib.load().aclip_peer_signal(
+                C.addressof(g), torch.cuda.current_stream(self.device).cuda_stream))
+
     def timed_out(self) -> List[int]:
         """Ranks whose rows did not arrive within the wait kernel's bound (synchronises)."""
-        marks = self.buf[2 * self.block + self.world: 2 * self.block + 2 * self.world]
-        return [r for r, v in enumerate(marks.view(torch.int32).tolist()) if v != 0]
+        return [r for r, v in enumerate(self._marks().tolist()) if v != 0]
+
+    def check(self) -> None:
+        """Synchronise and raise if any wait so far timed out (call before trusting results that
+        were consumed on the device only)."""
+        self._marks_event = None
+        self._raise_if_marked(self._marks().tolist())
+
+    def extra(self) -> torch.Tensor:
+        """The caller-defined symmetric floats behind the flag words (see `extra_floats`)."""
+        return self.buf[2 * self.block + 64:]
+
+    def extra_ptr(self, rank: int) -> int:
+        """Peer-mapped address of rank `rank`'s `extra()` region."""
+        return int(self.handle.buffer_ptrs[rank]) + 4 * (2 * self.block + 64)
+
+
+class FrameShardedScorer:
+    """One video (or batch of 512-frame units) scored by ALL ranks of one NVSwitch domain with the
+    frames sharded over the ranks -- BASELINE configs[3] / SURVEY 8e option (1): 2 048 frames over
+    8 GPUs are 256 frames per GPU, half a temporal unit, so the image encoder is sharded by FRAME
+    (frames are independent, anomaly_clip.py:119-123) and the temporal stage by 512-frame unit
+    (temporal_model.py:46-53).
+
+    Per call: every rank encodes its contiguous block of `frames_per_rank` frames; the epilogue of
+    the encoder's output projection stores the feature rows into every rank's gathered buffer over
+    NVLink peer memory (aclip_vit_forward_ex); after a stream-side flag wait each rank runs
+    selector + temporal + head on ITS block of units (`partition`), whose head kernel stores the
+    result rows [score | class_probs] into every rank's buffer again (PeerRowGather).  Two fused
+    exchanges, no NCCL call and no host synchronisation on the path; every rank ends with all rows.
+    """
+
+    def __init__(self, net, total_frames: int, device: torch.device,
+                 group: Optional[dist.ProcessGroup] = None) -> None:
+        group = group if group is not None else dist.group.WORLD
+        self.net, self.device = net, device
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        self.unit = net.num_segments * net.seg_length
+        if total_frames % self.world != 0 or total_frames % self.unit != 0:
+            raise ValueError(f"FrameShardedScorer: {total_frames} frames must divide into {self.world} "
+                             f"equal rank blocks and into {self.unit}-frame units")
+        self.total_frames = total_frames
+        self.frames_per_rank = total_frames // self.world
+        self.blocks = partition(total_frames // self.unit, self.world)       # units per rank
+        self.width = len(net.classnames)                                      # [score | class_probs]
+        dim = net.image_encoder.output_dim
+        self.features = PeerRowGather(self.frames_per_rank, dim, device, group)
+        most = max(c for _, c in self.blocks)
+        self.rows = PeerRowGather(most * self.unit, self.width, device, group)
+        self._local = torch.empty((self.frames_per_rank, dim), dtype=torch.float32, device=device)
+        self._group = group
+
+    def _agree_on_mode(self, encoder, local_frames: torch.Tensor) -> None:
+        """An "auto" encoder calibrates on the frames it sees; ranks see different frames, so the
+        decision is made collectively: the one-pass mode only if EVERY rank's calibration accepts
+        it (one tiny all-reduce, once per encoder)."""
+        if encoder.mode is not None:
+            return
+        encoder.calibrate(local_frames.contiguous())
+        ok = torch.tensor([1 if encoder.mode == 4 else 0], device=self.device)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
+        encoder.mode = 4 if int(ok.item()) == 1 else 2
+        encoder.calibration["mode"] = encoder.mode
+        encoder.calibration["agreed_over_ranks"] = self.world
+
+    def frame_block(self) -> Tuple[int, int]:
+        """(first frame, count) of the frames this rank encodes."""
+        return self.rank * self.frames_per_rank, self.frames_per_rank
+
+    @torch.no_grad()
+    def __call__(self, local_frames: torch.Tensor, ncentroid: torch.Tensor) -> torch.Tensor:
+        """local_frames: this rank's (frames_per_rank, 3, R, R) block (uint8 or fp32 normalised) of
+        the `total_frames` frames, units laid out back to back (segment_size 1 per unit).
+        Returns rows [total_frames, 1 + (C-1)] = [score | class_probs] of ALL frames."""
+        net = self.net
+        if local_frames.shape[0] != self.frames_per_rank:
+            raise ValueError("FrameShardedScorer: wrong number of local frames")
+        encoder = net.image_encoder.encoder()
+        self._agree_on_mode(encoder, local_frames)
+        encoder(local_frames, out=self._local, peer=self.features)
+        feats = self.features.wait()                     # [total_frames, dim], all ranks' rows
+        start, count = self.blocks[self.rank]
+        if count:
+            scorer = net.scorer()
+            text = net.get_text_features()
+            if text.device != self.device:
+                text = net._text_features = text.to(self.device)
+            scorer.packed.set_directions(text, ncentroid)
+            scorer(feats[start * self.unit:(start + count) * self.unit], 1, peer=self.rows)
+        else:
+            self.rows.signal()
+        rows = self.rows.wait()
+        per = self.rows.rows_per_rank
+        if all(c * self.unit == per for _, c in self.blocks):
+            return rows
+        return torch.cat([rows[r * per: r * per + c * self.unit]
+                          for r, (_, c) in enumerate(self.blocks) if c], dim=0)
+
+    def check(self) -> None:
+        self.features.check()
+        self.rows.check()

@@ -51,16 +51,32 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 
 
 # ================================================================================ ViT encoder
+# GEMM operand modes of the image encoder ("passes", include/aclip_b200.h):
+#   3  split-bf16, three bf16 passes          ~1e-5 on the features
+#   2  f16f8: fp16 + two e4m3 cross terms     ~1e-5, two pass-equivalents
+#   4  f16: fp16 operands end to end          ~2.5e-4, one pass (attention included)
+#   "auto"  calibrate on the first frames: f16 if it agrees with f16f8 on this checkpoint within
+#           `calib_tol` and nothing saturates, else f16f8
+#   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
+FP16_PACKED_MODES = (2, 4, "auto")
+
+
 class PackedVit:
     """VisionTransformer state_dict (clip/model.py:233-264 names) -> AclipVitWeights."""
 
     def __init__(self, sd: Weights, device: torch.device, heads: Optional[int] = None,
-                 passes: int = 3) -> None:
+                 passes=3) -> None:
+        _require_cuda(device)
+        with torch.cuda.device(device):   # the packing kernels run on the device that owns the weights
+            self._pack(sd, device, heads, passes)
+
+    def _pack(self, sd: Weights, device: torch.device, heads: Optional[int], passes) -> None:
         """passes: the GEMM mode the weights are packed for -- 3 / 1: bf16 hi/lo planes,
-        2: f16f8 planes with a per-tensor exponent (include/aclip_b200.h)."""
+        2 / 4 / "auto": f16f8 planes with a per-tensor exponent (include/aclip_b200.h); the f16 mode
+        reads the fp16 plane of the same pack."""
         _require_cuda(device)
         self.device = device
-        self.f16f8 = passes == 2
+        self.f16f8 = passes in FP16_PACKED_MODES
         conv = sd["conv1.weight"]
         self.width, _, self.patch, _ = conv.shape
         tokens = sd["positional_embedding"].shape[0]
@@ -102,6 +118,8 @@ class PackedVit:
             wo = _split_weight(sd[p + "attn.out_proj.weight"], device)
             keep.append(wo)
             b.out_w, b.out_s, b.out_b = wo.data_ptr(), 0.0, f32(p + "attn.out_proj.bias")
+            if self.f16f8:  # the f16 mode runs out_proj on fp16 operands as well
+                b.out_w16, b.out_s = spl(sd[p + "attn.out_proj.weight"])
             (b.fc_w, b.fc_s), b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
             (b.proj_w, b.proj_s), b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
         w = self.struct = _lib.VitWeights()
@@ -119,18 +137,61 @@ class PackedVit:
 class VitEncoder:
     """frames -> 512-d features through `aclip_vit_forward`."""
 
-    def __init__(self, packed: PackedVit, micro_batch: int = 256, passes: int = 3) -> None:
-        if (passes == 2) != packed.f16f8:
-            raise _lib.AclipError("VitEncoder: passes=2 needs weights packed with PackedVit(passes=2) "
-                                  "(and only then)")
+    def __init__(self, packed: PackedVit, micro_batch: int = 256, passes=3,
+                 calib_frames: int = 16, calib_tol: float = 5e-4) -> None:
+        if passes not in (1, 3) + FP16_PACKED_MODES:
+            raise ValueError(f"VitEncoder: unknown operand mode passes={passes!r}")
+        if (passes in FP16_PACKED_MODES) != packed.f16f8:
+            raise _lib.AclipError("VitEncoder: passes=2/4/'auto' need weights packed with "
+                                  "PackedVit(passes=2/4/'auto') (and only then)")
         self.packed = packed
         self.micro_batch = micro_batch
-        self.passes = passes
+        self.passes = passes                              # as requested
+        self.mode = None if passes == "auto" else passes  # as run (resolved by calibrate())
+        self.calib_frames, self.calib_tol = calib_frames, calib_tol
+        self.calibration: Optional[dict] = None
         self._ws = _Workspace()
         self._mean = (C.c_float * 3)(*CLIP_MEAN)
         self._std = (C.c_float * 3)(*CLIP_STD)
 
-    def __call__(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    def calibrate(self, frames: torch.Tensor) -> dict:
+        """Decide the operand mode of an "auto" encoder on THIS checkpoint and THESE frames: encode
+        the first `calib_frames` frames with f16f8 operands (fp32-faithful) and with fp16 operands;
+        the one-pass mode is taken only if the two agree within `calib_tol` (relative L2 and relative
+        max error of the features) and no activation left the fp16 range."""
+        k = max(1, min(self.calib_frames, frames.shape[0]))
+        with torch.cuda.device(frames.device):
+            _lib.saturation_count(reset=True)
+            ref = self._run(frames[:k], None, 2)
+            sat2 = _lib.saturation_count(reset=True)
+            fast = self._run(frames[:k], None, 4)
+            sat4 = _lib.saturation_count(reset=True)
+        if sat2:
+            raise _lib.AclipError(
+                f"VitEncoder: {sat2} activations left the fp16 range of the f16f8 encoding "
+                "(|x| >= 4094) on this checkpoint: use passes=3 (split-bf16 operands)")
+        d = (fast.double() - ref.double())
+        rel = float(d.norm() / ref.double().norm())
+        mx = float(d.abs().max() / ref.double().abs().max())
+        ok = rel <= self.calib_tol and mx <= self.calib_tol and sat4 == 0
+        self.mode = 4 if ok else 2
+        self.calibration = {"frames": k, "rel_l2_f16_vs_f16f8": rel, "max_err_f16_vs_f16f8": mx,
+                            "tolerance": self.calib_tol, "saturations_f16": sat4, "mode": self.mode}
+        return self.calibration
+
+    def __call__(self, frames: torch.Tensor, out: Optional[torch.Tensor] = None,
+                 peer=None) -> torch.Tensor:
+        """peer: optional `distributed.PeerRowGather` built for (frames.shape[0], output_dim): the
+        output projection then also stores the feature rows into every rank's gathered buffer over
+        NVLink peer memory (frame-sharded encoder; read them with peer.wait())."""
+        if self.mode is None:
+            self._check(frames)
+            if frames.shape[0] == 0:
+                return self._run(frames, out, 2)
+            self.calibrate(frames.contiguous())
+        return self._run(frames, out, self.mode, peer)
+
+    def _check(self, frames: torch.Tensor) -> None:
         p = self.packed
         if not frames.is_cuda:
             raise _lib.AclipError("VitEncoder: frames must already be on the CUDA device")
@@ -138,20 +199,32 @@ class VitEncoder:
             raise TypeError(f"VitEncoder: frames must be float32 (normalised) or uint8, got {frames.dtype}")
         if frames.dim() != 4 or tuple(frames.shape[1:]) != (3, p.resolution, p.resolution):
             raise ValueError(f"VitEncoder: expected (N,3,{p.resolution},{p.resolution}), got {tuple(frames.shape)}")
+
+    def _run(self, frames: torch.Tensor, out: Optional[torch.Tensor], mode: int,
+             peer=None) -> torch.Tensor:
+        p = self.packed
+        self._check(frames)
         frames = frames.contiguous()
         n = frames.shape[0]
         if out is None:
             out = torch.empty((n, p.output_dim), dtype=torch.float32, device=frames.device)
         if n == 0:
+            if peer is not None:
+                peer.signal()
             return out
         lib = _lib.load()
+        gather = peer.descriptor(n, p.output_dim) if peer is not None else None
         mb = max(1, min(self.micro_batch, n))
         nbytes = lib.aclip_vit_workspace_bytes(C.byref(p.struct), mb)
         ws = self._ws.get(nbytes, frames.device)
-        _lib.check(lib.aclip_vit_forward(
-            C.byref(p.struct), frames.data_ptr(), int(frames.dtype == torch.uint8), n, mb,
-            self._mean, self._std, out.data_ptr(), ws, nbytes, self.passes,
-            torch.cuda.current_stream().cuda_stream))
+        # kernels are enqueued on the stream of the device that owns the tensors, whatever the
+        # caller's current device is
+        with torch.cuda.device(frames.device):
+            _lib.check(lib.aclip_vit_forward_ex(
+                C.byref(p.struct), frames.data_ptr(), int(frames.dtype == torch.uint8), n, mb,
+                self._mean, self._std, out.data_ptr(), ws, nbytes, mode,
+                C.addressof(gather) if gather is not None else None,
+                torch.cuda.current_stream(frames.device).cuda_stream))
         return out
 
 
@@ -180,6 +253,13 @@ class PackedTemporal:
                  emb_size: int, depth: int, heads: int, num_segments: int, seg_length: int,
                  concat_features: bool, feature_dim: int = 512) -> None:
         _require_cuda(device)
+        with torch.cuda.device(device):
+            self._pack(sd, device, num_classes, normal_id, emb_size, depth, heads, num_segments,
+                       seg_length, concat_features, feature_dim)
+
+    def _pack(self, sd: Weights, device: torch.device, num_classes: int, normal_id: int,
+              emb_size: int, depth: int, heads: int, num_segments: int, seg_length: int,
+              concat_features: bool, feature_dim: int) -> None:
         self.device = device
         self.num_classes, self.normal_id = num_classes, normal_id
         self.num_dirs = num_classes - 1
@@ -274,7 +354,8 @@ class PackedTemporal:
         if tf.shape[0] != self.num_classes:
             raise ValueError(f"text_features has {tf.shape[0]} rows, expected {self.num_classes}")
         sw, sb = selector_operands(tf, m, self.normal_id, self.bn_mean, self.bn_var)
-        sws = ops.split(sw)
+        with torch.cuda.device(self.device):
+            sws = ops.split(sw)
         self._dir_keep = (m, sws, sb, text_features, ncentroid)
         self.struct.ncentroid = m.data_ptr()
         self.struct.selector_w = sws.data_ptr()
@@ -285,10 +366,12 @@ class PackedTemporal:
 class TemporalScorer:
     """feature rows -> (similarity, scores, class_probs) through `aclip_temporal_forward`."""
 
-    def __init__(self, packed: PackedTemporal, passes: int = 3,
+    def __init__(self, packed: PackedTemporal, passes=3,
                  max_chunk_sub_videos: int = 512) -> None:
         self.packed = packed
-        self.passes = passes
+        # the fp16-operand modes of the image encoder (4, "auto") map to the temporal stage's
+        # f16f8 mode: its conv GEMMs on f16f8 operands for large chunks, three passes otherwise
+        self.passes = 2 if passes in (4, "auto") else passes
         self.max_chunk = max_chunk_sub_videos
         self._ws = _Workspace()
 
@@ -316,12 +399,13 @@ class TemporalScorer:
         chunk = max(1, min(sub_videos, self.max_chunk))
         nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), chunk)
         ws = self._ws.get(nbytes, dev)
-        gather = peer.descriptor(n_rows, p.num_dirs + 1) if peer is not None else None
-        _lib.check(lib.aclip_temporal_forward_ex(
-            C.byref(p.struct), feats.data_ptr(), sub_videos, segment_size, sim.data_ptr(),
-            scores.data_ptr(), probs.data_ptr() if probs is not None else None, ws, nbytes,
-            self.passes, C.byref(gather) if gather is not None else None,
-            torch.cuda.current_stream().cuda_stream))
+        gather = peer.descriptor(n_rows, p.num_dirs + 1, partial=True) if peer is not None else None
+        with torch.cuda.device(dev):
+            _lib.check(lib.aclip_temporal_forward_ex(
+                C.byref(p.struct), feats.data_ptr(), sub_videos, segment_size, sim.data_ptr(),
+                scores.data_ptr(), probs.data_ptr() if probs is not None else None, ws, nbytes,
+                self.passes, C.byref(gather) if gather is not None else None,
+                torch.cuda.current_stream(dev).cuda_stream))
         return sim, scores, probs
 
 
@@ -348,13 +432,14 @@ class TemporalCore:
             x = torch.nn.functional.pad(x, (0, p.in_pad - p.in_dim))
         rows = x.shape[0]
         sub_videos = rows // unit
-        xs = ops.center(x.contiguous(), self._zeros, regroup=(n, segment_size, l))   # regroup + split
-        proj = ops.gemm(xs, p.proj_plain, bias=p.proj_bias, residual=p.pos, res_mod=unit)
-        scores = torch.empty(rows, dtype=torch.float32, device=x.device)
-        lib = _lib.load()
-        nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), sub_videos)
-        ws = self._ws.get(nbytes, x.device)
-        _lib.check(lib.aclip_temporal_core_forward(
-            C.byref(p.struct), proj.data_ptr(), sub_videos, segment_size, scores.data_ptr(), ws, nbytes,
-            self.passes, torch.cuda.current_stream().cuda_stream))
+        with torch.cuda.device(x.device):
+            xs = ops.center(x.contiguous(), self._zeros, regroup=(n, segment_size, l))   # regroup + split
+            proj = ops.gemm(xs, p.proj_plain, bias=p.proj_bias, residual=p.pos, res_mod=unit)
+            scores = torch.empty(rows, dtype=torch.float32, device=x.device)
+            lib = _lib.load()
+            nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), sub_videos)
+            ws = self._ws.get(nbytes, x.device)
+            _lib.check(lib.aclip_temporal_core_forward(
+                C.byref(p.struct), proj.data_ptr(), sub_videos, segment_size, scores.data_ptr(), ws,
+                nbytes, self.passes, torch.cuda.current_stream(x.device).cuda_stream))
         return scores.unsqueeze(1)

@@ -66,13 +66,16 @@ class VisionTransformer(nn.Module):
     """clip/model.py:233-290.  forward(frames (B,3,R,R) fp32 normalised | uint8) -> (B, output_dim)."""
 
     def __init__(self, input_resolution: int, patch_size: int, width: int, layers: int, heads: int,
-                 output_dim: int, micro_batch: int = 256, passes: Optional[int] = None) -> None:
+                 output_dim: int, micro_batch: int = 256, passes=None) -> None:
         """passes: GEMM operand mode -- 3 = split-bf16 x3, 2 = fp16 + e4m3 cross terms (both
-        fp32-faithful, ~1e-5 on the features), 1 = plain bf16; None picks 2 where the CTA-pair
-        kernel applies (width and output_dim multiples of 256, e.g. every CLIP ViT-B/L) else 3."""
+        fp32-faithful, ~1e-5 on the features), 4 = fp16 operands in one pass (~2.5e-4), "auto" =
+        4 if a calibration on the first frames shows it within 5e-4 of mode 2 on this checkpoint and
+        nothing saturates, else 2 (engine.VitEncoder.calibrate); 1 = plain bf16.  None picks "auto"
+        where the CTA-pair kernel applies (width and output_dim multiples of 256, e.g. every CLIP
+        ViT-B/L) else 3."""
         super().__init__()
         if passes is None:
-            passes = 2 if width % 256 == 0 and output_dim % 256 == 0 and patch_size % 4 == 0 else 3
+            passes = "auto" if width % 256 == 0 and output_dim % 256 == 0 and patch_size % 4 == 0 else 3
         self.input_resolution, self.output_dim = input_resolution, output_dim
         self.heads, self.micro_batch, self.passes = heads, micro_batch, passes
         self.conv1 = nn.Conv2d(3, width, patch_size, patch_size, bias=False)

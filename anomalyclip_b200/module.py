@@ -16,12 +16,18 @@ from typing import Any, Dict, List, Optional
 import torch
 from torch import nn
 
-try:  # pragma: no cover - Lightning is not installed in the build image
+try:  # Lightning is not installed in the build image; tests drive this branch with a stub package
+    import pytorch_lightning as _pl
     from pytorch_lightning import LightningModule as _Base
     _HAVE_LIGHTNING = True
+    try:
+        _LIGHTNING_MAJOR = int(str(getattr(_pl, "__version__", "1.8.3")).split(".")[0])
+    except ValueError:
+        _LIGHTNING_MAJOR = 1
 except Exception:  # noqa: BLE001
     _Base = nn.Module
     _HAVE_LIGHTNING = False
+    _LIGHTNING_MAJOR = 0
 
 
 class AnomalyCLIPModule(_Base):
@@ -35,6 +41,7 @@ class AnomalyCLIPModule(_Base):
         self.num_classes = kwargs.get("num_classes")
         self.save_dir = kwargs.get("save_dir")
         self.ncentroid: Optional[torch.Tensor] = None
+        self.last_metrics: Dict[str, float] = {}
         self.labels: List[torch.Tensor] = []
         self.abnormal_scores: List[torch.Tensor] = []
         self.class_probs: List[torch.Tensor] = []
@@ -102,6 +109,8 @@ class AnomalyCLIPModule(_Base):
         dev = self._device
         image_features = image_features.to(dev, non_blocking=True)
         labels = labels.squeeze(0).to(dev)
+        if self.ncentroid.device != dev:   # once: a side-car centroid is loaded on the CPU
+            self.ncentroid = self.ncentroid.to(dev)
         if torch.is_tensor(segment_size):
             segment_size = int(segment_size.reshape(-1)[0])
         similarity, abnormal_scores = self.forward(image_features, labels, self.ncentroid,
@@ -122,9 +131,14 @@ class AnomalyCLIPModule(_Base):
         return out
 
     # ---- metrics (anomaly_clip_module.py:501-619, the numeric part)
-    def test_epoch_end(self, outputs: Any = None) -> Dict[str, float]:
+    def finish_test_epoch(self) -> Dict[str, float]:
+        """Metrics over everything `test_step` accumulated, then clear the accumulators.  Called
+        again on empty accumulators (Lightning 1.8 fires `test_epoch_end(outputs)` and then
+        `on_test_epoch_end()`) it returns the metrics of the epoch just finished."""
         from .metrics import frame_metrics
 
+        if not self.labels:
+            return self.last_metrics
         labels = torch.cat(self.labels)
         scores = torch.cat(self.abnormal_scores)
         probs = torch.cat(self.class_probs)
@@ -135,6 +149,15 @@ class AnomalyCLIPModule(_Base):
             with open(Path(self.save_dir) / "metrics.json", "w") as fp:
                 json.dump(metrics, fp, indent=4, sort_keys=True)
         self.labels.clear(), self.abnormal_scores.clear(), self.class_probs.clear()
+        self.last_metrics = metrics
         return metrics
 
-    on_test_epoch_end = test_epoch_end
+    # One epoch-end hook per Lightning generation: 1.x (the reference pins 1.8.3) calls
+    # `test_epoch_end(outputs)`; 2.x rejects a module that overrides it and calls
+    # `on_test_epoch_end()` instead.  Without Lightning the 1.x name is kept for direct callers.
+    if _LIGHTNING_MAJOR >= 2:
+        def on_test_epoch_end(self) -> None:
+            self.finish_test_epoch()
+    else:
+        def test_epoch_end(self, outputs: Any = None) -> Dict[str, float]:
+            return self.finish_test_epoch()

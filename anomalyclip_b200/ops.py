@@ -103,6 +103,16 @@ def encode_f16f8(x: torch.Tensor, *, weight: bool = False, ld_out: Optional[int]
     return out
 
 
+def encode_f16(x: torch.Tensor) -> torch.Tensor:
+    """fp32 [rows, cols] -> the "f16" activation encoding fp16(x * 2^4) (tests build operands with
+    this torch cast; on the path the producing kernels write it)."""
+    return (x.to(torch.float32) * 2.0 ** ACT_EXP[0]).to(torch.float16).contiguous()
+
+
+def decode_f16(h: torch.Tensor) -> torch.Tensor:
+    return h.double() * 2.0 ** -ACT_EXP[0]
+
+
 def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = None,
          act: int = ACT_NONE, residual: Optional[torch.Tensor] = None, res_mod: int = 0,
          out_f32: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
@@ -114,10 +124,27 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     a: split [2, M, lda] (linear) or split NHWC grid [2, S, H, W, C] with conv=(S, H, W, C).
     w: split [2, N, ldw].
     passes=2: a and w are `F16F8` operands; out_enc=1 with want_split returns an `F16F8` output.
+    passes=4: a is an fp16 tensor [M, lda] (`encode_f16`; conv: [S*H*W, C]), w an `F16F8` weight (its
+    fp16 plane is read); out_enc=2 with want_split returns an fp16 tensor [rows, N].
     """
     lib = _lib.load()
     g = GemmArgs()
-    if passes == 2:
+    if passes == 4:
+        if not (isinstance(w, F16F8) and isinstance(a, torch.Tensor) and a.dtype == torch.float16):
+            raise TypeError("gemm(passes=4) needs an fp16 activation tensor and an F16F8 weight")
+        M, N = a.shape[0], w.rows
+        Kk = K if K is not None else a.shape[1]
+        g.lda, g.ldw = a.stride(0), w.ld
+        if conv is not None:
+            S, H, Wd, Cc = conv
+            if a.shape[0] != S * H * Wd or a.shape[1] != Cc:
+                raise ValueError("gemm(passes=4, conv): the fp16 grid must be [S*H*W, C]")
+            Kk = 9 * Cc
+            g.a_mode, g.conv_s, g.conv_h, g.conv_w, g.conv_c = 1, S, H, Wd, Cc
+        g.a_plane_stride, g.w_plane_stride = a.numel(), w.plane_stride
+        g.out_scale = 2.0 ** -(ACT_EXP[0] + w.exp)
+        dev = a.device
+    elif passes == 2:
         if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
             raise TypeError("gemm(passes=2) needs F16F8 operands")
         M, N = a.rows, w.rows
@@ -158,6 +185,8 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if out_f32 is None and out_split is None:
         if want_split and out_enc == 1:
             out_split = F16F8(rows, N, dev)
+        elif want_split and out_enc == 2:
+            out_split = torch.empty((rows, N), dtype=torch.float16, device=dev)
         elif want_split:
             out_split = torch.empty((2, rows, N), dtype=torch.bfloat16, device=dev)
         else:
@@ -167,6 +196,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
     if isinstance(out_split, F16F8):
         g.out_split, g.ld_split = out_split.data_ptr(), out_split.ld
         g.split_plane_stride = out_split.plane_stride
+    elif out_split is not None and out_split.dtype == torch.float16:
+        g.out_split, g.ld_split = out_split.data_ptr(), out_split.stride(0)
+        g.split_plane_stride = out_split.numel()
     elif out_split is not None:
         g.out_split, g.ld_split = out_split.data_ptr(), out_split.stride(1)
         g.split_plane_stride = out_split.stride(0)
@@ -182,15 +214,17 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
               chan_mode: bool = False, want_f32: bool = True, want_split: bool = False,
               out_enc: int = 0):
     """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std).
-    out_enc=1: the split output is an `F16F8` activation tensor."""
+    out_enc=1: the split output is an `F16F8` activation tensor; out_enc=2: an fp16 tensor."""
     x = _f32c(x, "x")
     rows, D = x.reshape(-1, x.shape[-1]).shape
     out_f32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
     out_split = None
     if want_split:
         out_split = F16F8(rows, D, x.device) if out_enc == 1 else \
+            torch.empty((rows, D), dtype=torch.float16, device=x.device) if out_enc == 2 else \
             torch.empty((2, rows, D), dtype=torch.bfloat16, device=x.device)
-    plane = 0 if out_split is None else (out_split.plane_stride if out_enc == 1 else out_split.stride(0))
+    plane = 0 if out_split is None else (out_split.plane_stride if out_enc == 1 else
+                                         out_split.numel() if out_enc == 2 else out_split.stride(0))
     lib = _lib.load()
     _lib.check(lib.aclip_layernorm(
         x.data_ptr(), rows, D, D, _f32c(gamma, "gamma").data_ptr(), _f32c(beta, "beta").data_ptr(),
@@ -203,9 +237,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
 
 def vit_attention(qkv_split: torch.Tensor, B: int, L: int, heads: int, kernel: int = 0,
                   out_enc: int = 0):
-    """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64] (out_enc=1: `F16F8`)."""
+    """qkv_split: [2, B*L, 3*heads*64] -> split [2, B*L, heads*64] (out_enc=1: `F16F8`).
+    out_enc=2: qkv is an fp16 tensor [B*L, 3*heads*64] (`encode_f16`), the result fp16 [B*L, heads*64]."""
     W = heads * 64
     lib = _lib.load()
+    if out_enc == 2:
+        if qkv_split.dtype != torch.float16 or qkv_split.dim() != 2:
+            raise TypeError("vit_attention(out_enc=2) needs an fp16 [B*L, 3W] tensor")
+        out = torch.empty((B * L, W), dtype=torch.float16, device=qkv_split.device)
+        _lib.check(lib.aclip_vit_attention(qkv_split.data_ptr(), qkv_split.numel(),
+                                           qkv_split.stride(0), B, L, heads, out.data_ptr(),
+                                           out.numel(), W, kernel, 2, _stream()))
+        return out
     if out_enc == 1:
         out = F16F8(B * L, W, qkv_split.device)
         plane, ld = out.plane_stride, W

@@ -5,9 +5,21 @@
 
 One "step" = one pass of the hot path over one 512-frame unit of synthetic ShanghaiTech-shaped
 raw frames (uint8 224x224; two 256-frame ViT micro-batches = one 32x16 temporal grid):
-ViT-B/16 encode -> selector -> axial temporal transformer -> score + class probabilities.
-With N > 1 every rank processes its own unit (weak scaling) and the per-frame result rows are
-exchanged with ONE NCCL all-gather per step.  Rank 0 prints ONE JSON line.
+ViT-B/16 encode -> selector -> axial temporal transformer -> score + class probabilities
+(BASELINE.json configs[2]).  With N > 1 every rank processes its own unit (weak scaling) and the
+per-frame result rows are exchanged once per step.  Rank 0 prints ONE JSON line.
+
+Besides the headline the line carries, each measured outside the headline's timed region:
+  parity_in_bench    N = 1: the GPU encoder and temporal stage against the CPU oracle on the
+                     inputs of the cpu_baseline leg (rel-L2, argmax agreement)
+  exchange_check     N > 1: the fused peer gather against one NCCL all-gather, bit for bit, on
+                     consecutive steps of both buffer parities, and no wait timed out
+  torch_gpu_baseline N = 1: the same arithmetic as stock PyTorch ops on the GPU (fp32, TF32 allowed)
+  features_path      BASELINE configs[1]: UCF-Crime-shaped features, 64 and 512 sub-videos
+  vit_block          BASELINE configs[4]: one ResidualAttentionBlock at batch 256
+  strong_scaling_xd  BASELINE configs[3]: XD-Violence-shaped frames, 2 048 frames per step over
+                     the N ranks (frame-sharded encoder, fused feature + score gathers), with a
+                     bit-identity check against the same frames scored by one rank alone
 """
 from __future__ import annotations
 
@@ -30,27 +42,34 @@ UNIT = "frames/s"
 PRESET = "shanghaitech"
 FRAMES_PER_STEP = 512
 VIT_GFLOP_PER_FRAME = 35.127      # SURVEY 8d / BASELINE.md 2 (algorithmic, fp32 semantics)
-TEMPORAL_MFLOP_PER_FRAME = 40.2   # ShanghaiTech configuration
+VIT_BLOCK_GFLOP_PER_FRAME = 2.9079
+TEMPORAL_MFLOP_PER_FRAME = {"ucfcrime": 20.2, "shanghaitech": 40.2, "xdviolence": 5.1}
+STRONG_FRAMES = 2048              # configs[3]
 
-
+# operand mode of the image encoder -> (dtype string, description, bf16-pass equivalents per product)
 PRECISION = {
     3: ("bf16x3-split operands, f32 accumulate/residual",
-        "split-bf16 x3 tensor-core passes, fp32 accumulate (parity mode)"),
+        "split-bf16 x3 tensor-core passes, fp32 accumulate", 3.0),
     2: ("f16 + e4m3 cross-term operands (2 pass-equivalents), f32 accumulate/residual",
         "fp16 main product + two e4m3 cross-term products per GEMM (2 bf16-pass equivalents of "
-        "tensor time), fp32 accumulate (parity mode); attention and the temporal stage: split-bf16 x3"),
+        "tensor time), fp32 accumulate; attention and out_proj: split-bf16 x3", 2.0),
+    4: ("f16 operands (one pass), f32 accumulate/residual/LayerNorm/softmax",
+        "fp16 operands in one tensor-core pass for every ViT GEMM and the attention, fp32 accumulate, "
+        "fp32 residual stream / LayerNorm statistics / softmax; selected per checkpoint by calibration "
+        "against the f16f8 mode (features within 5e-4, no fp16 saturation)", 1.0),
 }
 
 
-def _workload_config(n_gpus: int, micro_batch: int = 256, passes: int = 3) -> dict:
+def _workload_config(n_gpus: int, micro_batch: int = 256) -> dict:
+    """Names the workload only (identical on both arms); precision and transport are reported in
+    their own keys."""
     return {
         "workload": ("configs[2]: ShanghaiTech-shaped raw frames 224x224 uint8, 512 frames/step/GPU "
                      "(2 ViT micro-batches of 256 = one 32x16 temporal unit), full ViT-B/16 + selector "
                      "+ temporal + score path"),
         "frames_per_step_per_gpu": FRAMES_PER_STEP,
         "vit_micro_batch": micro_batch,
-        "precision": PRECISION[passes][1],
-        "l2": "inputs rotate over 4 frame buffers (308 MB) and activations are ~0.9 GB per micro-batch, both > 126 MB L2",
+        "l2": "inputs rotate over 4 frame buffers (308 MB) and activations are ~0.5-0.9 GB per micro-batch, both > 126 MB L2",
         "parallelism": f"dp{n_gpus} over sub-videos, one exchange of score rows per step",
     }
 
@@ -64,6 +83,17 @@ def _peaks() -> dict:
                 "tf_sustained": p.get("bf16_tflops_sustained", p["bf16_tflops"]), "src": "measured"}
     except Exception:  # noqa: BLE001 - fallback stated by B200_PROFILING.md
         return {"hbm": 6650.0, "tf_burst": 1590.0, "tf_sustained": 1400.0, "src": "fallback"}
+
+
+def _ncu_traffic() -> dict:
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of the ViT-block GEMMs from the
+    tracked ncu --set full capture of this round (profiles/r2_ncu_gemm_traffic.json, written by
+    scripts/ncu_traffic.py from the .ncu-rep; it records the commit it was taken at)."""
+    try:
+        with open(os.path.join(ROOT, "profiles", "r2_ncu_gemm_traffic.json")) as fp:
+            return json.load(fp)
+    except Exception:  # noqa: BLE001
+        return {}
 
 
 class _ClockSampler:
@@ -108,24 +138,43 @@ class _ClockSampler:
                 "samples": len(sm)}
 
 
+def _time_gpu(fn, iters: int, warmup: int = 3, flush=None) -> float:
+    """Mean device milliseconds of fn() over `iters` calls (CUDA events on the current stream,
+    synchronised both sides; the L2 is flushed between iterations when a flush buffer is given)."""
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    tot = 0.0
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(); fn(); b.record()
+        torch.cuda.synchronize()
+        tot += a.elapsed_time(b)
+    return tot / iters
+
+
 # ------------------------------------------------------------------------------------------
-def _cpu_reference_step(sample_frames: int, threads: int, state) -> float:
+def _cpu_reference_step(sample_frames: int, threads: int, state):
     """One bounded sample of the reference arithmetic on the host cores (the oracle port):
     ViT on `sample_frames` frames + selector/temporal/head on one 512-row unit.  Returns the
-    frames/s the whole 512-frame step would run at (ViT time scaled to 512 frames)."""
+    frames/s the whole 512-frame step would run at (ViT time scaled to 512 frames) and the
+    oracle's outputs (features of the sample, similarity, scores) for the in-bench parity check."""
     from oracle import anomalyclip_oracle as oracle
     cfg, sd, vit_sd, text, m, frames, feats = state
     torch.set_num_threads(threads)
     with torch.no_grad():
         t0 = time.perf_counter()
-        oracle.vit_forward(vit_sd, frames[:sample_frames])
+        vit_out = oracle.vit_forward(vit_sd, frames[:sample_frames])
         t1 = time.perf_counter()
-        oracle.anomaly_clip_forward(sd, feats, m, text, segment_size=1, normal_id=cfg.normal_id,
-                                    num_segments=cfg.num_segments, seg_length=cfg.seg_length,
-                                    depth=cfg.depth, heads=cfg.heads,
-                                    concat_features=cfg.concat_features)
+        sim, scores = oracle.anomaly_clip_forward(sd, feats, m, text, segment_size=1, normal_id=cfg.normal_id,
+                                                  num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                                                  depth=cfg.depth, heads=cfg.heads,
+                                                  concat_features=cfg.concat_features)
         t2 = time.perf_counter()
-    return FRAMES_PER_STEP / ((t1 - t0) * FRAMES_PER_STEP / sample_frames + (t2 - t1))
+    value = FRAMES_PER_STEP / ((t1 - t0) * FRAMES_PER_STEP / sample_frames + (t2 - t1))
+    return value, (vit_out, sim, scores)
 
 
 def _cpu_state(sample_frames: int):
@@ -136,6 +185,33 @@ def _cpu_state(sample_frames: int):
     frames = syn.normalise_frames(syn.make_frames_u8(sample_frames, seed=0))
     feats = syn.make_features(cfg, 1, seed=0)
     return cfg, sd, vit_sd, syn.make_text_features(cfg), syn.make_ncentroid(cfg), frames, feats
+
+
+def _rel(a: torch.Tensor, b: torch.Tensor) -> float:
+    a, b = a.detach().double().cpu(), b.detach().double().cpu()
+    return float((a - b).norm() / b.norm().clamp_min(1e-30))
+
+
+def _parity_in_bench(net, dev, sample_frames: int, state, oracle_out) -> dict:
+    """The product path against the oracle outputs of the cpu_baseline leg (same seeded inputs)."""
+    from anomalyclip_b200 import synthetic as syn
+    cfg, _, _, text, m, _, feats = state
+    vit_ref, sim_ref, sc_ref = oracle_out
+    u8 = syn.make_frames_u8(sample_frames, seed=0).to(dev)
+    feat_gpu = net.image_encoder(u8)
+    scorer = net.scorer()
+    scorer.packed.set_directions(text.to(dev), m.to(dev))
+    sim, sc, probs = scorer(feats.reshape(-1, feats.shape[-1]).to(dev), 1)
+    probs_ref = torch.softmax(sim_ref, dim=1) * sc_ref.reshape(-1, 1)
+    top = probs.cpu().argmax(dim=1)
+    return {"vit_features_rel_l2": _rel(feat_gpu, vit_ref),
+            "vit_features_max_err_over_max": float((feat_gpu.cpu().double() - vit_ref.double()).abs().max()
+                                                   / vit_ref.double().abs().max()),
+            "similarity_rel_l2": _rel(sim, sim_ref), "scores_rel_l2": _rel(sc, sc_ref.reshape(-1)),
+            "class_argmax_mismatches": int((top != probs_ref.argmax(dim=1)).sum()),
+            "rows": int(top.numel()), "frames": sample_frames, "bar": 1e-3,
+            "what": "GPU path vs CPU oracle on the cpu_baseline leg's inputs (uint8 frames seed 0; "
+                    "one 512-row feature unit), outside the timed region"}
 
 
 def _torch_gpu_baseline(dev) -> dict:
@@ -174,8 +250,56 @@ def _torch_gpu_baseline(dev) -> dict:
         torch.cuda.synchronize()
         out[name] = {"frames_per_s": FRAMES_PER_STEP * 3 / (e0.elapsed_time(e1) * 1e-3)}
     torch.backends.cuda.matmul.allow_tf32 = False
+    torch.backends.cudnn.allow_tf32 = False
     out["what"] = "oracle torch ops on cuda:0, 512 frames/step in 2 ViT batches of 256, 2 warm-ups + 3 steps"
     return out
+
+
+def _features_path(dev) -> dict:
+    """BASELINE configs[1]: UCF-Crime-shaped pre-extracted features through selector + temporal +
+    head (load_from_features=True), 64 and 512 sub-videos of 32 x 16 rows."""
+    from anomalyclip_b200 import synthetic as syn
+    from anomalyclip_b200.engine import PackedTemporal, TemporalScorer
+    cfg = syn.PRESETS["ucfcrime"]
+    packed = PackedTemporal(syn.make_state_dict(cfg, with_vit=False), dev, num_classes=cfg.num_classes,
+                            normal_id=cfg.normal_id, emb_size=cfg.emb_size, depth=cfg.depth,
+                            heads=cfg.heads, num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                            concat_features=cfg.concat_features)
+    packed.set_directions(syn.make_text_features(cfg).to(dev), syn.make_ncentroid(cfg).to(dev))
+    scorer = TemporalScorer(packed, passes=2, max_chunk_sub_videos=1024)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    out = {"workload": "configs[1]: UCF-Crime-shaped features (32 segments x 16 rows, 14 classes), "
+                       "selector + temporal + head, inputs resident, L2 flushed between iterations",
+           "mflop_per_row": TEMPORAL_MFLOP_PER_FRAME["ucfcrime"]}
+    for B in (1, 64, 512):
+        feats = torch.randn(B * cfg.unit, 512, device=dev) * 0.5
+        ms = _time_gpu(lambda: scorer(feats, 1), iters=5, flush=flush)
+        rows = B * cfg.unit
+        out[f"sub_videos_{B}"] = {"ms": round(ms, 4), "rows_per_s": round(rows / ms * 1e3),
+                                  "algo_tflops": round(rows * TEMPORAL_MFLOP_PER_FRAME["ucfcrime"] / ms / 1e3, 1)}
+    return out
+
+
+def _vit_block(dev, mode: int, peaks: dict) -> dict:
+    """BASELINE configs[4]: one ResidualAttentionBlock (seq 197, d 768) at batch 256: the per-block
+    time is (3-layer encoder - 1-layer encoder) / 2 on the same frames."""
+    from anomalyclip_b200 import synthetic as syn
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    B = 256
+    enc = {n: VitEncoder(PackedVit(syn.make_vit_weights(layers=n), dev, passes=mode), micro_batch=B, passes=mode)
+           for n in (1, 3)}
+    frames = syn.make_frames_u8(64, seed=1).to(dev).repeat(B // 64, 1, 1, 1).contiguous()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    buf = torch.empty(B, 512, device=dev)
+    t = {n: _time_gpu(lambda e=e: e(frames, buf), iters=5, flush=flush) for n, e in enc.items()}
+    block_ms = (t[3] - t[1]) / 2
+    tf = VIT_BLOCK_GFLOP_PER_FRAME * B / block_ms
+    passes = PRECISION[mode][2]
+    return {"workload": "configs[4]: one ViT-B/16 ResidualAttentionBlock, seq_len 197, d 768, batch 256",
+            "block_ms": round(block_ms, 4), "algo_tflops": round(tf, 1),
+            "frac_of_sustained_bf16_peak": round(tf / peaks["tf_sustained"], 3),
+            "frac_of_burst_bf16_peak": round(tf / peaks["tf_burst"], 3),
+            "pass_equivalents": passes, "tensor_pipe_issued_frac_of_burst": round(passes * tf / peaks["tf_burst"], 3)}
 
 
 def run_reference(args) -> None:
@@ -193,7 +317,7 @@ def run_reference(args) -> None:
     vals = []
     t0 = time.perf_counter()
     for _ in range(args.steps):
-        vals.append(_cpu_reference_step(sample, threads, state))
+        vals.append(_cpu_reference_step(sample, threads, state)[0])
     wall = time.perf_counter() - t0
     value = statistics.median(vals)
     sample_txt = (f"per step: oracle ViT-B/16 on {sample} frames (scaled to {FRAMES_PER_STEP}) + "
@@ -202,7 +326,7 @@ def run_reference(args) -> None:
         "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * wall / max(args.steps, 1),
         "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-        "data": "synthetic", "config": _workload_config(args.gpus, args.micro_batch, args.passes),
+        "data": "synthetic", "config": _workload_config(args.gpus, args.micro_batch),
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port",
                          "sample": sample_txt},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
@@ -211,11 +335,93 @@ def run_reference(args) -> None:
 
 
 # ------------------------------------------------------------------------------------------
+def _build_net(cfg, dev, micro_batch, passes):
+    from anomalyclip_b200 import synthetic as syn
+    from anomalyclip_b200.models import AnomalyCLIP
+    net = AnomalyCLIP(arch="ViT-B/16", classnames=[f"class_{i:02d}" for i in range(cfg.num_classes)],
+                      emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, dim_heads=None,
+                      num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                      concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=cfg.stride,
+                      load_from_features=False, ncrops=cfg.ncrops, build_text_tower=False,
+                      micro_batch=micro_batch, passes=passes)
+    missing, unexpected = net.load_state_dict(syn.make_state_dict(cfg, with_vit=True), strict=False)
+    assert not unexpected and not missing, (missing, unexpected)
+    net.set_text_features(syn.make_text_features(cfg))
+    net.to(dev).eval()
+    return net
+
+
+def _strong_scaling_xd(dev, world, rank, args, barrier, max_over_ranks) -> dict:
+    """BASELINE configs[3]: XD-Violence-shaped raw frames, 2 048 frames per step over the N ranks
+    (strong scaling: the global batch is fixed, each rank encodes 2048 / N frames), frame-sharded
+    encoder with the feature all-gather fused into the projection GEMM, units dealt to the ranks,
+    score rows gathered by the head kernel."""
+    import torch.distributed as dist
+    from anomalyclip_b200 import _lib, synthetic as syn
+    cfg = syn.PRESETS["xdviolence"]
+    net = _build_net(cfg, dev, args.micro_batch, args.passes)
+    m = syn.make_ncentroid(cfg).to(dev)
+    per = STRONG_FRAMES // world
+    n_buf = 2
+    # every rank generates the same global frame set and keeps its own block (plus, for the
+    # one-off check, rank 0's view of everything)
+    full = [syn.make_frames_u8(STRONG_FRAMES, seed=500 + i) for i in range(n_buf)]
+    local = [f[rank * per:(rank + 1) * per].to(dev) for f in full]
+    steps = max(3, min(args.steps, 10))
+    record = {"workload": "configs[3]: XD-Violence-shaped raw frames 224x224 uint8, 2048 frames/step over "
+                          f"{world} GPU(s) (strong scaling, {per} frames/GPU), full ViT-B/16 + selector + "
+                          "temporal + score path", "frames_per_step": STRONG_FRAMES, "scaling": "strong",
+              "n_gpus": world, "steps": steps}
+    if world == 1:
+        # units laid out back to back = a batch of 4 videos of 512 frames
+        def step(i):
+            _, scores = net(local[i % n_buf].reshape(STRONG_FRAMES // cfg.unit, cfg.unit, 3, 224, 224),
+                            None, m, 1, True)
+            return torch.cat((scores.unsqueeze(1), net.class_probs), dim=1)
+        check = None
+    else:
+        from anomalyclip_b200.distributed import FrameShardedScorer
+        sharded = FrameShardedScorer(net, STRONG_FRAMES, dev)
+
+        def step(i):
+            return sharded(local[i % n_buf], m)
+        # bit identity with the same frames scored by this rank alone (single-rank path)
+        rows = step(0).clone()
+        _, sc = net(full[0].to(dev).reshape(STRONG_FRAMES // cfg.unit, cfg.unit, 3, 224, 224), None, m, 1, True)
+        alone = torch.cat((sc.unsqueeze(1), net.class_probs), dim=1)
+        same = torch.tensor([int(torch.equal(rows, alone))], device=dev)
+        dist.all_reduce(same, op=dist.ReduceOp.MIN)
+        diff = (rows - alone).abs().max().reshape(1)
+        dist.all_reduce(diff, op=dist.ReduceOp.MAX)
+        check = {"bit_identical_to_single_rank": bool(int(same.item())), "max_abs_diff": float(diff.item()),
+                 "rows": int(rows.shape[0]),
+                 "what": "rows of all 2048 frames from the frame-sharded path vs the same frames scored "
+                         "by each rank alone, compared on every rank"}
+    for i in range(3):
+        step(i)
+    barrier()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(steps):
+        step(i)
+    e1.record()
+    barrier()
+    ms = max_over_ranks(e0.elapsed_time(e1))
+    if world > 1:
+        sharded.check()
+    record.update({"value": STRONG_FRAMES * steps / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms / steps,
+                   "gpu_launches_rank0": _lib.launch_count() - l0, "check": check,
+                   "exchange": "none (1 GPU)" if world == 1 else
+                   "features: stored into every rank's buffer by the projection GEMM's epilogue; score rows: "
+                   "by the head kernel (NVLink peer memory, stream-side flag waits, no NCCL on the path)"})
+    return record
+
+
 def run_b200(args) -> None:
     import torch.distributed as dist
     from anomalyclip_b200 import _lib, synthetic as syn
     from anomalyclip_b200.distributed import gather_rows
-    from anomalyclip_b200.models import AnomalyCLIP
     from anomalyclip_b200.module import AnomalyCLIPModule
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -233,16 +439,7 @@ def run_b200(args) -> None:
     n_gpus = world
 
     cfg = syn.PRESETS[PRESET]
-    net = AnomalyCLIP(arch="ViT-B/16", classnames=[f"class_{i:02d}" for i in range(cfg.num_classes)],
-                      emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, dim_heads=None,
-                      num_segments=cfg.num_segments, seg_length=cfg.seg_length,
-                      concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=cfg.stride,
-                      load_from_features=False, ncrops=cfg.ncrops, build_text_tower=False,
-                      micro_batch=args.micro_batch, passes=args.passes)
-    missing, unexpected = net.load_state_dict(syn.make_state_dict(cfg, with_vit=True), strict=False)
-    assert not unexpected and not missing, (missing, unexpected)
-    net.set_text_features(syn.make_text_features(cfg))
-    net.to(dev).eval()
+    net = _build_net(cfg, dev, args.micro_batch, args.passes)
     module = AnomalyCLIPModule(net, num_classes=cfg.num_classes)
     module.ncentroid = syn.make_ncentroid(cfg).to(dev)
 
@@ -296,20 +493,51 @@ def run_b200(args) -> None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    if args.ncu:  # under ncu: one warm-up step + one profiled step, nothing else
-        step_resident(0)
+    if args.ncu:  # under ncu: warm-up steps + one profiled step, nothing else
+        for i in range(2):
+            step_resident(i)
         torch.cuda.synchronize()
         torch.cuda.profiler.start()
-        step_resident(1)
+        step_resident(2)
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
 
-    # ---- device-resident timing (value)
-    for i in range(max(args.warmup, 3)):
-        step_resident(i)
+    # ---- warm-up (the first call also calibrates an "auto" encoder); at N > 1 every warm-up step
+    # runs BOTH transports on the same rows and compares them bit for bit on every rank
+    exchange_check = None
+    n_warm = max(args.warmup, 3 if world == 1 else 4)
+    if world > 1 and peer is not None:
+        mismatches, checked = 0, 0
+        for i in range(n_warm):
+            _, scores = net(resident[i % n_buf], None, module.ncentroid, 1, True)
+            fused = peer.wait().clone()
+            via_nccl = gather_rows(torch.cat((scores.unsqueeze(1), net.class_probs), dim=1),
+                                   [FRAMES_PER_STEP] * world)
+            mismatches += int(not torch.equal(fused, via_nccl))
+            checked += 1
+        bad = torch.tensor([mismatches], device=dev)
+        dist.all_reduce(bad, op=dist.ReduceOp.SUM)
+        exchange_check = {"steps_compared": checked, "parities": "both (consecutive epochs)",
+                          "ranks_with_mismatch_total": int(bad.item()),
+                          "against": "one NCCL all-gather of the same rows", "ok": int(bad.item()) == 0}
+        if int(bad.item()) != 0:
+            if rank == 0:
+                _emit({"error": "fused peer gather differs from the NCCL all-gather", "exchange_check": exchange_check})
+            raise SystemExit(3)
+    else:
+        for i in range(n_warm):
+            step_resident(i)
+    enc = net.image_encoder.encoder()
+    if world > 1:   # ranks calibrate on their own frames; run the same mode everywhere
+        ok = torch.tensor([1 if enc.mode == 4 else 0], device=dev)
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if enc.passes == "auto":
+            enc.mode = 4 if int(ok.item()) == 1 else 2
+    mode = enc.mode
     sampler = _ClockSampler(local_rank) if rank == 0 else None
     barrier()
+    _lib.saturation_count(reset=True)
     launches0 = _lib.launch_count()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
@@ -321,6 +549,10 @@ def run_b200(args) -> None:
     launches = _lib.launch_count() - launches0
     clocks = sampler.stop() if sampler is not None else None
     value = n_gpus * FRAMES_PER_STEP * args.steps / (ms_total * 1e-3)
+    saturations = _lib.saturation_count()
+    if peer is not None:
+        peer.check()                                   # raises if any stream-side wait timed out
+        exchange_check["timed_out_ranks"] = peer.timed_out()
 
     # ---- end to end through the module API with host buffers (e2e): pinned uint8 frames ->
     # DevicePrefetcher (H2D of batch i+1 on a side stream while batch i computes) ->
@@ -351,30 +583,29 @@ def run_b200(args) -> None:
     _lib.timing_enable(False)
     kinds = _lib.timing_collect()
     peaks = _peaks()
+    passes = PRECISION[mode][2]
     total_kernel_ms = sum(k["ms"] for k in kinds.values()) or 1.0
     gemm = kinds.get("gemm_tcgen05", {"ms": 0.0, "flops": 0.0, "launches": 0, "bytes": 0.0})
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
+    traffic = _ncu_traffic()
     roofline = {
-        "kernel": "gemm_tcgen05_kernel (all dense contractions: patch-embed, QKV, out-proj, MLP, "
-                  "selector/projection, axial q|kv/out, 3x3 conv implicit GEMM)",
+        "kernel": "gemm2_tcgen05_kernel / gemm_tcgen05_kernel (all dense contractions: patch-embed, QKV, "
+                  "out-proj, MLP, selector/projection, axial q|kv/out, 3x3 conv implicit GEMM)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tf_sustained"],
         "peak_source": f"{peaks['src']} bf16 sustained (kernel timed inside a long step)",
-        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean of the four ViT-block GEMM
-        # launches (in_proj 577 MB, out_proj 424 MB, c_fc 739 MB, c_proj 1005 MB) in the ncu --set full
-        # capture profiles/r1_ncu_full_block_f16f8.json; the algorithmic figure is next to it
-        "traffic": 686e6, "traffic_unit": "bytes/launch (ncu, ViT-block GEMMs at B=256)",
+        # dram__bytes_read.sum + dram__bytes_write.sum per launch, mean over the ViT-block GEMM
+        # launches of the tracked ncu --set full capture (commit recorded next to it)
+        "traffic": traffic.get("mean_bytes_per_launch"),
+        "traffic_source": traffic.get("source"), "traffic_commit": traffic.get("commit"),
+        "traffic_per_gemm": traffic.get("per_gemm"),
         "algorithmic_bytes_per_launch": gemm["bytes"] / max(gemm["launches"], 1),
-        "passes": args.passes, "tensor_pipe_issued_tflops": args.passes * achieved,
-        "tensor_pipe_issued_frac": args.passes * achieved / peaks["tf_sustained"],
+        "passes": passes, "tensor_pipe_issued_tflops": passes * achieved,
+        "tensor_pipe_issued_frac": passes * achieved / peaks["tf_sustained"],
         "launches_per_step": gemm["launches"], "avg_launch_ms": gemm["ms"] / max(gemm["launches"], 1),
         "share_of_step_kernel_time": gemm["ms"] / total_kernel_ms,
-        "note": ("achieved counts ALGORITHMIC flops (2MNK once); every product is issued as 3 bf16 "
-                 "MMA passes (hi*hi + lo*hi + hi*lo) to meet the 1e-3 fp32 parity bar, so the tensor "
-                 "pipe executes 3x this figure") if args.passes == 3 else
-                ("achieved counts ALGORITHMIC flops (2MNK once); every product is issued as one fp16 "
-                 "MMA pass plus two e4m3 MMA passes at twice the rate (x_H w_H + x_L w_C + x_C w_L) to "
-                 "meet the 1e-3 fp32 parity bar: 2 bf16-pass equivalents of tensor-pipe time"),
+        "note": "achieved counts ALGORITHMIC flops (2MNK once) over the summed device time of the GEMM "
+                f"launches of one step; operand mode: {PRECISION[mode][1]}",
     }
     breakdown = {name: {"ms": round(k["ms"], 4), "launches": k["launches"],
                         "share": round(k["ms"] / total_kernel_ms, 4),
@@ -382,40 +613,57 @@ def run_b200(args) -> None:
                         "gbs": round(k["bytes"] / (k["ms"] * 1e-3) / 1e9, 1) if k["ms"] else 0.0}
                  for name, k in kinds.items()}
 
-    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the oracle on the host cores
-    cpu_baseline = None
+    # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the oracle on the host cores, and
+    # the product path checked against the oracle's outputs of that very leg
+    cpu_baseline, parity = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = 16
         state = _cpu_state(sample)
         _cpu_reference_step(sample, threads, state)
-        vals = [_cpu_reference_step(sample, threads, state) for _ in range(3)]
-        cpu_baseline = {"value": statistics.median(vals), "unit": UNIT, "cores": threads, "kind": "port",
+        runs = [_cpu_reference_step(sample, threads, state) for _ in range(3)]
+        cpu_baseline = {"value": statistics.median(r[0] for r in runs), "unit": UNIT, "cores": threads,
+                        "kind": "port",
                         "sample": f"oracle ViT-B/16 on {sample} frames (scaled to {FRAMES_PER_STEP}) + "
                                   f"selector/temporal/head on one {FRAMES_PER_STEP}-row unit, fp32, "
                                   "1 warm-up + median of 3"}
+        parity = _parity_in_bench(net, dev, sample, state, runs[-1][1])
 
-    torch_gpu = None
-    if rank == 0 and world == 1 and args.torch_gpu_baseline:
-        torch_gpu = _torch_gpu_baseline(dev)
+    extras = {}
+    if rank == 0 and world == 1 and not args.no_extras:
+        extras["torch_gpu_baseline"] = _torch_gpu_baseline(dev)
+        extras["features_path"] = _features_path(dev)
+        extras["vit_block"] = _vit_block(dev, mode, peaks)
+        if mode != 2:   # the fp32-faithful fallback mode of the same build, for the record
+            net2 = _build_net(cfg, dev, args.micro_batch, 2)
+            m2 = module.ncentroid
+            ms2 = _time_gpu(lambda: net2(resident[0], None, m2, 1, True), iters=5, warmup=2)
+            extras["f16f8_mode"] = {"frames_per_s": FRAMES_PER_STEP / (ms2 * 1e-3), "ms_per_step": ms2,
+                                    "what": "same step with passes=2 (fp16 + e4m3 cross terms, ~1e-5 on the "
+                                            "features): what 'auto' falls back to when calibration fails"}
+            del net2
+    if not args.no_extras:
+        extras["strong_scaling_xd"] = _strong_scaling_xd(dev, world, rank, args, barrier, max_over_ranks)
 
     if rank == 0:
-        flops_per_frame = VIT_GFLOP_PER_FRAME * 1e9 + TEMPORAL_MFLOP_PER_FRAME * 1e6
+        flops_per_frame = VIT_GFLOP_PER_FRAME * 1e9 + TEMPORAL_MFLOP_PER_FRAME[PRESET] * 1e6
         _emit({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": n_gpus, "steps": args.steps,
-            "warmup": max(args.warmup, 3), "ms_per_step": ms_total / args.steps,
+            "warmup": n_warm, "ms_per_step": ms_total / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": PRECISION[args.passes][0], "data": "synthetic",
-            "config": dict(_workload_config(n_gpus, args.micro_batch, args.passes), exchange=transport),
+            "dtype": PRECISION[mode][0], "data": "synthetic",
+            "config": _workload_config(n_gpus, args.micro_batch),
+            "precision": {"requested": args.passes, "mode": mode, "description": PRECISION[mode][1],
+                          "calibration": enc.calibration, "fp16_saturations_in_timed_region": saturations},
+            "exchange": transport, "exchange_check": exchange_check,
             "clocks": clocks,
             "e2e": {"value": e2e_value, "unit": UNIT,
                     "h2d_bytes_per_step": FRAMES_PER_STEP * 3 * 224 * 224,
                     "d2h_bytes_per_step": FRAMES_PER_STEP * width * 4 * n_gpus},
             "gpu_launches": launches,
-            "roofline": roofline, "cpu_baseline": cpu_baseline,
+            "roofline": roofline, "cpu_baseline": cpu_baseline, "parity_in_bench": parity,
             "algorithmic_tflops_whole_path": value * flops_per_frame / 1e12 / n_gpus,
-            "torch_gpu_baseline": torch_gpu,
-            "kernels": breakdown,
+            "kernels": breakdown, **extras,
         })
     if world > 1:
         dist.destroy_process_group()
@@ -439,6 +687,10 @@ def _emit(obj: dict) -> None:
     out.flush()
 
 
+def _passes_arg(v: str):
+    return "auto" if v == "auto" else int(v)
+
+
 def main() -> None:
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -446,15 +698,16 @@ def main() -> None:
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", choices=("b200", "reference"), default="b200")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extras", action="store_true",
+                    help="skip the sub-records measured outside the headline (torch GPU baseline, "
+                         "features path, ViT block, strong scaling)")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
-    ap.add_argument("--passes", type=int, choices=(2, 3), default=2,
-                    help="GEMM operand mode of the image encoder, both fp32-faithful: 3 = split-bf16 x3, "
-                         "2 = fp16 + e4m3 cross terms (two pass-equivalents)")
-    ap.add_argument("--torch-gpu-baseline", action="store_true",
-                    help="also time the reference arithmetic as stock PyTorch ops ON THE GPU (fp32 and "
-                         "TF32-allowed): the bar a hand-written path has to beat (SURVEY 8d)")
+    ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, "auto"), default="auto",
+                    help="GEMM operand mode of the image encoder: 3 = split-bf16 x3, 2 = fp16 + e4m3 cross "
+                         "terms (both ~1e-5 on the features), 4 = fp16 operands in one pass (~2.5e-4), "
+                         "auto = 4 if the calibration on this checkpoint agrees with 2 within 5e-4, else 2")
     ap.add_argument("--ncu", action="store_true",
-                    help="profiling aid: 1 warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
+                    help="profiling aid: warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()
     _quiet_stdout()
     if args.impl == "reference":

@@ -29,6 +29,12 @@
  *     pass-equivalents instead of the three bf16 passes at the same ~1e-5 end-to-end error.
  *     Activations use (e_main, e_res, e_coarse) = (4, 7, 0); a weight tensor packed with exponent
  *     ew uses (ew, 4, ew - 7) with ew chosen so that max|w| * 2^ew lies in (2^14, 2^15].
+ *   - "f16" tensors (GEMM passes = 4, out_enc = 2) are the H plane alone: a plain fp16 matrix
+ *     [rows][ld] holding fp16(v * 2^4); weights reuse the H plane of their f16f8 pack.  One MMA
+ *     pass per product, ~2.5e-4 relative on the ViT-B/16 features instead of ~1e-5: the host
+ *     selects it per checkpoint after a calibration against the f16f8 mode.
+ *   - The fp16 conversions saturate; aclip_saturation_count() reports how many threads stored a
+ *     value at or beyond the fp16 range since the last reset (0 on a healthy run).
  */
 #ifndef ACLIP_B200_H_
 #define ACLIP_B200_H_
@@ -53,6 +59,9 @@ int aclip_version(void);
 const char* aclip_last_error(void);
 /* Number of kernels this library has launched in the calling process (all streams). */
 long long aclip_launch_count(void);
+/* Threads that stored an activation beyond the fp16 range of the f16f8 / f16 encodings on the
+ * CURRENT device since the last reset (synchronises the device); reset != 0 clears the counter. */
+long long aclip_saturation_count(int reset);
 
 /* Optional device timing of every kernel this library launches (cudaEvent pairs on the launch
  * stream), grouped by kernel kind, with the ALGORITHMIC flops / bytes of the launches: bench.py
@@ -105,6 +114,8 @@ int aclip_resize_crop_u8(const uint8_t* frames_hwc, int num_frames, int H, int W
                          const int* vbounds, const int* vcoeffs, int vk, uint8_t* tmp,
                          uint8_t* out_chw, void* stream);
 
+struct AclipPeerGather;   /* defined below: fused all-gather over NVLink peer memory */
+
 typedef struct AclipGemmArgs {
   /* operands (bf16 split planes) */
   const void* a;  /* linear: [planes][M][lda]; conv3x3: [planes][S][H][W][C]            */
@@ -113,7 +124,8 @@ typedef struct AclipGemmArgs {
   int lda, ldw;   /* row pitches in elements, multiples of 8                              */
   long long a_plane_stride, w_plane_stride; /* elements between hi and lo plane          */
   int passes;     /* 3 = split-bf16 (fp32-faithful), 1 = plain bf16 (hi plane only),
-                     2 = f16f8 operands (fp32-faithful, CTA-pair kernel, N % 256 == 0)     */
+                     2 = f16f8 operands (fp32-faithful, CTA-pair kernel, N % 256 == 0),
+                     4 = fp16 operands, one pass (CTA-pair kernel, N % 256 == 0)           */
   int a_mode;     /* 0 linear, 1 conv3x3 (zero padding 1, stride 1)                      */
   int conv_c, conv_h, conv_w, conv_s; /* conv3x3: channels, grid height, width, images  */
   /* epilogue: out = act(acc + bias) + residual */
@@ -131,17 +143,24 @@ typedef struct AclipGemmArgs {
    * out_row = (m / row_group) * row_group_stride + (m % row_group) + row_offset */
   int row_group, row_group_stride, row_offset;
   int max_ctas;          /* 0 = one persistent CTA per SM */
-  int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256),
-                            4 = clusters of two CTA pairs sharing the W tile by TMA multicast */
+  int kernel;            /* 0 = auto, 1 = single-CTA tiles (128 x N), 2 = CTA-pair tiles (256 x 256) */
   float out_scale;       /* passes = 2: 2^-(e_act + e_weight) applied to the accumulator; 0 = 1 */
-  int out_enc;           /* encoding of out_split: 0 = bf16 hi/lo, 1 = f16f8 activation planes */
+  int out_enc;           /* encoding of out_split: 0 = bf16 hi/lo, 1 = f16f8 activation planes,
+                            2 = fp16 plane [*][ld_split] */
+  /* optional fused all-gather of the fp32 output (NULL = off): every row stored to out_f32 also
+   * goes to row (rank * rows_per_rank + gather_row0 + m) of every rank's gathered buffer
+   * (gather->width must equal ldc); gather_signal != 0 publishes this rank's flag when the launch
+   * has stored everything (set it on the launch that completes the rank's block). */
+  const struct AclipPeerGather* gather;
+  int gather_signal;
+  long long gather_row0;
 } AclipGemmArgs;
 
 /* tcgen05 / TMA GEMM with fused epilogue. N must be a multiple of 32, K a multiple of 8. */
 int aclip_gemm(const AclipGemmArgs* args, void* stream);
 
 /* out_enc (here and below): encoding of the split output, 0 = bf16 hi/lo planes, 1 = f16f8
- * activation planes (the A operand of a passes = 2 GEMM).
+ * activation planes (the A operand of a passes = 2 GEMM), 2 = fp16 plane (passes = 4).
  * nn.LayerNorm (mode 0, clip/model.py:174-180) or axial_attention's ChanLayerNorm (mode 1:
  * (x-mean)/(std+eps)) over rows of D fp32 values; writes fp32 and/or split-bf16 rows. */
 int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
@@ -152,7 +171,8 @@ int aclip_layernorm(const float* x, long long rows, int D, long long ldx, const 
 /* softmax(Q K^T / 8) V for B frames of L tokens, `heads` heads of 64 dims; qkv_split is the
  * split-bf16 [2][B*L][ld_in] output of the in_proj GEMM (q | k | v), out_split [2][B*L][ld_out].
  * Replaces nn.MultiheadAttention inside ResidualAttentionBlock.attention (clip/model.py:206-212).
- * kernel: 0 = default (tcgen05/TMEM kernel), 1 = warp-level mma.sync kernel, 2 = tcgen05 kernel. */
+ * out_enc = 2: qkv_split and out_split are fp16 matrices (the "f16" encoding) and every product is
+ * one MMA pass.  kernel: 0 or 2 = the tcgen05/TMEM kernel (the only one). */
 int aclip_vit_attention(const void* qkv_split, long long in_plane_stride, int ld_in, int B, int L,
                         int heads, void* out_split, long long out_plane_stride, int ld_out,
                         int kernel, int out_enc, void* stream);
@@ -179,6 +199,9 @@ typedef struct AclipVitBlock {      /* one ResidualAttentionBlock, clip/model.py
    * accumulator scale of that GEMM (4 = the activations' e_main); out_w stays bf16 hi/lo (the
    * attention output feeds out_proj in that form) and out_s is unused.  Ignored otherwise. */
   float qkv_s, out_s, fc_s, proj_s;
+  /* passes = 4 only: attn.out_proj.weight as f16f8 / fp16 planes (its fp16 plane is read) with
+   * accumulator scale out_s; NULL otherwise. */
+  const void* out_w16;
 } AclipVitBlock;
 
 typedef struct AclipVitWeights {    /* VisionTransformer, clip/model.py:233-264 */
@@ -201,11 +224,25 @@ size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
  * (>= aclip_vit_workspace_bytes(w, micro_batch) bytes, 1024-byte aligned).
  * passes = 3: split-bf16 GEMMs (fp32-faithful, the parity mode); passes = 1: plain bf16 GEMMs;
  * passes = 2: f16f8 operands (fp32-faithful at two pass-equivalents; the weights in `w` must have
- * been packed with aclip_encode_f16f8 and width / output_dim must be multiples of 256). */
+ * been packed with aclip_encode_f16f8 and width / output_dim must be multiples of 256);
+ * passes = 4: fp16 operands end to end, one pass per product (same packed weights plus out_w16). */
 int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
                       long long num_frames, int micro_batch, const float* mean3_host,
                       const float* std3_host, float* features_out, void* workspace,
                       size_t workspace_bytes, int passes, void* stream);
+/* Same, for an encoder whose frames are sharded over the ranks of one NVSwitch domain (frames of a
+ * video are independent, anomaly_clip.py:119-123): with `gather` set (rows_per_rank = num_frames,
+ * width = output_dim) the epilogue of the output projection also stores every feature row into ALL
+ * ranks' gathered buffers [world * num_frames][output_dim] over NVLink peer memory and the last
+ * micro-batch's launch raises this rank's flag -- the all-gather of the features is fused into the
+ * GEMM that produces them.  aclip_peer_wait holds the consumer's stream until every rank's rows
+ * have arrived.  gather == NULL: identical to aclip_vit_forward. */
+struct AclipPeerGather;
+int aclip_vit_forward_ex(const AclipVitWeights* w, const void* frames, int frames_are_u8,
+                         long long num_frames, int micro_batch, const float* mean3_host,
+                         const float* std3_host, float* features_out, void* workspace,
+                         size_t workspace_bytes, int passes, const struct AclipPeerGather* gather,
+                         void* stream);
 
 typedef struct AclipAxialAttnWeights { /* PreNorm(SelfAttention), one per axis per depth */
   const float *norm_g, *norm_b;       /* nn.LayerNorm(E) */
@@ -266,6 +303,9 @@ typedef struct AclipPeerGather {
 /* local_flags: [2 * world] words: arrival flags, then timeout markers (set to 1 for a rank whose
  * flag did not arrive within ~5 s; the wait never hangs the device). */
 int aclip_peer_wait(unsigned int* local_flags, int world, unsigned int epoch, void* stream);
+/* Raise this rank's flag on every peer without storing rows: a rank that has no unit in a call
+ * (fewer units than ranks) still takes part in the exchange of that epoch. */
+int aclip_peer_signal(const AclipPeerGather* gather, void* stream);
 
 /* AnomalyCLIP.forward(test_mode=True) after the image encoder (anomaly_clip.py:132-154) fused with
  * test_step's softmax(similarity) * score (anomaly_clip_module.py:473-477).

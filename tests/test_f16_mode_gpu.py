@@ -1,0 +1,182 @@
+"""The one-pass fp16 operand mode (GEMM passes = 4, out_enc = 2; csrc/split.cuh) through the C ABI:
+per operator against fp64 torch on the SAME rounded operands (so only accumulation order and the
+documented output rounding may differ), the ViT-B/16 against the oracle at the 1e-3 bar, the
+calibration that selects the mode per checkpoint, and the saturation guard."""
+import pytest
+import torch
+
+from oracle import anomalyclip_oracle as oracle
+from tests.parity import assert_parity, rel_l2
+from tests.util_weights import make_frames_u8, make_vit_weights, normalise_frames
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from anomalyclip_b200 import ops as _ops
+    return _ops
+
+
+def _rel(a, b):
+    return rel_l2(a, b)
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 256, 64), (300, 256, 768), (1000, 768, 768),
+                                   (197 * 8, 2304, 768), (129, 768, 3072), (4096, 3072, 768),
+                                   (50432, 768, 768)])
+def test_gemm_f16(ops, M, N, K):
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    ea, ew = ops.encode_f16(a), ops.encode_f16f8(w, weight=True)
+    out = ops.gemm(ea, ew, passes=4)
+    torch.cuda.synchronize()
+    wh = ew.planes()[0].double() * 2.0 ** -ew.exp          # the fp16 plane the kernel reads
+    exact = ops.decode_f16(ea) @ wh.T                       # fp16 x fp16 products are exact in fp32
+    err_rounded, err_true = _rel(out, exact), _rel(out, a.double() @ w.double().T)
+    print(f"gemm f16 M={M} N={N} K={K}: vs rounded operands {err_rounded:.3e}, vs fp64 {err_true:.3e}")
+    assert err_rounded < 2e-6      # only the fp32 accumulation differs
+    assert err_true < 6e-4         # 2^-12 relative rounding of each operand
+
+
+def test_gemm_f16_epilogues_and_fp16_output(ops):
+    torch.manual_seed(5)
+    M, N, K = 777, 768, 512
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    ea, ew = ops.encode_f16(a), ops.encode_f16f8(w, weight=True)
+    wh = ew.planes()[0].double() * 2.0 ** -ew.exp
+    pre = ops.decode_f16(ea) @ wh.T + bias.double()
+    out = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, residual=res, passes=4)
+    assert _rel(out, pre * torch.sigmoid(1.702 * pre) + res.double()) < 3e-6
+    # hidden activations leave the epilogue as the fp16 plane of the next GEMM's A operand
+    enc = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=4, want_split=True, out_enc=2)
+    f32 = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=4)
+    assert enc.dtype == torch.float16 and torch.equal(enc, ops.encode_f16(f32))
+    # fp32 + fp16 output in one launch (residual GEMMs never need it, but the epilogue supports it)
+    both = torch.empty_like(f32)
+    enc2 = torch.empty_like(enc)
+    ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=4, out_f32=both, out_split=enc2, out_enc=2)
+    assert torch.equal(both, f32) and torch.equal(enc2, enc)
+    # a fp16 A operand also feeds the f16f8 weight's other consumers unchanged: K tail / pitch
+    out_k = ops.gemm(ea, ew, passes=4, K=448)
+    assert _rel(out_k, ops.decode_f16(ea)[:, :448] @ wh[:, :448].T) < 3e-6
+
+
+def test_gemm_f16_conv3x3(ops):
+    torch.manual_seed(11)
+    S, H, W, Cin, Cout = 9, 32, 16, 256, 1024
+    x = torch.randn(S, Cin, H, W, device="cuda")
+    wt = torch.randn(Cout, Cin, 3, 3, device="cuda") * 0.02
+    b = torch.randn(Cout, device="cuda")
+    a = ops.encode_f16(x.permute(0, 2, 3, 1).reshape(S * H * W, Cin).contiguous())
+    wk = ops.encode_f16f8(wt.permute(0, 2, 3, 1).reshape(Cout, 9 * Cin).contiguous(), weight=True)
+    out = ops.gemm(a, wk, bias=b, conv=(S, H, W, Cin), passes=4)
+    xr = ops.decode_f16(a).reshape(S, H, W, Cin).permute(0, 3, 1, 2)
+    wr = (wk.planes()[0].double() * 2.0 ** -wk.exp).reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2)
+    ref = torch.nn.functional.conv2d(xr, wr, b.double(), padding=1)
+    assert _rel(out, ref.permute(0, 2, 3, 1).reshape(S * H * W, Cout)) < 3e-6
+
+
+@pytest.mark.parametrize("rows,D", [(1, 768), (197 * 3, 768), (1000, 256)])
+def test_layernorm_fp16_output(ops, rows, D):
+    torch.manual_seed(rows + D)
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    g = 1 + 0.2 * torch.randn(D, device="cuda")
+    b = 0.1 * torch.randn(D, device="cuda")
+    out, enc = ops.layernorm(x, g, b, want_f32=True, want_split=True, out_enc=2)
+    assert torch.equal(enc, ops.encode_f16(out))     # exactly the encoding of its own fp32 output
+
+
+@pytest.mark.parametrize("B,L,heads", [(1, 197, 12), (3, 197, 12), (2, 5, 2), (2, 64, 1), (1, 224, 3),
+                                        (4, 17, 2), (2, 130, 4), (40, 197, 12), (297, 197, 12)])
+def test_vit_attention_fp16(ops, B, L, heads):
+    torch.manual_seed(B * 1000 + L)
+    W = heads * 64
+    qkv = ops.encode_f16(torch.randn(B * L, 3 * W, device="cuda") * 1.5)
+    out = ops.decode_f16(ops.vit_attention(qkv, B, L, heads, out_enc=2))
+    x = ops.decode_f16(qkv).reshape(B, L, 3, heads, 64)
+    q, k, v = (x[:, :, i].transpose(1, 2) for i in range(3))
+    p = torch.softmax(q @ k.transpose(-1, -2) / 8.0, dim=-1)
+    ref = (p @ v).transpose(1, 2).reshape(B * L, W)
+    # P and the output are rounded to fp16 (2^-12 relative each)
+    assert_parity(out, ref, f"fp16 vit attention B={B} L={L} h={heads}", rtol=5e-4)
+
+
+def _encoder(sd, heads=None, micro_batch=256, passes=4):
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    return VitEncoder(PackedVit(sd, torch.device("cuda"), heads=heads, passes=passes), micro_batch, passes)
+
+
+@pytest.fixture(scope="module")
+def vitb16():
+    return make_vit_weights()
+
+
+def test_vit_b16_f16_mode_meets_the_parity_bar(vitb16):
+    sd = vitb16
+    enc4 = _encoder(sd, passes=4)
+    torch.manual_seed(5)
+    frames = torch.randn(3, 3, 224, 224)
+    ref = oracle.vit_forward(sd, frames)
+    e4 = assert_parity(enc4(frames.cuda()), ref, "ViT-B/16 features, fp16 operands (one pass)")
+    from anomalyclip_b200.engine import VitEncoder
+    e2 = rel_l2(VitEncoder(enc4.packed, passes=2)(frames.cuda()), ref)
+    print(f"rel-L2 vs oracle: f16 {e4:.3e}, f16f8 {e2:.3e}")
+    assert e4 < 5e-4 and e2 < 1e-4
+    u8 = make_frames_u8(5, seed=3)
+    assert_parity(enc4(u8.cuda()), oracle.vit_forward(sd, normalise_frames(u8)),
+                  "ViT-B/16 features from uint8 frames, fp16 operands")
+    # micro-batching does not change a bit
+    assert torch.equal(enc4(u8.cuda()), VitEncoder(enc4.packed, micro_batch=2, passes=4)(u8.cuda()))
+
+
+def test_auto_mode_calibrates_per_checkpoint(vitb16):
+    """passes="auto": the one-pass mode is taken on a well-conditioned checkpoint; on weights whose
+    LayerNorm gains / projections carry 20x outlier channels (the network amplifies operand rounding
+    ~9x, scripts/numerics_passes.py) the calibration falls back to f16f8 and the features stay
+    fp32-faithful."""
+    from anomalyclip_b200 import _lib
+    sd = vitb16
+    u8 = make_frames_u8(20, seed=4).cuda()
+    enc = _encoder(sd, passes="auto")
+    out = enc(u8)
+    print("calibration (synthetic CLIP-style init):", enc.calibration)
+    assert enc.mode == 4 and enc.calibration["rel_l2_f16_vs_f16f8"] < 5e-4
+    assert torch.equal(out, _encoder(sd, passes=4)(u8))
+    assert _lib.saturation_count() == 0
+
+    bad = {k: v.clone() for k, v in sd.items()}
+    for k, v in bad.items():
+        if k.endswith("ln_1.weight") or k.endswith("ln_2.weight"):
+            v[::97] *= 20
+        if k.endswith("c_fc.weight") or k.endswith("in_proj_weight"):
+            v[::131, ::53] *= 20
+    enc_bad = _encoder(bad, passes="auto")
+    out_bad = enc_bad(u8)
+    print("calibration (20x outlier channels):", enc_bad.calibration)
+    assert enc_bad.mode == 2, "the calibration must reject the one-pass mode on this checkpoint"
+    ref = oracle.vit_forward(bad, normalise_frames(u8[:3].cpu()))
+    e = assert_parity(out_bad[:3], ref, "outlier-channel ViT-B/16, auto -> f16f8")
+    assert e < 3e-4
+
+
+def test_saturation_is_counted_not_silent():
+    """Activations beyond the fp16 range of the encodings are clamped by cvt.satfinite; the counter
+    reports it and an "auto" encoder refuses such a checkpoint instead of returning wrong features."""
+    from anomalyclip_b200 import _lib
+    from anomalyclip_b200._lib import AclipError
+    sd = make_vit_weights(width=256, layers=1, patch=16, resolution=32, output_dim=256, seed=7)
+    frames = torch.randn(4, 3, 32, 32, device="cuda")
+    _lib.saturation_count(reset=True)
+    _encoder(sd, passes=4)(frames)
+    assert _lib.saturation_count() == 0
+    _encoder(sd, passes=4)(frames * 1e4)           # patch values ~1e4 >= 4094: saturate in patchify
+    assert _lib.saturation_count(reset=True) > 0
+    assert _lib.saturation_count() == 0
+    with pytest.raises(AclipError):
+        _encoder(sd, passes="auto")(frames * 1e4)
+    _lib.saturation_count(reset=True)

@@ -193,3 +193,39 @@ def test_mirror_net_on_raw_frames_matches_oracle():
     assert_parity(sc, sc_ref, "mirror net, raw frames: scores")
     probs_ref, _ = oracle.test_step_postprocess(sim_ref, sc_ref)
     assert torch.equal(net.class_probs.argmax(1).cpu(), probs_ref.argmax(1))
+
+
+def test_compute_ncentroid_runs_the_encoder_over_the_normal_set():
+    """SURVEY 8f3 at world size 1: `compute_ncentroid` streams the (test-mode) normal videos through
+    the image encoder, keeps the real frames only and averages -- against the oracle ViT's mean
+    feature (anomaly_clip_module.py:419-441).  The 2-rank NCCL version is in nccl_worker.py."""
+    import anomalyclip_b200.models as models
+    from anomalyclip_b200.models import AnomalyCLIP
+    from anomalyclip_b200.module import AnomalyCLIPModule
+    from tests.util_weights import make_vit_weights, normalise_frames
+    cfg = PRESETS["xdviolence"]
+    models.ARCHS["test-tiny"] = dict(resolution=32, patch=16, width=256, layers=2, embed_dim=512,
+                                     text_width=512, text_layers=1, text_heads=8, context_length=77,
+                                     vocab_size=64)
+    net = AnomalyCLIP(arch="test-tiny", classnames=[f"c{i}" for i in range(cfg.num_classes)],
+                      emb_size=cfg.emb_size, depth=cfg.depth, heads=cfg.heads, dim_heads=None,
+                      num_segments=cfg.num_segments, seg_length=cfg.seg_length,
+                      concat_features=cfg.concat_features, normal_id=cfg.normal_id, stride=1,
+                      load_from_features=False, ncrops=1, build_text_tower=False, passes=2)
+    vit = make_vit_weights(width=256, layers=2, patch=16, resolution=32, output_dim=512, seed=11)
+    sd = make_state_dict(cfg, with_vit=False)
+    sd.update({"image_encoder." + k: v for k, v in vit.items()})
+    missing, unexpected = net.load_state_dict(sd, strict=False)
+    assert not missing and not unexpected
+    net.cuda().eval()
+    module = AnomalyCLIPModule(net, num_classes=cfg.num_classes)
+    vids, real = [], []
+    for v in range(3):
+        g = torch.Generator().manual_seed(40 + v)
+        n_real = 300 + 37 * v
+        x = torch.randint(0, 256, (1, cfg.unit, 3, 32, 32), dtype=torch.uint8, generator=g)
+        vids.append((x, torch.zeros(1, n_real, dtype=torch.long)))
+        real.append(x[0, :n_real])
+    got = module.compute_ncentroid(vids, load_from_features=False)
+    ref = oracle.vit_forward(vit, normalise_frames(torch.cat(real))).double().mean(0).float()
+    assert_parity(got, ref, "ncentroid over the normal set (frames path)", rtol=1e-4)

@@ -39,7 +39,7 @@ def test_layernorm(ops, rows, D, chan):
 
 @pytest.mark.parametrize("B,L,heads", [(1, 197, 12), (3, 197, 12), (2, 5, 2), (2, 64, 1), (1, 224, 3),
                                         (4, 17, 2), (2, 130, 4), (40, 197, 12)])
-@pytest.mark.parametrize("kernel", [2, 1])
+@pytest.mark.parametrize("kernel", [2])
 def test_vit_attention(ops, B, L, heads, kernel):
     torch.manual_seed(B * 1000 + L)
     W = heads * 64
