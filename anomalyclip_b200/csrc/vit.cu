@@ -9,7 +9,10 @@
 //
 // The residual stream X stays fp32; GEMM operands travel in the encoding of the requested mode
 // (gemm.cuh / split.cuh): passes = 3 split-bf16, 2 f16f8 (out_proj and the attention stay
-// split-bf16), 4 fp16 planes end to end (every GEMM and the attention in one pass).  No allocation,
+// split-bf16), 4 fp16 planes end to end (every GEMM and the attention in one pass), 5 "mixed":
+// the attention side of a block (in_proj, attention, out_proj: a third of its flops, a tenth of its
+// error sensitivity -- scripts/numerics_passes.py) on fp16 operands, the MLP pair, the patch
+// embedding and the output projection on f16f8 operands.  No allocation,
 // no synchronisation: everything is enqueued on the caller's stream into the caller's workspace.
 #include "common.h"
 
@@ -49,7 +52,7 @@ VitPlan plan_vit(const AclipVitWeights& w, int mb) {
 AclipGemmArgs linear(const void* a, long long a_plane, int M, int K, int lda, const void* w, int N,
                      int passes, float w_scale = 0.0f) {
   AclipGemmArgs g{};
-  g.out_scale = (passes == 2 || passes == 4) ? w_scale : 0.0f;
+  g.out_scale = (passes == 2 || passes == 4) ? w_scale : 0.0f;   // fp16-based operands: 2^-(4 + e_w)
   g.a = a; g.w = w;
   g.M = M; g.N = N; g.K = K;
   g.lda = lda; g.ldw = K;
@@ -102,13 +105,18 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
   ACLIP_TRY(check_weights(w));
   ACLIP_REQUIRE(frames != nullptr && features_out != nullptr, "vit_forward: null frames/output");
   ACLIP_REQUIRE(num_frames >= 0 && micro_batch > 0, "vit_forward: bad frame count / micro-batch");
-  ACLIP_REQUIRE(passes >= 1 && passes <= 4, "vit_forward: passes must be 1, 2, 3 or 4");
-  ACLIP_REQUIRE((passes != 2 && passes != 4) || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
-                                                 (3 * w.patch * w.patch) % 16 == 0),
+  ACLIP_REQUIRE(passes >= 1 && passes <= 5, "vit_forward: passes must be 1 .. 5");
+  ACLIP_REQUIRE(passes == 1 || passes == 3 || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
+                                               (3 * w.patch * w.patch) % 16 == 0),
                 "vit_forward: passes=%d (fp16-based operands) needs width and output_dim multiples of 256",
                 passes);
-  const bool f16 = passes == 4;
-  const int enc = f16 ? 2 : passes == 2 ? 1 : 0;  // encoding of every GEMM A operand on this path
+  // operand mode of the attention side (in_proj, attention, out_proj) and of everything else
+  const int p_att = passes == 5 ? 4 : passes;
+  const int p_mlp = passes == 5 ? 2 : passes;
+  const bool f16 = p_att == 4;                       // fp16 q | k | v, one-pass attention and out_proj
+  const int enc_att = f16 ? 2 : p_att == 2 ? 1 : 0;  // encoding of ln_1's output (in_proj's A operand)
+  const int enc = p_mlp == 4 ? 2 : p_mlp == 2 ? 1 : 0;  // encoding of the other GEMM A operands
+  passes = p_mlp;
   ACLIP_REQUIRE(gather == nullptr || (gather->width == w.output_dim && num_frames == gather->rows_per_rank),
                 "vit_forward: the feature gather must be built for %lld rows of %d values", num_frames,
                 w.output_dim);
@@ -156,9 +164,9 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
                         (f16 ? b.out_w16 != nullptr : b.out_w != nullptr) &&
                         b.out_b && b.fc_w && b.fc_b && b.proj_w && b.proj_b,
                     "vit_forward: block %d has a null weight", l);
-      ACLIP_TRY(layernorm(X, M, W, W, b.ln1_g, b.ln1_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc, stream));
+      ACLIP_TRY(layernorm(X, M, W, W, b.ln1_g, b.ln1_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc_att, stream));
       {
-        AclipGemmArgs g = linear(H, hp, M, W, W, b.qkv_w, 3 * W, passes, b.qkv_s);
+        AclipGemmArgs g = linear(H, hp, M, W, W, b.qkv_w, 3 * W, p_att, b.qkv_s);
         g.bias = b.qkv_b;
         g.out_split = BIG; g.split_plane_stride = bp; g.ld_split = 3 * W;
         g.out_enc = f16 ? 2 : 0;
@@ -171,7 +179,7 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
       ACLIP_TRY(vit_attention(BIG, bp, 3 * W, Bm, T, w.heads, H, hp, W, 0, f16 ? 2 : 0, stream));
       {
         AclipGemmArgs g = f16 ? linear(H, hp, M, W, W, b.out_w16, W, 4, b.out_s)
-                              : linear(H, hp, M, W, W, b.out_w, W, passes == 2 ? 3 : passes);
+                              : linear(H, hp, M, W, W, b.out_w, W, p_att == 2 ? 3 : p_att);
         g.bias = b.out_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;

@@ -94,6 +94,19 @@ def sharded_mean(local_sum: torch.Tensor, local_count: int,
     return (packed[:-1] / packed[-1].clamp_min(1.0)).to(torch.float32).reshape(local_sum.shape)
 
 
+_MODE_SPEED = {4: 2, 5: 1, 2: 0}     # operand modes of the image encoder, fastest = highest
+
+
+def agree_on_mode(mode: int, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> int:
+    """Ranks calibrate an "auto" encoder on their own frames; everybody then runs the most
+    conservative of the chosen modes (one tiny all-reduce)."""
+    if not (dist.is_available() and dist.is_initialized()) or mode not in _MODE_SPEED:
+        return mode
+    t = torch.tensor([_MODE_SPEED[mode]], device=device)
+    dist.all_reduce(t, op=dist.ReduceOp.MIN, group=group)
+    return {v: k for k, v in _MODE_SPEED.items()}[int(t.item())]
+
+
 class PeerRowGather:
     """Fused all-gather of the per-frame result rows over NVLink peer memory.
 
@@ -257,9 +270,7 @@ class FrameShardedScorer:
         if encoder.mode is not None:
             return
         encoder.calibrate(local_frames.contiguous())
-        ok = torch.tensor([1 if encoder.mode == 4 else 0], device=self.device)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN, group=self._group)
-        encoder.mode = 4 if int(ok.item()) == 1 else 2
+        encoder.mode = agree_on_mode(encoder.mode, self.device, self._group)
         encoder.calibration["mode"] = encoder.mode
         encoder.calibration["agreed_over_ranks"] = self.world
 

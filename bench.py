@@ -55,8 +55,14 @@ PRECISION = {
         "tensor time), fp32 accumulate; attention and out_proj: split-bf16 x3", 2.0),
     4: ("f16 operands (one pass), f32 accumulate/residual/LayerNorm/softmax",
         "fp16 operands in one tensor-core pass for every ViT GEMM and the attention, fp32 accumulate, "
-        "fp32 residual stream / LayerNorm statistics / softmax; selected per checkpoint by calibration "
-        "against the f16f8 mode (features within 5e-4, no fp16 saturation)", 1.0),
+        "fp32 residual stream / LayerNorm statistics / softmax", 1.0),
+    5: ("f16 operands (attention side, one pass) + f16/e4m3 cross-term operands (MLP side, 2 pass-equivalents), "
+        "f32 accumulate/residual/LayerNorm/softmax",
+        "mixed: in_proj / attention / out_proj on fp16 operands in one pass, c_fc / c_proj / patch-embed / "
+        "proj as fp16 main product + two e4m3 cross-term products (the MLP GEMMs carry 8x the error "
+        "variance of the attention side); 1.64 bf16-pass equivalents per product on average; selected "
+        "per checkpoint by calibration against the f16f8 mode (features within 3e-4, no fp16 saturation)",
+        (1048 * 1.0 + 1860 * 2.0) / 2908),
 }
 
 
@@ -529,11 +535,9 @@ def run_b200(args) -> None:
         for i in range(n_warm):
             step_resident(i)
     enc = net.image_encoder.encoder()
-    if world > 1:   # ranks calibrate on their own frames; run the same mode everywhere
-        ok = torch.tensor([1 if enc.mode == 4 else 0], device=dev)
-        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
-        if enc.passes == "auto":
-            enc.mode = 4 if int(ok.item()) == 1 else 2
+    if world > 1 and enc.passes == "auto":   # ranks calibrate on their own frames; run one mode everywhere
+        from anomalyclip_b200.distributed import agree_on_mode
+        enc.mode = agree_on_mode(enc.mode, dev)
     mode = enc.mode
     sampler = _ClockSampler(local_rank) if rank == 0 else None
     barrier()
@@ -615,7 +619,7 @@ def run_b200(args) -> None:
 
     # ---- CPU baseline (rank 0, N = 1 only): bounded sample of the oracle on the host cores, and
     # the product path checked against the oracle's outputs of that very leg
-    cpu_baseline, parity = None, None
+    cpu_baseline, parity, oracle_vit = None, None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         threads = os.cpu_count() or 1
         sample = 16
@@ -628,20 +632,30 @@ def run_b200(args) -> None:
                                   f"selector/temporal/head on one {FRAMES_PER_STEP}-row unit, fp32, "
                                   "1 warm-up + median of 3"}
         parity = _parity_in_bench(net, dev, sample, state, runs[-1][1])
+        oracle_vit = runs[-1][1][0]
 
     extras = {}
     if rank == 0 and world == 1 and not args.no_extras:
         extras["torch_gpu_baseline"] = _torch_gpu_baseline(dev)
         extras["features_path"] = _features_path(dev)
         extras["vit_block"] = _vit_block(dev, mode, peaks)
-        if mode != 2:   # the fp32-faithful fallback mode of the same build, for the record
-            net2 = _build_net(cfg, dev, args.micro_batch, 2)
-            m2 = module.ncentroid
-            ms2 = _time_gpu(lambda: net2(resident[0], None, m2, 1, True), iters=5, warmup=2)
-            extras["f16f8_mode"] = {"frames_per_s": FRAMES_PER_STEP / (ms2 * 1e-3), "ms_per_step": ms2,
-                                    "what": "same step with passes=2 (fp16 + e4m3 cross terms, ~1e-5 on the "
-                                            "features): what 'auto' falls back to when calibration fails"}
-            del net2
+        # every operand mode of the same build on the same step, with its own parity figure against
+        # the oracle features of the cpu_baseline leg (the headline above ran mode `mode`)
+        modes = {}
+        for m_ in (2, 5, 4):
+            net_m = net if m_ == mode else _build_net(cfg, dev, args.micro_batch, m_)
+            ms_m = _time_gpu(lambda: net_m(resident[0], None, module.ncentroid, 1, True), iters=5, warmup=2)
+            rec = {"frames_per_s": FRAMES_PER_STEP / (ms_m * 1e-3), "ms_per_step": ms_m,
+                   "pass_equivalents": PRECISION[m_][2]}
+            if parity is not None:
+                u8 = syn.make_frames_u8(16, seed=0).to(dev)
+                rec["vit_features_rel_l2_vs_oracle"] = _rel(net_m.image_encoder(u8), oracle_vit)
+            modes[str(m_)] = rec
+            if net_m is not net:
+                del net_m
+        extras["operand_modes"] = {"what": "the same 512-frame step in each operand mode of the image encoder "
+                                           "(2 = f16f8, 5 = mixed, 4 = fp16 one pass); 5 timed calls each",
+                                   "selected": mode, **modes}
     if not args.no_extras:
         extras["strong_scaling_xd"] = _strong_scaling_xd(dev, world, rank, args, barrier, max_over_ranks)
 
@@ -702,10 +716,11 @@ def main() -> None:
                     help="skip the sub-records measured outside the headline (torch GPU baseline, "
                          "features path, ViT block, strong scaling)")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
-    ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, "auto"), default="auto",
+    ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, 5, "auto"), default="auto",
                     help="GEMM operand mode of the image encoder: 3 = split-bf16 x3, 2 = fp16 + e4m3 cross "
-                         "terms (both ~1e-5 on the features), 4 = fp16 operands in one pass (~2.5e-4), "
-                         "auto = 4 if the calibration on this checkpoint agrees with 2 within 5e-4, else 2")
+                         "terms (both ~1e-5 on the features), 4 = fp16 operands in one pass (~4e-4), 5 = mixed "
+                         "(attention side as 4, MLP side as 2, ~1e-4), auto = the fastest of 4, 5 whose "
+                         "calibration on this checkpoint agrees with 2 within 3e-4, else 2")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()

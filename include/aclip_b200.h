@@ -225,7 +225,9 @@ size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
  * passes = 3: split-bf16 GEMMs (fp32-faithful, the parity mode); passes = 1: plain bf16 GEMMs;
  * passes = 2: f16f8 operands (fp32-faithful at two pass-equivalents; the weights in `w` must have
  * been packed with aclip_encode_f16f8 and width / output_dim must be multiples of 256);
- * passes = 4: fp16 operands end to end, one pass per product (same packed weights plus out_w16). */
+ * passes = 4: fp16 operands end to end, one pass per product (same packed weights plus out_w16);
+ * passes = 5: "mixed" -- in_proj, attention and out_proj as passes = 4, the MLP pair, the patch
+ * embedding and the output projection as passes = 2 (~1e-4 on the features). */
 int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
                       long long num_frames, int micro_batch, const float* mean3_host,
                       const float* std3_host, float* features_out, void* workspace,

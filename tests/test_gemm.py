@@ -256,27 +256,6 @@ def test_gemm_f16f8_epilogue_and_encoded_output(ops):
     assert _rel(_unsplit(s), pre) < 3e-5
 
 
-@pytest.mark.parametrize("M,N,K", [(512, 256, 64), (300, 256, 768), (1000, 768, 768),
-                                   (197 * 8, 2304, 768), (257, 768, 3072), (50432, 768, 768)])
-@pytest.mark.parametrize("passes", [3, 2])
-def test_gemm_four_cta_kernel_is_bit_identical_to_the_pair_kernel(ops, M, N, K, passes):
-    """kernel=4: clusters of two CTA pairs share the W tile by TMA multicast (odd tile counts leave a
-    phantom M tile in the last cluster); same MMA order per tile, so the results are identical."""
-    torch.manual_seed(M + N + K)
-    a = torch.randn(M, K, device="cuda")
-    w = torch.randn(N, K, device="cuda") * 0.05
-    bias = torch.randn(N, device="cuda")
-    if passes == 2:
-        ea, ew = ops.encode_f16f8(a), ops.encode_f16f8(w, weight=True)
-    else:
-        ea, ew = ops.split(a), ops.split(w)
-    ref = ops.gemm(ea, ew, bias=bias, passes=passes, kernel=2)
-    out = ops.gemm(ea, ew, bias=bias, passes=passes, kernel=4)
-    torch.cuda.synchronize()
-    assert torch.equal(out, ref)
-    assert _rel(out, a.double() @ w.double().T + bias.double()) < 3e-5
-
-
 @pytest.mark.parametrize("S,Cin,Cout", [(1, 64, 256), (3, 256, 1024), (2, 1024, 256), (9, 256, 256)])
 def test_conv3x3_implicit_gemm_f16f8(ops, S, Cin, Cout):
     """The 3x3 "same" convolution over an f16f8 NHWC grid (5-D TMA maps for the fp16 plane and for
