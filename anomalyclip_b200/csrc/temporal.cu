@@ -184,9 +184,10 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
                 sub_videos, segment_size);
   ACLIP_REQUIRE(passes >= 1 && passes <= 3, "temporal_forward: passes must be 1, 2 or 3");
   if (sub_videos == 0) return ACLIP_OK;
+  // a rank may contribute fewer rows than its block holds (uneven unit counts over the ranks)
   ACLIP_REQUIRE(gather == nullptr ||
-                    gather->rows_per_rank == sub_videos * w.num_segments * w.seg_length,
-                "temporal_forward: peer gather expects %lld rows per rank",
+                    gather->rows_per_rank >= sub_videos * w.num_segments * w.seg_length,
+                "temporal_forward: peer gather holds %lld rows per rank, fewer than this call's",
                 gather ? gather->rows_per_rank : 0ll);
   ACLIP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) == 0,
                 "temporal_forward: workspace must be 1024-byte aligned");
