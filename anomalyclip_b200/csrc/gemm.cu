@@ -96,8 +96,9 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   timing_begin(KIND_GEMM, stream);
   kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
   {
-    const double planes = PASSES == 1 ? 1.0 : 2.0;
-    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);
+    const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : 2.0;
+    const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? (p.out_enc == 2 ? 2.0 : 4.0) : 0.0) +
+                         (p.residual ? 4.0 : 0.0);
     // algorithmic: 2MNK flops (one product per term, whatever the number of passes); bytes = each
     // operand once + outputs (+ residual) once; the conv mode reads each activation once, not 9x
     const double a_elems = p.a_mode == 1 ? (double)p.M * (p.K / 9) : (double)p.M * p.K;
@@ -150,9 +151,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                 "gemm: out_enc must be 0 (bf16 hi/lo), 1 (f16f8) or 2 (fp16 plane)");
   if (g.passes == 4) {
     // fp16 operands, one pass: A is an fp16 matrix [M][lda] (or NHWC grid), W the fp16 plane of a
-    // weight packed with aclip_encode_f16f8; CTA-pair kernel only
-    ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1,
-                  "gemm: passes=4 (fp16 operands) runs on the CTA-pair kernel: N %% 256 == 0 (N=%d)", g.N);
+    // weight packed with aclip_encode_f16f8
     ACLIP_REQUIRE(g.out_scale > 0.0f, "gemm: passes=4 needs out_scale = 2^-(e_act + e_weight)");
   }
   if (g.passes == 2) {
@@ -193,7 +192,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2,
                 "gemm: kernel must be 0 (auto), 1 (single CTA) or 2 (CTA pair)");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
-  const bool pair = g.kernel == 2 || g.passes == 2 || g.passes == 4 ||
+  const bool pair = g.kernel == 2 || g.passes == 2 ||
                     (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
@@ -351,15 +350,14 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     return g.passes == 3   ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
            : g.passes == 4 ? launch_pair<4>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
                            : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
-  if (block_n == 256) {
-    return g.passes == 3 ? launch<256, 3>(tmA, tmB, p, g.max_ctas, stream)
-                         : launch<256, 1>(tmA, tmB, p, g.max_ctas, stream);
-  }
-  if (block_n == 128)
-    return g.passes == 3 ? launch<128, 3>(tmA, tmB, p, g.max_ctas, stream)
-                         : launch<128, 1>(tmA, tmB, p, g.max_ctas, stream);
-  return g.passes == 3 ? launch<64, 3>(tmA, tmB, p, g.max_ctas, stream)
-                       : launch<64, 1>(tmA, tmB, p, g.max_ctas, stream);
+#define ACLIP_LAUNCH_SINGLE(BN)                                                          \
+  return g.passes == 3   ? launch<BN, 3>(tmA, tmB, p, g.max_ctas, stream)                \
+         : g.passes == 4 ? launch<BN, 4>(tmA, tmB, p, g.max_ctas, stream)                \
+                         : launch<BN, 1>(tmA, tmB, p, g.max_ctas, stream)
+  if (block_n == 256) { ACLIP_LAUNCH_SINGLE(256); }
+  if (block_n == 128) { ACLIP_LAUNCH_SINGLE(128); }
+  ACLIP_LAUNCH_SINGLE(64);
+#undef ACLIP_LAUNCH_SINGLE
 }
 
 }  // namespace aclip

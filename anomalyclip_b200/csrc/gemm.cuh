@@ -11,7 +11,7 @@
 //                (K = 16) per K step plus two kind::f8f6f4 MMAs (K = 32, twice the rate) for the
 //                cross terms: two bf16-pass equivalents, ~2^-16 as well (CTA-pair kernels only)
 //   PASSES == 1  plain bf16 (hi plane only)
-//   PASSES == 4  "f16": the fp16 main plane only, one kind::f16 MMA per K step (CTA-pair kernel);
+//   PASSES == 4  "f16": the fp16 main plane only, one kind::f16 MMA per K step (both kernels);
 //                ~2^-12 relative per product, selected by the host after calibration (split.cuh)
 //
 // Two kernels share the producer / issuer / epilogue code:
@@ -88,7 +88,7 @@ struct GemmCfg {
   static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
   static constexpr int UMMA_K = 16;
   static constexpr int PASSES = PASSES_;
-  static constexpr int PLANES = PASSES_ == 1 ? 1 : 2;
+  static constexpr int PLANES = (PASSES_ == 1 || PASSES_ == 4) ? 1 : 2;
   static constexpr int A_PLANE_BYTES = BLOCK_M * 128;
   static constexpr int B_PLANE_BYTES = BLOCK_N * 128;
   static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
@@ -353,7 +353,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
     if (lane == 0) {
-      constexpr uint32_t idesc = ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, BLOCK_N);
+      constexpr uint32_t idesc = PASSES == 4 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, BLOCK_N)   // fp16
+                                             : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, BLOCK_N);
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {

@@ -88,9 +88,12 @@ int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, v
   const int n = w.num_segments, l = w.seg_length, E = w.emb;
   const long long rows = cs * n * l;
   // passes = 2: f16f8 operands for the conv GEMMs when the CTA-pair kernel applies (N = 4E and E
-  // multiples of 256, enough rows to fill it); every other GEMM of this stage runs three passes
+  // multiples of 256, enough rows to fill it); passes = 4: fp16 operands in ONE pass for the conv
+  // GEMMs (94 % of this stage's flops; ~9e-5 on the scores, which scale every class alike and so
+  // cannot change a class index) at any chunk size; every other GEMM of this stage runs three passes
   const bool want8 = passes == 2 && E % 256 == 0 && rows >= 4096;
-  if (passes == 2) passes = 3;
+  const bool want16 = passes == 4 && E % 256 == 0;
+  if (passes == 2 || passes == 4) passes = 3;
   const float* x1 = P;  // both reversible streams start as the same tensor
   for (int d = 0; d < w.depth; ++d) {
     for (int axis = 0; axis < 2; ++axis) {  // y1 = x1 + Attn_n(LN(x2)); y2 = x2 + Attn_l(LN(y1))
@@ -120,20 +123,24 @@ int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, v
                     "temporal_forward: feed-forward %d/%d has a null weight", d, fg);
       const float* src = fg == 0 ? P : A1;
       float* dst = fg == 0 ? A1 : P;
-      const bool ff8 = want8 && c.conv1_w8 != nullptr && c.conv2_w8 != nullptr;
-      ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, ff8 ? 1 : 0, stream));
+      const bool have8 = c.conv1_w8 != nullptr && c.conv2_w8 != nullptr;
+      const bool ff16 = want16 && have8;             // fp16 planes (of the f16f8 weight pack), one pass
+      const bool ff8 = (want8 && have8) || ff16;     // fp16-based operands: accumulator scale applies
+      const int ff_passes = ff16 ? 4 : ff8 ? 2 : passes;
+      const int ff_enc = ff16 ? 2 : ff8 ? 1 : 0;
+      ACLIP_TRY(layernorm(src, rows, E, E, c.g, c.b, 1e-5f, 1, nullptr, 0, H, E, hp, ff_enc, stream));
       {
-        AclipGemmArgs g = linear(H, hp, rows, 9 * E, E, ff8 ? c.conv1_w8 : c.conv1_w, 4 * E, ff8 ? 2 : passes);
+        AclipGemmArgs g = linear(H, hp, rows, 9 * E, E, ff8 ? c.conv1_w8 : c.conv1_w, 4 * E, ff_passes);
         g.a_mode = 1; g.conv_c = E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
         g.bias = c.conv1_b;
         g.act = ACLIP_ACT_LEAKYRELU;
         g.out_split = MID; g.split_plane_stride = mp; g.ld_split = 4 * E;
         g.out_scale = ff8 ? c.conv1_s : 0.0f;
-        g.out_enc = ff8 ? 1 : 0;
+        g.out_enc = ff_enc;
         ACLIP_TRY(gemm(g, stream));
       }
       {
-        AclipGemmArgs g = linear(MID, mp, rows, 36 * E, 4 * E, ff8 ? c.conv2_w8 : c.conv2_w, E, ff8 ? 2 : passes);
+        AclipGemmArgs g = linear(MID, mp, rows, 36 * E, 4 * E, ff8 ? c.conv2_w8 : c.conv2_w, E, ff_passes);
         g.out_scale = ff8 ? c.conv2_s : 0.0f;
         g.a_mode = 1; g.conv_c = 4 * E; g.conv_h = n; g.conv_w = l; g.conv_s = static_cast<int>(cs);
         g.bias = c.conv2_b;
@@ -182,7 +189,7 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
   ACLIP_REQUIRE(sub_videos >= 0 && segment_size >= 1 && sub_videos % segment_size == 0,
                 "temporal_forward: sub_videos=%lld must be a multiple of segment_size=%d",
                 sub_videos, segment_size);
-  ACLIP_REQUIRE(passes >= 1 && passes <= 3, "temporal_forward: passes must be 1, 2 or 3");
+  ACLIP_REQUIRE(passes >= 1 && passes <= 4, "temporal_forward: passes must be 1, 2, 3 or 4");
   if (sub_videos == 0) return ACLIP_OK;
   // a rank may contribute fewer rows than its block holds (uneven unit counts over the ranks)
   ACLIP_REQUIRE(gather == nullptr ||
@@ -219,6 +226,7 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
   const long long fp = static_cast<long long>(pl.f_plane), hp = static_cast<long long>(pl.h_plane);
   const long long mp = static_cast<long long>(pl.mid_plane);
 
+  const int lin_passes = (passes == 2 || passes == 4) ? 3 : passes;  // selector / projection: split-bf16
   for (long long u0 = 0; u0 < sub_videos; u0 += chunk) {
     const long long cs = sub_videos - u0 < chunk ? sub_videos - u0 : chunk;
     const long long rows = cs * unit;
@@ -226,7 +234,7 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
 
     ACLIP_TRY(center_regroup(features, rows, D, w.ncentroid, map, F, w.ldf, fp, stream));
     {  // similarity = BatchNorm_eval((x - m) @ directions^T)
-      AclipGemmArgs g = linear(F, fp, rows, D, w.ldf, w.selector_w, 32, passes == 2 ? 3 : passes);
+      AclipGemmArgs g = linear(F, fp, rows, D, w.ldf, w.selector_w, 32, lin_passes);
       g.bias = w.selector_b;
       g.out_f32 = SIM; g.ldc = 32;
       if (w.concat) {  // similarity columns follow the centred features in the packed rows
@@ -237,7 +245,7 @@ extern "C" int aclip_temporal_forward_ex(const AclipTemporalWeights* wp, const f
       ACLIP_TRY(gemm(g, stream));
     }
     {  // projection + axial positional embedding
-      AclipGemmArgs g = linear(F, fp, rows, w.ldf, w.ldf, w.proj_w, E, passes == 2 ? 3 : passes);
+      AclipGemmArgs g = linear(F, fp, rows, w.ldf, w.ldf, w.proj_w, E, lin_passes);
       g.bias = w.proj_b;
       g.residual = w.pos; g.res_mod = static_cast<int>(unit); g.ldr = E;
       g.out_f32 = P; g.ldc = E;
@@ -265,7 +273,7 @@ extern "C" int aclip_temporal_core_forward(const AclipTemporalWeights* wp, float
                 "temporal_core_forward: unsupported configuration or null weight");
   ACLIP_REQUIRE(sub_videos >= 0 && segment_size >= 1 && sub_videos % segment_size == 0,
                 "temporal_core_forward: sub_videos must be a multiple of segment_size");
-  ACLIP_REQUIRE(passes >= 1 && passes <= 3, "temporal_core_forward: passes must be 1, 2 or 3");
+  ACLIP_REQUIRE(passes >= 1 && passes <= 4, "temporal_core_forward: passes must be 1, 2, 3 or 4");
   if (sub_videos == 0) return ACLIP_OK;
   ACLIP_REQUIRE(workspace != nullptr && (reinterpret_cast<uintptr_t>(workspace) & (kAlign - 1)) == 0,
                 "temporal_core_forward: workspace must be 1024-byte aligned");

@@ -291,12 +291,17 @@ class FrameShardedScorer:
         encoder(local_frames, out=self._local, peer=self.features)
         feats = self.features.wait()                     # [total_frames, dim], all ranks' rows
         start, count = self.blocks[self.rank]
+        scorer = net.scorer()
         if count:
-            scorer = net.scorer()
             text = net.get_text_features()
             if text.device != self.device:
                 text = net._text_features = text.to(self.device)
             scorer.packed.set_directions(text, ncentroid)
+        if scorer.mode is None:      # "auto": ranks with units calibrate, everybody runs the agreed mode
+            if count:
+                scorer.calibrate(feats[start * self.unit:(start + count) * self.unit].contiguous(), 1)
+            scorer.mode = agree_on_mode(scorer.mode if scorer.mode is not None else 4, self.device, self._group)
+        if count:
             scorer(feats[start * self.unit:(start + count) * self.unit], 1, peer=self.rows)
         else:
             self.rows.signal()

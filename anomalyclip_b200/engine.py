@@ -374,14 +374,46 @@ class PackedTemporal:
 class TemporalScorer:
     """feature rows -> (similarity, scores, class_probs) through `aclip_temporal_forward`."""
 
-    def __init__(self, packed: PackedTemporal, passes=3,
-                 max_chunk_sub_videos: int = 512) -> None:
+    def __init__(self, packed: PackedTemporal, passes=3, max_chunk_sub_videos: int = 512,
+                 calib_tol: float = 3e-4, graph_max_sub_videos: int = 16) -> None:
+        """passes: operand mode of the 3x3 conv feed-forward GEMMs (94 % of this stage's flops; the
+        selector, projection and attention linears always run split-bf16 x3) --
+          3  split-bf16 x3           2  f16f8 where the CTA-pair kernel applies (>= 8 sub-videos)
+          4  fp16 operands, one pass (~9e-5 on the scores; cannot change a class index)
+          "auto"  4 if the scores of the first call agree with mode 3 within `calib_tol` (relative
+                  L2; max error within 2x that) and nothing saturates, else 2
+        The image encoder's modes 5 / "auto" map to "auto" here.
+        graph_max_sub_videos: calls of up to this many sub-videos are captured in a CUDA graph per
+        shape and replayed (the small-batch path is launch-bound: ~35 kernels and their tensor-map
+        encodes per call); 0 disables."""
         self.packed = packed
-        # the fp16-operand modes of the image encoder (4, "auto") map to the temporal stage's
-        # f16f8 mode: its conv GEMMs on f16f8 operands for large chunks, three passes otherwise
-        self.passes = 2 if passes in (4, 5, "auto") else passes
+        self.passes = "auto" if passes in (5, "auto") else passes
+        self.mode = None if self.passes == "auto" else self.passes
+        self.calib_tol = calib_tol
+        self.calibration: Optional[dict] = None
         self.max_chunk = max_chunk_sub_videos
+        self.graph_max = graph_max_sub_videos
+        self._graphs: Dict[tuple, tuple] = {}
         self._ws = _Workspace()
+
+    def calibrate(self, feats: torch.Tensor, segment_size: int) -> dict:
+        """Decide the conv operand mode of an "auto" scorer on this checkpoint: scores of the first
+        (up to 8) sub-videos in mode 4 against mode 3."""
+        p = self.packed
+        unit = p.struct.num_segments * p.struct.seg_length * segment_size
+        k = max(1, min(8 // max(segment_size, 1), feats.shape[0] // unit)) * unit
+        with torch.cuda.device(feats.device):
+            _lib.saturation_count(reset=True)
+            ref = self._launch(feats[:k], segment_size, 3, None)[1].double()
+            fast = self._launch(feats[:k], segment_size, 4, None)[1].double()
+            sat = _lib.saturation_count(reset=True)
+        rel = float((fast - ref).norm() / ref.norm().clamp_min(1e-30))
+        mx = float((fast - ref).abs().max() / ref.abs().max().clamp_min(1e-30))
+        ok = rel <= self.calib_tol and mx <= 2 * self.calib_tol and sat == 0
+        self.mode = 4 if ok else 2
+        self.calibration = {"rows": k, "scores_rel_l2_mode4_vs_mode3": rel, "scores_max_err_mode4_vs_mode3": mx,
+                            "saturations": sat, "tolerance": self.calib_tol, "mode": self.mode}
+        return self.calibration
 
     def __call__(self, features: torch.Tensor, segment_size: int = 1, want_probs: bool = True,
                  peer=None):
@@ -398,11 +430,26 @@ class TemporalScorer:
         if feats.shape[1] != p.struct.feature_dim or n_rows % (unit * segment_size) != 0:
             raise ValueError(f"TemporalScorer: {tuple(feats.shape)} rows are not a multiple of "
                              f"num_segments*seg_length*segment_size = {unit * segment_size}")
+        if self.mode is None:
+            self.calibrate(feats, segment_size)
         sub_videos = n_rows // unit
+        if (peer is None and want_probs and 0 < sub_videos <= self.graph_max
+                and not torch.cuda.is_current_stream_capturing()):
+            return self._replay(feats, segment_size)
+        return self._launch(feats, segment_size, self.mode, peer, want_probs)
+
+    def _launch(self, feats: torch.Tensor, segment_size: int, mode: int, peer, want_probs: bool = True,
+                out=None):
+        p = self.packed
+        n_rows = feats.shape[0]
+        sub_videos = n_rows // (p.struct.num_segments * p.struct.seg_length)
         dev = feats.device
-        sim = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev)
-        scores = torch.empty((n_rows,), dtype=torch.float32, device=dev)
-        probs = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev) if want_probs else None
+        if out is None:
+            sim = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev)
+            scores = torch.empty((n_rows,), dtype=torch.float32, device=dev)
+            probs = torch.empty((n_rows, p.num_dirs), dtype=torch.float32, device=dev) if want_probs else None
+        else:
+            sim, scores, probs = out
         lib = _lib.load()
         chunk = max(1, min(sub_videos, self.max_chunk))
         nbytes = lib.aclip_temporal_workspace_bytes(C.byref(p.struct), chunk)
@@ -412,9 +459,43 @@ class TemporalScorer:
             _lib.check(lib.aclip_temporal_forward_ex(
                 C.byref(p.struct), feats.data_ptr(), sub_videos, segment_size, sim.data_ptr(),
                 scores.data_ptr(), probs.data_ptr() if probs is not None else None, ws, nbytes,
-                self.passes, C.byref(gather) if gather is not None else None,
+                mode, C.byref(gather) if gather is not None else None,
                 torch.cuda.current_stream(dev).cuda_stream))
         return sim, scores, probs
+
+    def _replay(self, feats: torch.Tensor, segment_size: int):
+        """Small calls: one CUDA graph per (rows, segment_size, mode, weights) holding the whole
+        stage -- regroup, ~35 kernels, head -- with static input / output buffers; a call is one
+        device-to-device copy of the features plus one graph launch.  The packed weights, the
+        selector operand and the workspace are baked into the graph, so it is rebuilt whenever any
+        of them changes."""
+        p = self.packed
+        base = (feats.shape[0], segment_size, self.mode, str(feats.device), p.struct.selector_w,
+                p.struct.ncentroid)
+        entry = self._graphs.get(base)
+        if entry is not None and entry[3] != self._ws._buf.data_ptr():
+            entry = None                                    # the workspace was reallocated since
+        if entry is None:
+            static_in = torch.empty_like(feats)
+            static_in.copy_(feats)
+            self._launch(static_in, segment_size, self.mode, None)          # warm-up (sizes the workspace)
+            out = (torch.empty((feats.shape[0], p.num_dirs), dtype=torch.float32, device=feats.device),
+                   torch.empty((feats.shape[0],), dtype=torch.float32, device=feats.device),
+                   torch.empty((feats.shape[0], p.num_dirs), dtype=torch.float32, device=feats.device))
+            graph = torch.cuda.CUDAGraph()
+            side = torch.cuda.Stream(device=feats.device)
+            side.wait_stream(torch.cuda.current_stream(feats.device))
+            with torch.cuda.stream(side):
+                with torch.cuda.graph(graph, stream=side):
+                    self._launch(static_in, segment_size, self.mode, None, out=out)
+            torch.cuda.current_stream(feats.device).wait_stream(side)
+            if len(self._graphs) >= 8:                      # a handful of shapes in practice
+                self._graphs.pop(next(iter(self._graphs)))
+            entry = self._graphs[base] = (graph, static_in, out, self._ws._buf.data_ptr())
+        graph, static_in, out, _ = entry
+        static_in.copy_(feats)
+        graph.replay()
+        return tuple(t.clone() for t in out)
 
 
 class TemporalCore:

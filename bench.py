@@ -272,7 +272,7 @@ def _features_path(dev) -> dict:
                             heads=cfg.heads, num_segments=cfg.num_segments, seg_length=cfg.seg_length,
                             concat_features=cfg.concat_features)
     packed.set_directions(syn.make_text_features(cfg).to(dev), syn.make_ncentroid(cfg).to(dev))
-    scorer = TemporalScorer(packed, passes=2, max_chunk_sub_videos=1024)
+    scorer = TemporalScorer(packed, passes="auto", max_chunk_sub_videos=1024)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     out = {"workload": "configs[1]: UCF-Crime-shaped features (32 segments x 16 rows, 14 classes), "
                        "selector + temporal + head, inputs resident, L2 flushed between iterations",
@@ -283,6 +283,21 @@ def _features_path(dev) -> dict:
         rows = B * cfg.unit
         out[f"sub_videos_{B}"] = {"ms": round(ms, 4), "rows_per_s": round(rows / ms * 1e3),
                                   "algo_tflops": round(rows * TEMPORAL_MFLOP_PER_FRAME["ucfcrime"] / ms / 1e3, 1)}
+    out["conv_operand_mode"] = scorer.mode
+    out["calibration"] = scorer.calibration
+    out["note"] = ("conv feed-forward GEMMs (94 % of the flops) in the calibrated operand mode (4 = fp16 one "
+                   "pass); calls of <= 16 sub-videos replay a CUDA graph of the whole stage")
+    # one ShanghaiTech-shaped sub-video (depth 2, concat features): the per-video latency of a short clip
+    sht = syn.PRESETS["shanghaitech"]
+    packed_s = PackedTemporal(syn.make_state_dict(sht, with_vit=False), dev, num_classes=sht.num_classes,
+                              normal_id=sht.normal_id, emb_size=sht.emb_size, depth=sht.depth, heads=sht.heads,
+                              num_segments=sht.num_segments, seg_length=sht.seg_length,
+                              concat_features=sht.concat_features)
+    packed_s.set_directions(syn.make_text_features(sht).to(dev), syn.make_ncentroid(sht).to(dev))
+    one = torch.randn(sht.unit, 512, device=dev) * 0.5
+    for name, sc in (("graph", TemporalScorer(packed_s, passes="auto")),
+                     ("no_graph", TemporalScorer(packed_s, passes="auto", graph_max_sub_videos=0))):
+        out[f"shanghaitech_one_sub_video_ms_{name}"] = round(_time_gpu(lambda sc=sc: sc(one, 1), iters=20, flush=flush), 4)
     return out
 
 

@@ -316,7 +316,9 @@ int aclip_peer_signal(const AclipPeerGather* gather, void* stream);
  * scores_out [N], class_probs_out [N][num_dirs] (may be NULL).  Sub-videos are processed in as
  * large chunks as `workspace` allows.  passes: 3 (split-bf16) or 1 (bf16) for every GEMM; 2 runs the
  * 3x3 conv GEMMs (94 % of the work) on f16f8 operands where AclipConvFFWeights carries them and the
- * chunk is large enough for the CTA-pair kernel, everything else as passes = 3. */
+ * chunk is large enough for the CTA-pair kernel, everything else as passes = 3; 4 runs the conv
+ * GEMMs on fp16 operands in one pass at any chunk size (~9e-5 on the scores; class indices cannot
+ * change: the score scales every class alike), everything else as passes = 3. */
 int aclip_temporal_forward(const AclipTemporalWeights* w, const float* features,
                            long long sub_videos, int segment_size, float* similarity_out,
                            float* scores_out, float* class_probs_out, void* workspace,
