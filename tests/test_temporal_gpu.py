@@ -164,7 +164,20 @@ def test_auto_mode_and_512_sub_videos_match_oracle():
     assert scorer.mode == 4
     assert_parity(sc, sc_ref, "512 sub-videos scores (auto)")
     assert_parity(probs, probs_ref, "512 sub-videos class probabilities (auto)")
-    assert torch.equal(probs.argmax(1).cpu(), probs_ref.argmax(1)), "argmax class differs"
+    # 262 144 rows x 13 classes hold exact near-ties: a class index may differ from the oracle's only
+    # where the oracle's own top-2 probabilities are closer than the tolerance band ...
+    top, ref_top = probs.argmax(1).cpu(), probs_ref.argmax(1)
+    two = probs_ref.topk(2, dim=1).values
+    margin = (two[:, 0] - two[:, 1]) / two[:, 0]
+    differs = top != ref_top
+    print(f"class indices differing from the oracle: {int(differs.sum())} of {top.numel()}, "
+          f"largest reference margin among them {float(margin[differs].max()) if differs.any() else 0:.2e}")
+    assert int(differs.sum()) <= top.numel() // 10000 and not (differs & (margin > 1e-4)).any()
+    # ... and the operand mode of the conv GEMMs cannot change one at all: the score scales every
+    # class of a row alike, the similarity is bit-identical in every mode
+    strict = _scorer(cfg, sd, passes=3, max_chunk=128); strict.packed.set_directions(text, m)
+    sim3, _, probs3 = strict(feats.cuda(), 1)
+    assert torch.equal(sim, sim3) and torch.equal(probs.argmax(1), probs3.argmax(1))
 
 
 def test_small_calls_replay_a_cuda_graph_with_identical_results():
