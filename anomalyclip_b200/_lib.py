@@ -92,6 +92,7 @@ SIGNATURES = {
     "aclip_last_error": (C.c_char_p, []),
     "aclip_launch_count": (C.c_longlong, []),
     "aclip_saturation_count": (C.c_longlong, [C.c_int]),
+    "aclip_note_launches": (C.c_longlong, [C.c_longlong]),
     "aclip_timing_enable": (C.c_int, [C.c_int]),
     "aclip_timing_collect": (C.c_int, [C.POINTER(TimingRow), C.c_int]),
     "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),

@@ -64,6 +64,12 @@ extern "C" long long aclip_launch_count(void) {
   return aclip::g_launches.load(std::memory_order_relaxed);
 }
 
+extern "C" long long aclip_note_launches(long long n) {
+  // kernels replayed from a captured CUDA graph never pass through the launchers again: the host
+  // side that replays the graph reports how many of this library's kernels it holds
+  return aclip::g_launches.fetch_add(n > 0 ? n : 0, std::memory_order_relaxed) + (n > 0 ? n : 0);
+}
+
 extern "C" int aclip_timing_enable(int on) {
   aclip::g_timing_on.store(on ? 1 : 0, std::memory_order_relaxed);
   return ACLIP_OK;

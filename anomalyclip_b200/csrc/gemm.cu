@@ -77,11 +77,11 @@ static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint6
   return ACLIP_OK;
 }
 
-template <int BLOCK_N, int PASSES>
+template <int BLOCK_N, int PASSES, int EPI = 0>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                   int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, PASSES>;
-  auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES, EPI>;
   static PerDeviceOnce once;
   int once_dev;
   if (once.need(once_dev)) {
@@ -110,12 +110,12 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   return ACLIP_OK;
 }
 
-template <int PASSES>
+template <int PASSES, int EPI = 0>
 static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUtensorMap& tmA8,
                        const CUtensorMap& tmB8, const GemmParams& p, int max_ctas,
                        cudaStream_t stream) {
   using Cfg = Gemm2Cfg<PASSES>;
-  auto kernel = gemm2_tcgen05_kernel<PASSES>;
+  auto kernel = gemm2_tcgen05_kernel<PASSES, EPI>;
   static PerDeviceOnce once;
   int once_dev;
   if (once.need(once_dev)) {
@@ -305,7 +305,10 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
       ACLIP_TRY(make_tmap(&tmA8, static_cast<const uint8_t*>(g.a) + 2 * ps, 5, dims_8, str_8, box_8,
                           CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_64B));
     }
-    return launch_pair<2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
+    const int epi = encoded_epilogue_kind(p);
+    return epi == 1   ? launch_pair<2, 1>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
+           : epi == 2 ? launch_pair<2, 2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
+                      : launch_pair<2, 0>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
   }
   if (g.a_mode == 0) {
     ACLIP_REQUIRE(g.lda % 8 == 0 && g.lda >= g.K, "gemm: lda=%d invalid for K=%d", g.lda, g.K);
@@ -346,13 +349,19 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box, op_dtype));
   }
 
-  if (pair)
-    return g.passes == 3   ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
-           : g.passes == 4 ? launch_pair<4>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
-                           : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+  const int epi = g.passes == 4 ? encoded_epilogue_kind(p) : 0;   // fp16-based operands feed fp16-based outputs
+  if (pair) {
+    if (g.passes == 4)
+      return epi == 2   ? launch_pair<4, 2>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+             : epi == 1 ? launch_pair<4, 1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+                        : launch_pair<4, 0>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+    return g.passes == 3 ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+                         : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+  }
 #define ACLIP_LAUNCH_SINGLE(BN)                                                          \
   return g.passes == 3   ? launch<BN, 3>(tmA, tmB, p, g.max_ctas, stream)                \
-         : g.passes == 4 ? launch<BN, 4>(tmA, tmB, p, g.max_ctas, stream)                \
+         : g.passes == 4 ? (epi == 2 ? launch<BN, 4, 2>(tmA, tmB, p, g.max_ctas, stream) \
+                                     : launch<BN, 4, 0>(tmA, tmB, p, g.max_ctas, stream)) \
                          : launch<BN, 1>(tmA, tmB, p, g.max_ctas, stream)
   if (block_n == 256) { ACLIP_LAUNCH_SINGLE(256); }
   if (block_n == 128) { ACLIP_LAUNCH_SINGLE(128); }

@@ -252,6 +252,145 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
   }
 }
 
+// ------------------------------------------------------------------------------------------
+// Encoded-output epilogue (the GEMMs whose only output feeds another GEMM or the attention:
+// in_proj, c_fc, conv1): no fp32 output, no residual, no row remap.  Differences to the generic
+// path above, all of them fewer instructions per element (these K = 768 GEMMs are epilogue-bound:
+// 6 k / 12 k tensor cycles per 256 x 256 tile against ~30 thread instructions per element before):
+//   * the values are ENCODED in the accumulator layout (one row per lane) and staged already
+//     narrow: 64 B (fp16) resp. 64 + 32 + 32 B (f16f8 planes H | L | C) per row instead of 128 B of
+//     fp32, so the transposed read-back and the global stores move 16 bytes per lane and
+//     instruction (4 resp. 8 of each per chunk instead of 8 + 8..24 narrower stores);
+//   * the TMEM load of chunk c + 1 is issued before chunk c is processed;
+//   * no residual registers, no per-row remap arithmetic.
+// Staging layouts (per warp, 4 KB): H rows of 64 B with the 16-byte piece XOR-ed by (row >> 1) & 3,
+// L and C rows of 32 B with the piece XOR-ed by (row >> 2) & 1: conflict-free for the row-per-lane
+// writes and for the 8-rows-per-instruction reads.
+template <int ENC>   // 1 = f16f8 planes, 2 = fp16 plane
+__device__ __forceinline__ void epilogue_encode_store(const GemmParams& p, const uint32_t (&raw)[32],
+                                                      int n, int m_base, int lane, uint8_t* stage,
+                                                      float& amax) {
+  // ---- scale + bias + activation, one row per lane
+  float v[32];
+  const float sc = p.out_scale;
+  if (p.bias != nullptr) {
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const float4 b = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+      v[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), sc, b.x);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), sc, b.y);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), sc, b.z);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), sc, b.w);
+    }
+  } else {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(raw[j]) * sc;
+  }
+  if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+  } else if (p.act == ACT_LEAKYRELU) {
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+  }
+#pragma unroll
+  for (int j = 0; j < 8; ++j) amax = sat_track(amax, v[4 * j], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+  // ---- encode and stage (row = lane)
+  __syncwarp();  // the previous chunk's readers are done with the staging buffer
+  uint8_t* srow_h = stage + lane * 64;
+  const int swz_h = (lane >> 1) & 3;
+  if (ENC == 2) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {   // 8 values = 16 bytes of fp16 per piece
+      uint2 a, b;
+      f16_pack4(v[8 * q + 0], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], a);
+      f16_pack4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7], b);
+      *reinterpret_cast<uint4*>(srow_h + ((q ^ swz_h) << 4)) = make_uint4(a.x, a.y, b.x, b.y);
+    }
+  } else {
+    uint8_t* srow_l = stage + 2048 + lane * 32;
+    uint8_t* srow_c = stage + 3072 + lane * 32;
+    const int swz_8 = (lane >> 2) & 1;
+    uint32_t lw[8], cw[8];
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+      uint2 a, b;
+      f16f8_pack4(v[8 * q + 0], v[8 * q + 1], v[8 * q + 2], v[8 * q + 3], kActScaleMain, kActScaleRes,
+                  kActScaleCoarse, a, lw[2 * q], cw[2 * q]);
+      f16f8_pack4(v[8 * q + 4], v[8 * q + 5], v[8 * q + 6], v[8 * q + 7], kActScaleMain, kActScaleRes,
+                  kActScaleCoarse, b, lw[2 * q + 1], cw[2 * q + 1]);
+      *reinterpret_cast<uint4*>(srow_h + ((q ^ swz_h) << 4)) = make_uint4(a.x, a.y, b.x, b.y);
+    }
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {   // 16 values = 16 bytes of e4m3 per piece
+      *reinterpret_cast<uint4*>(srow_l + ((q ^ swz_8) << 4)) =
+          make_uint4(lw[4 * q], lw[4 * q + 1], lw[4 * q + 2], lw[4 * q + 3]);
+      *reinterpret_cast<uint4*>(srow_c + ((q ^ swz_8) << 4)) =
+          make_uint4(cw[4 * q], cw[4 * q + 1], cw[4 * q + 2], cw[4 * q + 3]);
+    }
+  }
+  __syncwarp();
+  // ---- row-contiguous stores: H 8 rows x 64 B per instruction, L / C 16 rows x 32 B
+  uint8_t* out = reinterpret_cast<uint8_t*>(p.out_split);
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int row = i * 8 + (lane >> 2), piece = lane & 3;
+    const int m = m_base + row;
+    if (m < p.M) {
+      const uint4 h = *reinterpret_cast<const uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+      const long long off = static_cast<long long>(m + p.row_offset) * p.ld_split + n + piece * 8;
+      *reinterpret_cast<uint4*>(out + 2 * off) = h;
+    }
+  }
+  if (ENC == 1) {
+#pragma unroll
+    for (int i = 0; i < 2; ++i) {
+      const int row = i * 16 + (lane >> 1), piece = lane & 1;
+      const int m = m_base + row;
+      if (m < p.M) {
+        const int sw = (piece ^ ((row >> 2) & 1)) << 4;
+        const uint4 l = *reinterpret_cast<const uint4*>(stage + 2048 + row * 32 + sw);
+        const uint4 c = *reinterpret_cast<const uint4*>(stage + 3072 + row * 32 + sw);
+        const long long off = static_cast<long long>(m + p.row_offset) * p.ld_split + n + piece * 16;
+        *reinterpret_cast<uint4*>(out + 2 * p.split_plane_stride + off) = l;
+        *reinterpret_cast<uint4*>(out + 3 * p.split_plane_stride + off) = c;
+      }
+    }
+  }
+}
+
+// The warp's column chunks of one tile through the encoded-output epilogue, with the TMEM load of
+// the next chunk in flight while the current one is processed.  chunks: 32-column chunks of this warp.
+template <int ENC>
+__device__ __forceinline__ void epilogue_tile_encoded(const GemmParams& p, uint32_t t_row, int n0,
+                                                      int chunks, int m_base, int lane, uint8_t* stage) {
+  if (m_base >= p.M) return;  // warp-uniform: the whole 32-row block is padding
+  uint32_t raw[2][32];
+  float amax = 0.f;
+  ptx::tmem_ld_32x32(t_row, raw[0]);
+#pragma unroll 1
+  for (int c = 0; c < chunks; c += 2) {
+    ptx::tmem_ld_wait();
+    const bool more1 = c + 1 < chunks && n0 + (c + 1) * 32 < p.N;
+    if (more1) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, raw[1]);
+    epilogue_encode_store<ENC>(p, raw[0], n0 + c * 32, m_base, lane, stage, amax);
+    if (!more1) break;
+    ptx::tmem_ld_wait();
+    const bool more2 = c + 2 < chunks && n0 + (c + 2) * 32 < p.N;
+    if (more2) ptx::tmem_ld_32x32(t_row + (c + 2) * 32, raw[0]);
+    epilogue_encode_store<ENC>(p, raw[1], n0 + (c + 1) * 32, m_base, lane, stage, amax);
+    if (!more2) break;
+  }
+  sat_report(p.sat, amax);
+}
+
+// 1 / 2 when the launch qualifies for the encoded-output epilogue with f16f8 / fp16 planes, else 0
+inline int encoded_epilogue_kind(const GemmParams& p) {
+  const bool ok = p.out_f32 == nullptr && p.out_split != nullptr && p.out_enc != 0 &&
+                  p.residual == nullptr && p.row_group_stride == 0 && p.peer_world == 0;
+  return ok ? p.out_enc : 0;
+}
+
 // End of a GEMM whose epilogue stored into peer memory: called by every thread after its last
 // store; the block-level barrier that follows in the kernels orders the fences before the count.
 __device__ __forceinline__ void peer_fence(const GemmParams& p) {
@@ -272,7 +411,10 @@ __device__ __forceinline__ void peer_publish(const GemmParams& p) {
   }
 }
 
-template <int BLOCK_N, int PASSES>
+// EPI: epilogue compiled into the instantiation -- 0 generic (epilogue_chunk), 1 / 2 encoded-output
+// only with f16f8 / fp16 planes (epilogue_tile_encoded).  One path per instantiation keeps the code
+// and the register allocation of each small (all paths in one kernel cost the generic one 23 %).
+template <int BLOCK_N, int PASSES, int EPI>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
@@ -398,11 +540,15 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
+      if (EPI != 0) {
+        epilogue_tile_encoded<EPI>(p, t_row, n0, BLOCK_N / 32, m_base, lane, stage);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < BLOCK_N / 32; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;  // warp-uniform
-        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+        for (int c = 0; c < BLOCK_N / 32; ++c) {
+          const int n = n0 + c * 32;
+          if (n >= p.N) break;  // warp-uniform
+          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+        }
       }
       // hand the accumulator buffer back to the MMA warp
       ptx::tc_fence_before();
@@ -452,7 +598,7 @@ struct Gemm2Cfg {
   static constexpr int THREADS = 64 + EPI_WARPS * 32;
 };
 
-template <int PASSES>
+template <int PASSES, int EPI>
 __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(320, 1)
 gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                      const __grid_constant__ CUtensorMap tmB,
@@ -632,11 +778,15 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
                              (static_cast<uint32_t>(quarter * 32) << 16);
+      if (EPI != 0) {
+        epilogue_tile_encoded<EPI>(p, t_row, n0, 4, m_base, lane, stage);
+      } else {
 #pragma unroll 1
-      for (int c = 0; c < 4; ++c) {
-        const int n = n0 + c * 32;
-        if (n >= p.N) break;  // warp-uniform
-        epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+        for (int c = 0; c < 4; ++c) {
+          const int n = n0 + c * 32;
+          if (n >= p.N) break;  // warp-uniform
+          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+        }
       }
       ptx::tc_fence_before();
       __syncwarp();

@@ -485,16 +485,19 @@ class TemporalScorer:
             graph = torch.cuda.CUDAGraph()
             side = torch.cuda.Stream(device=feats.device)
             side.wait_stream(torch.cuda.current_stream(feats.device))
+            n0 = _lib.launch_count()
             with torch.cuda.stream(side):
                 with torch.cuda.graph(graph, stream=side):
                     self._launch(static_in, segment_size, self.mode, None, out=out)
+            kernels = _lib.launch_count() - n0              # this library's kernels inside the graph
             torch.cuda.current_stream(feats.device).wait_stream(side)
             if len(self._graphs) >= 8:                      # a handful of shapes in practice
                 self._graphs.pop(next(iter(self._graphs)))
-            entry = self._graphs[base] = (graph, static_in, out, self._ws._buf.data_ptr())
-        graph, static_in, out, _ = entry
+            entry = self._graphs[base] = (graph, static_in, out, self._ws._buf.data_ptr(), kernels)
+        graph, static_in, out, _, kernels = entry
         static_in.copy_(feats)
         graph.replay()
+        _lib.load().aclip_note_launches(kernels)
         return tuple(t.clone() for t in out)
 
 

@@ -59,6 +59,9 @@ int aclip_version(void);
 const char* aclip_last_error(void);
 /* Number of kernels this library has launched in the calling process (all streams). */
 long long aclip_launch_count(void);
+/* Add n to the launch counter: a caller that replays a captured CUDA graph holding n kernels of
+ * this library reports them here (the launchers only run at capture time). Returns the new count. */
+long long aclip_note_launches(long long n);
 /* Threads that stored an activation beyond the fp16 range of the f16f8 / f16 encodings on the
  * CURRENT device since the last reset (synchronises the device); reset != 0 clears the counter. */
 long long aclip_saturation_count(int reset);
