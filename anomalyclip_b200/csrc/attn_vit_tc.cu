@@ -234,6 +234,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   uint8_t* out_stage = reinterpret_cast<uint8_t*>(sum_buf + 4 * TILE_Q);  // [4 quarters][2 planes][32][128 B]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
   if (warp == PRODUCER_WARP && lane == 0) {
     ptx::prefetch_tmap(&tmQ);
     ptx::prefetch_tmap(&tmKV);
@@ -256,6 +257,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // q | k | v and the output buffer belong to the predecessors until here
 
   const int my_items = (p.items - static_cast<int>(blockIdx.x) + static_cast<int>(gridDim.x) - 1) /
                        static_cast<int>(gridDim.x);
@@ -671,14 +673,14 @@ int vit_attention_tc(const void* qkv_split, long long in_plane_stride, int ld_in
   // (profiling experiments) forces the generic one
   const bool fixed13 = LP == 208 && !(debug & 8);
   if (out_enc == 2) {
-    if (fixed13) vit_attention_tc_kernel<2, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
-    else vit_attention_tc_kernel<2, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    if (fixed13) ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<2, 13>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
+    else ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<2, 0>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
   } else if (out_enc == 1) {
-    if (fixed13) vit_attention_tc_kernel<1, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
-    else vit_attention_tc_kernel<1, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    if (fixed13) ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<1, 13>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
+    else ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<1, 0>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
   } else {
-    if (fixed13) vit_attention_tc_kernel<0, 13><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
-    else vit_attention_tc_kernel<0, 0><<<ctas, ATT_THREADS, smem, stream>>>(tmQ, tmKV, p);
+    if (fixed13) ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<0, 13>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
+    else ACLIP_CUDA_OK(launch_pdl(vit_attention_tc_kernel<0, 0>, dim3(ctas), dim3(ATT_THREADS), smem, stream, tmQ, tmKV, p));
   }
   timing_end(KIND_VIT_ATTENTION, stream, 4.0 * B * heads * (double)L * L * HD,
              (double)B * L * heads * HD * (f16 ? 3 * 2.0 + 2.0 : 3 * 4.0 + 4.0));

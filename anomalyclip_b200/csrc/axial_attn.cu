@@ -10,6 +10,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 #include "split.cuh"
 
 namespace aclip {
@@ -24,6 +25,8 @@ axial_attention_kernel(const float* __restrict__ qkv, int E, int heads, int L, l
                        int inner, int inner_mul, int stride, float scale,
                        __nv_bfloat16* __restrict__ out, long long plane_stride) {
   extern __shared__ float ax_smem[];
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   if (warp >= heads) return;
   const long long q = blockIdx.x;
@@ -142,11 +145,11 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
                                          cudaFuncAttributeMaxDynamicSharedMemorySize, 8 * 2 * MAX_L * 32 * 4));
       once.mark(once_dev);
     }
-    axial_attention_kernel<32><<<static_cast<unsigned>(seqs), heads * 32, smem, stream>>>(
-        qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride);
+    ACLIP_CUDA_OK(launch_pdl(axial_attention_kernel<32>, dim3(static_cast<unsigned>(seqs)), dim3(heads * 32), smem,
+                             stream, qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride));
   } else {
-    axial_attention_kernel<16><<<static_cast<unsigned>(seqs), heads * 32, smem, stream>>>(
-        qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride);
+    ACLIP_CUDA_OK(launch_pdl(axial_attention_kernel<16>, dim3(static_cast<unsigned>(seqs)), dim3(heads * 32), smem,
+                             stream, qkv, E, heads, L, unit, inner, inner_mul, stride, scale, o, plane_stride));
   }
   timing_end(KIND_AXIAL_ATTENTION, stream, 4.0 * seqs * (double)L * L * E, (double)seqs * L * E * 16.0);
   ACLIP_CHECK_LAUNCH();

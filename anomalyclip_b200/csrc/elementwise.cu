@@ -3,6 +3,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 #include "split.cuh"
 #include "rowmap.cuh"
 
@@ -166,6 +167,8 @@ __global__ void __launch_bounds__(256)
 patchify_kernel(const void* __restrict__ frames, int B, int R, int P, Norm3 nrm,
                 __nv_bfloat16* __restrict__ out, long long plane_stride,
                 unsigned int* __restrict__ sat) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int G = R / P;
   const int K = 3 * P * P;
   const int groups_per_row = K >> 3;
@@ -242,7 +245,8 @@ int patchify(const void* frames, int is_u8, int B, int R, int P, const float* me
   const int grid = grid_for(total, 256);
   unsigned int* sat = out_enc != 0 ? saturation_counter() : nullptr;
 #define ACLIP_PATCHIFY(U8, ENC) \
-  patchify_kernel<U8, ENC><<<grid, 256, 0, stream>>>(frames, B, R, P, nrm, o, plane_stride, sat)
+  ACLIP_CUDA_OK(launch_pdl(patchify_kernel<U8, ENC>, dim3(grid), dim3(256), 0, stream, frames, B, R, P, nrm, o, \
+                           plane_stride, sat))
   if (is_u8) {
     if (out_enc == 2) ACLIP_PATCHIFY(true, 2);
     else if (out_enc == 1) ACLIP_PATCHIFY(true, 1);
@@ -264,6 +268,8 @@ int patchify(const void* frames, int is_u8, int B, int R, int P, const float* me
 // x[b*tokens + 0, :] = class_embedding + positional_embedding[0]   (clip/model.py:270-278)
 __global__ void cls_rows_kernel(float* __restrict__ x, int B, int tokens, int width,
                                 const float* __restrict__ cls, const float* __restrict__ pos) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= B * width) return;
   const int b = i / width, c = i - b * width;
@@ -274,7 +280,8 @@ int cls_rows(float* x, int B, int tokens, int width, const float* cls, const flo
              cudaStream_t stream) {
   ACLIP_REQUIRE(x && cls && pos && B > 0, "cls_rows: bad arguments");
   timing_begin(KIND_CLS_ROWS, stream);
-  cls_rows_kernel<<<(B * width + 255) / 256, 256, 0, stream>>>(x, B, tokens, width, cls, pos);
+  ACLIP_CUDA_OK(launch_pdl(cls_rows_kernel, dim3((B * width + 255) / 256), dim3(256), 0, stream, x, B, tokens,
+                           width, cls, pos));
   timing_end(KIND_CLS_ROWS, stream, 0.0, 4.0 * B * width);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -289,6 +296,8 @@ __global__ void __launch_bounds__(256)
 center_regroup_kernel(const float* __restrict__ feats, long long rows, int D,
                       const float* __restrict__ centroid, RowMap map,
                       __nv_bfloat16* __restrict__ out, int ld_out, long long plane_stride) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int groups_per_row = D >> 3;
   const long long total = rows * groups_per_row;
   for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < total;
@@ -321,8 +330,9 @@ int center_regroup(const float* feats, long long rows, int D, const float* centr
                 "center_regroup: inputs must be 16-byte aligned");
   if (rows <= 0) return ACLIP_OK;
   timing_begin(KIND_CENTER_REGROUP, stream);
-  center_regroup_kernel<<<grid_for(rows * (D >> 3), 256), 256, 0, stream>>>(
-      feats, rows, D, centroid, map, static_cast<__nv_bfloat16*>(out_split), ld_out, plane_stride);
+  ACLIP_CUDA_OK(launch_pdl(center_regroup_kernel, dim3(grid_for(rows * (D >> 3), 256)), dim3(256), 0, stream,
+                           feats, rows, D, centroid, map, static_cast<__nv_bfloat16*>(out_split), ld_out,
+                           plane_stride));
   timing_end(KIND_CENTER_REGROUP, stream, (double)rows * D, (double)rows * D * 8.0);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);

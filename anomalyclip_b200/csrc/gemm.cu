@@ -39,6 +39,14 @@ int sm_count() {
 
 std::atomic<long long> g_launches{0};
 
+bool pdl_enabled() {
+  static const bool on = [] {
+    const char* off = getenv("ACLIP_NO_PDL");
+    return !(off != nullptr && off[0] == '1');
+  }();
+  return on;
+}
+
 // ------------------------------------------------------------------ tensor maps
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
@@ -94,7 +102,7 @@ static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmPara
   int ctas = max_ctas > 0 ? max_ctas : sm_count();
   if (ctas > m_tiles * n_tiles) ctas = m_tiles * n_tiles;
   timing_begin(KIND_GEMM, stream);
-  kernel<<<ctas, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, p);
+  ACLIP_CUDA_OK(launch_pdl(kernel, dim3(ctas), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB, p));
   {
     const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : 2.0;
     const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? (p.out_enc == 2 ? 2.0 : 4.0) : 0.0) +
@@ -129,7 +137,8 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   if (clusters > m_tiles * n_tiles) clusters = m_tiles * n_tiles;
   if (clusters < 1) clusters = 1;
   timing_begin(KIND_GEMM, stream);
-  kernel<<<2 * clusters, Cfg::THREADS, Cfg::SMEM_BYTES, stream>>>(tmA, tmB, tmA8, tmB8, p);
+  ACLIP_CUDA_OK(launch_pdl(kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB,
+                           tmA8, tmB8, p));
   {
     const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : 2.0;
     const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? (p.out_enc == 2 ? 2.0 : 4.0) : 0.0) +

@@ -433,6 +433,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  ptx::pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -455,6 +456,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   __syncthreads();
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // operands, residual and outputs belong to the predecessors until here
 
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
@@ -622,6 +624,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const uint32_t rank = ptx::cluster_ctarank();  // 0 = leader
   const int cluster_id = blockIdx.x >> 1;
   const int num_clusters = gridDim.x >> 1;
+  ptx::pdl_launch_dependents();
 
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
@@ -648,6 +651,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   ptx::cluster_sync();  // barriers and TMEM of BOTH CTAs are ready before anyone touches them
   ptx::tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
+  ptx::pdl_wait();   // operands, residual and outputs belong to the predecessors until here
 
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;

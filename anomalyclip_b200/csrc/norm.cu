@@ -5,6 +5,7 @@
 #include <cuda_bf16.h>
 
 #include "common.h"
+#include "ptx.cuh"
 #include "rowmap.cuh"
 #include "split.cuh"
 
@@ -42,6 +43,8 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
                  float* __restrict__ out_f32, long long ld_f32,
                  __nv_bfloat16* __restrict__ out_split, long long ld_split,
                  long long plane_stride, unsigned int* __restrict__ sat) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   // Rows are walked from the LAST to the first: the GEMM that produced x wrote its highest rows
   // last, so they are the ones still resident in L2 (x is larger than L2 at the bench's micro-batch),
@@ -122,6 +125,8 @@ head_kernel(const float* __restrict__ x1, const float* __restrict__ x2, long lon
             const float* __restrict__ w, float bias, const float* __restrict__ sim, int ld_sim,
             int ncls, RowMap map, float* __restrict__ scores, float* __restrict__ sim_out,
             float* __restrict__ probs_out, PeerDev pg) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
   const int lane = threadIdx.x & 31;
   const long long row = static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5);
   if (row < rows) {
@@ -254,8 +259,8 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   timing_begin(KIND_LAYERNORM, stream);
   unsigned int* sat = (out_split != nullptr && out_enc != 0) ? saturation_counter() : nullptr;
 #define ACLIP_LN(MODE, ENC)                                                      \
-  layernorm_kernel<MODE, ENC><<<grid, kWarpsPerCta * 32, 0, stream>>>(           \
-      x, rows, D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat)
+  ACLIP_CUDA_OK(launch_pdl(layernorm_kernel<MODE, ENC>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, \
+                           D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat))
   if (mode == 0) {
     if (out_enc == 2) ACLIP_LN(0, 2);
     else if (out_enc == 1) ACLIP_LN(0, 1);
@@ -298,9 +303,8 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
   }
   const unsigned grid = static_cast<unsigned>((rows + kWarpsPerCta - 1) / kWarpsPerCta);
   timing_begin(KIND_SCORE_HEAD, stream);
-  head_kernel<<<grid, kWarpsPerCta * 32, 0, stream>>>(x1, x2, rows, E, gamma, beta, eps, w, bias,
-                                                      sim, ld_sim, ncls, map, scores, sim_out,
-                                                      probs_out, pg);
+  ACLIP_CUDA_OK(launch_pdl(head_kernel, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x1, x2, rows, E, gamma,
+                           beta, eps, w, bias, sim, ld_sim, ncls, map, scores, sim_out, probs_out, pg));
   timing_end(KIND_SCORE_HEAD, stream, 12.0 * rows * E, (double)rows * (8.0 * E + 4.0 * ld_sim + 4.0 + 8.0 * ncls));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);

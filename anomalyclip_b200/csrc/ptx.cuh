@@ -25,6 +25,18 @@ __device__ __forceinline__ bool elect_one() {
   return pred != 0;
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// Every hot-path kernel is launched with cudaLaunchAttributeProgrammaticStreamSerialization
+// (common.h: launch_pdl): it lets its successor start as soon as all of its own CTAs are running
+// (pdl_launch_dependents, first statement) and does its own set-up -- barrier init, TMEM allocation,
+// tensor-map prefetch -- before pdl_wait(), which returns once every predecessor grid has completed
+// and flushed.  Nothing produced or still read by a predecessor is touched before pdl_wait().
+// Without the launch attribute both instructions are no-ops.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+
 // ---------------------------------------------------------------- mbarrier
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
