@@ -114,6 +114,153 @@ axial_attention_kernel(const float* __restrict__ qkv, int E, int heads, int L, l
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------
+// Tensor-core version for the reference's grid (L = 32 segments or 16 frames, 16 or 32 dims per
+// head): one warp per (sequence, head) again, but S = Q K^T and O = P V run as warp-level
+// mma.sync m16n8k16 tiles on split-bf16 operands (hi*hi + lo*hi + hi*lo, the GEMMs' three-pass
+// product), with every operand fragment read straight from global memory in its MMA layout
+// (8-byte loads, 32-byte sectors fully used), the scores kept in the accumulator registers through
+// the softmax and re-used as the A fragments of P V (the m16n8 C layout of two adjacent key tiles IS
+// the m16k16 A layout).  About 700 instructions per warp instead of ~2 600 (the SIMT kernel issues
+// one shared-memory broadcast load per four FMAs), no shared memory, all loads in flight at once:
+// the stage is HBM-bound, not issue-bound.  (tcgen05's M = 128 tiles would be 4-8x padding here.)
+__device__ __forceinline__ void mma_16816(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k16.row.col.f32.bf16.bf16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+__device__ __forceinline__ void mma3(float (&c)[4], const uint32_t (&ah)[4], const uint32_t (&al)[4],
+                                     const uint32_t (&bh)[2], const uint32_t (&bl)[2]) {
+  mma_16816(c, ah, bh);
+  mma_16816(c, al, bh);
+  mma_16816(c, ah, bl);
+}
+
+template <int L, int EH>
+__global__ void __launch_bounds__(256)
+axial_attention_mma_kernel(const float* __restrict__ qkv, int E, int heads, long long unit, int inner,
+                           int inner_mul, int stride, float scale_log2,
+                           __nv_bfloat16* __restrict__ out, long long plane_stride) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  if (warp >= heads) return;
+  constexpr int MT = L / 16, NT = L / 8, KS = EH / 16, DT = EH / 8;
+  const int g = lane >> 2, t = lane & 3;
+  const long long q = blockIdx.x;
+  const long long base = (q / inner) * unit + (q % inner) * inner_mul;
+  const long long ld = 3ll * E;
+  const float* Q = qkv + base * ld + warp * EH;   // row j of the sequence: + j * stride * ld
+  const float* K = Q + E;
+  const float* V = Q + 2 * E;
+  const long long rs = static_cast<long long>(stride) * ld;
+
+  // ---- Q fragments (A operand of S), hi / lo
+  uint32_t qh[MT][KS][4], ql[MT][KS][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float* r0 = Q + (mt * 16 + g) * rs + ks * 16 + 2 * t;
+      const float* r1 = r0 + 8 * rs;
+      const float2 a = *reinterpret_cast<const float2*>(r0), b = *reinterpret_cast<const float2*>(r1);
+      const float2 c = *reinterpret_cast<const float2*>(r0 + 8), d = *reinterpret_cast<const float2*>(r1 + 8);
+      split_pack2(a.x, a.y, qh[mt][ks][0], ql[mt][ks][0]);
+      split_pack2(b.x, b.y, qh[mt][ks][1], ql[mt][ks][1]);
+      split_pack2(c.x, c.y, qh[mt][ks][2], ql[mt][ks][2]);
+      split_pack2(d.x, d.y, qh[mt][ks][3], ql[mt][ks][3]);
+    }
+  // ---- S = Q K^T (B fragment of key tile nt: key nt*8 + g, dims 2t, 2t+1 and +8)
+  float s[MT][NT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) s[mt][nt][i] = 0.f;
+#pragma unroll
+  for (int nt = 0; nt < NT; ++nt)
+#pragma unroll
+    for (int ks = 0; ks < KS; ++ks) {
+      const float* kr = K + (nt * 8 + g) * rs + ks * 16 + 2 * t;
+      const float2 a = *reinterpret_cast<const float2*>(kr), b = *reinterpret_cast<const float2*>(kr + 8);
+      uint32_t kh[2], kl[2];
+      split_pack2(a.x, a.y, kh[0], kl[0]);
+      split_pack2(b.x, b.y, kh[1], kl[1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma3(s[mt][nt], qh[mt][ks], ql[mt][ks], kh, kl);
+    }
+  // ---- softmax over the keys: a row's scores sit in the four lanes of a quad
+  uint32_t ph[MT][L / 16][4], pl[MT][L / 16][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt) {
+    float m0 = -INFINITY, m1 = -INFINITY;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      m0 = fmaxf(m0, fmaxf(s[mt][nt][0], s[mt][nt][1]));
+      m1 = fmaxf(m1, fmaxf(s[mt][nt][2], s[mt][nt][3]));
+    }
+    m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 1)); m0 = fmaxf(m0, __shfl_xor_sync(0xffffffffu, m0, 2));
+    m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 1)); m1 = fmaxf(m1, __shfl_xor_sync(0xffffffffu, m1, 2));
+    float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+    for (int nt = 0; nt < NT; ++nt) {
+      s[mt][nt][0] = exp2f((s[mt][nt][0] - m0) * scale_log2);
+      s[mt][nt][1] = exp2f((s[mt][nt][1] - m0) * scale_log2);
+      s[mt][nt][2] = exp2f((s[mt][nt][2] - m1) * scale_log2);
+      s[mt][nt][3] = exp2f((s[mt][nt][3] - m1) * scale_log2);
+      d0 += s[mt][nt][0] + s[mt][nt][1];
+      d1 += s[mt][nt][2] + s[mt][nt][3];
+    }
+    d0 += __shfl_xor_sync(0xffffffffu, d0, 1); d0 += __shfl_xor_sync(0xffffffffu, d0, 2);
+    d1 += __shfl_xor_sync(0xffffffffu, d1, 1); d1 += __shfl_xor_sync(0xffffffffu, d1, 2);
+    const float i0 = 1.0f / d0, i1 = 1.0f / d1;
+#pragma unroll
+    for (int kk = 0; kk < L / 16; ++kk) {   // key tiles 2kk, 2kk+1 -> one 16-key A fragment
+      split_pack2(s[mt][2 * kk][0] * i0, s[mt][2 * kk][1] * i0, ph[mt][kk][0], pl[mt][kk][0]);
+      split_pack2(s[mt][2 * kk][2] * i1, s[mt][2 * kk][3] * i1, ph[mt][kk][1], pl[mt][kk][1]);
+      split_pack2(s[mt][2 * kk + 1][0] * i0, s[mt][2 * kk + 1][1] * i0, ph[mt][kk][2], pl[mt][kk][2]);
+      split_pack2(s[mt][2 * kk + 1][2] * i1, s[mt][2 * kk + 1][3] * i1, ph[mt][kk][3], pl[mt][kk][3]);
+    }
+  }
+  // ---- O = P V (B fragment of dim tile dt: dim dt*8 + g, keys 2t, 2t+1 and +8 of the 16-key step)
+  float o[MT][DT][4];
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt)
+#pragma unroll
+      for (int i = 0; i < 4; ++i) o[mt][dt][i] = 0.f;
+#pragma unroll
+  for (int dt = 0; dt < DT; ++dt)
+#pragma unroll
+    for (int kk = 0; kk < L / 16; ++kk) {
+      const float* vr = V + (kk * 16 + 2 * t) * rs + dt * 8 + g;
+      uint32_t vh[2], vl[2];
+      split_pack2(vr[0], vr[rs], vh[0], vl[0]);
+      split_pack2(vr[8 * rs], vr[9 * rs], vh[1], vl[1]);
+#pragma unroll
+      for (int mt = 0; mt < MT; ++mt) mma3(o[mt][dt], ph[mt][kk], pl[mt][kk], vh, vl);
+    }
+  // ---- split-bf16 rows out (row stride of the output: E elements, sequence stride `stride` rows)
+#pragma unroll
+  for (int mt = 0; mt < MT; ++mt)
+#pragma unroll
+    for (int dt = 0; dt < DT; ++dt) {
+      const long long r0 = (base + static_cast<long long>(mt * 16 + g) * stride) * E + warp * EH + dt * 8 + 2 * t;
+      const long long r1 = r0 + 8ll * stride * E;
+      uint32_t h, l;
+      split_pack2(o[mt][dt][0], o[mt][dt][1], h, l);
+      *reinterpret_cast<uint32_t*>(out + r0) = h;
+      *reinterpret_cast<uint32_t*>(out + r0 + plane_stride) = l;
+      split_pack2(o[mt][dt][2], o[mt][dt][3], h, l);
+      *reinterpret_cast<uint32_t*>(out + r1) = h;
+      *reinterpret_cast<uint32_t*>(out + r1 + plane_stride) = l;
+    }
+}
+
 }  // namespace
 
 // axis 0: attend along the n segments (long range); axis 1: along the l frames of a segment.
@@ -137,7 +284,24 @@ int axial_attention(const float* qkv, long long sub_videos, int n, int l, int E,
   const int smem = heads * 2 * MAX_L * eh * static_cast<int>(sizeof(float));
   auto* o = static_cast<__nv_bfloat16*>(out_split);
   timing_begin(KIND_AXIAL_ATTENTION, stream);
-  if (eh == 32) {
+  // the reference's grid (32 segments x 16 frames) runs on the tensor cores; ACLIP_AXIAL_SIMT=1
+  // forces the fp32 SIMT kernel (A/B runs), which also serves every other sequence length
+  static const bool force_simt = [] {
+    const char* e = getenv("ACLIP_AXIAL_SIMT");
+    return e != nullptr && e[0] == '1';
+  }();
+  if (!force_simt && (L == 32 || L == 16)) {
+    const float scale_log2 = scale * 1.4426950408889634f;
+    const dim3 grid(static_cast<unsigned>(seqs)), block(heads * 32);
+#define ACLIP_AXIAL_MMA(LL, EE)                                                                    \
+  ACLIP_CUDA_OK(launch_pdl(axial_attention_mma_kernel<LL, EE>, grid, block, 0, stream, qkv, E, heads, unit, \
+                           inner, inner_mul, stride, scale_log2, o, plane_stride))
+    if (L == 32 && eh == 32) ACLIP_AXIAL_MMA(32, 32);
+    else if (L == 32) ACLIP_AXIAL_MMA(32, 16);
+    else if (eh == 32) ACLIP_AXIAL_MMA(16, 32);
+    else ACLIP_AXIAL_MMA(16, 16);
+#undef ACLIP_AXIAL_MMA
+  } else if (eh == 32) {
     static PerDeviceOnce once;
     int once_dev;
     if (once.need(once_dev)) {

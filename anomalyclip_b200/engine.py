@@ -259,8 +259,13 @@ class PackedTemporal:
 
     def __init__(self, sd: Weights, device: torch.device, *, num_classes: int, normal_id: int,
                  emb_size: int, depth: int, heads: int, num_segments: int, seg_length: int,
-                 concat_features: bool, feature_dim: int = 512) -> None:
+                 concat_features: bool, feature_dim: int = 512, core_only: bool = False) -> None:
+        """core_only: pack only what `TemporalModel.forward` on its own needs (projection in the
+        reference's column order, transformer, classifier): `feature_dim` is then simply the
+        module's input size, whatever it is made of (512, 529 = 17 similarities + 512, 768 ...),
+        and no selector operand / reordered projection exists."""
         _require_cuda(device)
+        self.core_only = core_only
         with torch.cuda.device(device):
             self._pack(sd, device, num_classes, normal_id, emb_size, depth, heads, num_segments,
                        seg_length, concat_features, feature_dim)
@@ -305,7 +310,9 @@ class PackedTemporal:
         if concat_features:  # reference input is [similarity | x]; packed rows are [x | similarity | 0]
             pw = torch.cat((pw[:, self.num_dirs:], pw[:, : self.num_dirs],
                             pw.new_zeros(E, 32 - self.num_dirs)), dim=1)
-        w.proj_w, w.proj_b = spl(pw), f32t(sd[pre + "projection.bias"])
+        if not self.core_only:
+            w.proj_w = spl(pw)
+        w.proj_b = f32t(sd[pre + "projection.bias"])
         # the projection in the reference's own column order, K padded to a multiple of 8
         # (TemporalModel.forward on its own)
         pw0 = sd[pre + "projection.weight"].detach().to(torch.float32)

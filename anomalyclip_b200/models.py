@@ -200,11 +200,12 @@ class TemporalModel(nn.Module):
         if getattr(self, "_core", None) is None or key != self._core_key:
             dev = self.projection.weight.device
             sd = {"temporal_model." + k: v for k, v in self.state_dict().items()}
-            concat = self.input_size != 512
+            # on its own the module just projects `input_size` columns, whatever they are made of
+            # (512 features, 17 similarities + 512 features, ...): no selector, no column reorder
             packed = engine.PackedTemporal(
-                sd, dev, num_classes=self.input_size - 512 + 1 if concat else 2, normal_id=0,
-                emb_size=self.emb_size, depth=self.depth, heads=self.heads,
-                num_segments=self.num_segments, seg_length=self.seg_length, concat_features=concat)
+                sd, dev, num_classes=2, normal_id=0, emb_size=self.emb_size, depth=self.depth,
+                heads=self.heads, num_segments=self.num_segments, seg_length=self.seg_length,
+                concat_features=False, feature_dim=self.input_size, core_only=True)
             self._core, self._core_key = engine.TemporalCore(packed), key
         return self._core(features, int(segment_size))
 

@@ -21,8 +21,9 @@ def main():
     ap.add_argument("--preset", default="ucfcrime")
     ap.add_argument("--batches", default="1,8,64,512,2048")
     ap.add_argument("--iters", type=int, default=5)
-    ap.add_argument("--passes", type=int, choices=(2, 3), default=2,
-                    help="2: conv GEMMs on f16f8 operands for chunks of >= 8 sub-videos (E = 256); 3: split-bf16")
+    ap.add_argument("--passes", type=lambda v: v if v == "auto" else int(v), choices=(2, 3, 4, "auto"), default="auto",
+                    help="conv feed-forward operand mode: 3 split-bf16, 2 f16f8 for chunks of >= 8 sub-videos (E = 256), "
+                         "4 fp16 one pass, auto = 4 if the calibration accepts it")
     args = ap.parse_args()
     dev = torch.device("cuda")
     cfg = syn.PRESETS[args.preset]
@@ -32,6 +33,7 @@ def main():
                             concat_features=cfg.concat_features)
     packed.set_directions(syn.make_text_features(cfg), syn.make_ncentroid(cfg))
     scorer = TemporalScorer(packed, passes=args.passes, max_chunk_sub_videos=1024)
+    scorer.packed.set_directions(syn.make_text_features(cfg).to(dev), syn.make_ncentroid(cfg).to(dev))
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for B in [int(b) for b in args.batches.split(",")]:
         feats = torch.randn(B * cfg.unit, 512, device=dev) * 0.5
