@@ -317,6 +317,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     const int epi = encoded_epilogue_kind(p);
     return epi == 1   ? launch_pair<2, 1>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
            : epi == 2 ? launch_pair<2, 2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
+           : epi == 3 ? launch_pair<2, 3>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
                       : launch_pair<2, 0>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
   }
   if (g.a_mode == 0) {
@@ -358,19 +359,25 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     ACLIP_TRY(make_tmap(&tmB, g.w, 3, dims, strides, box, op_dtype));
   }
 
-  const int epi = g.passes == 4 ? encoded_epilogue_kind(p) : 0;   // fp16-based operands feed fp16-based outputs
+  int epi = encoded_epilogue_kind(p);
+  if (g.passes != 4 && epi != 3) epi = 0;   // encoded outputs pair with fp16-based operands only
   if (pair) {
     if (g.passes == 4)
       return epi == 2   ? launch_pair<4, 2>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
              : epi == 1 ? launch_pair<4, 1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+             : epi == 3 ? launch_pair<4, 3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
                         : launch_pair<4, 0>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
-    return g.passes == 3 ? launch_pair<3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
-                         : launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+    if (g.passes == 3)
+      return epi == 3 ? launch_pair<3, 3>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream)
+                      : launch_pair<3, 0>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
+    return launch_pair<1>(tmA, tmB, tmA, tmB, p, g.max_ctas, stream);
   }
-#define ACLIP_LAUNCH_SINGLE(BN)                                                          \
-  return g.passes == 3   ? launch<BN, 3>(tmA, tmB, p, g.max_ctas, stream)                \
-         : g.passes == 4 ? (epi == 2 ? launch<BN, 4, 2>(tmA, tmB, p, g.max_ctas, stream) \
-                                     : launch<BN, 4, 0>(tmA, tmB, p, g.max_ctas, stream)) \
+#define ACLIP_LAUNCH_SINGLE(BN)                                                            \
+  return g.passes == 3   ? (epi == 3 ? launch<BN, 3, 3>(tmA, tmB, p, g.max_ctas, stream)   \
+                                     : launch<BN, 3, 0>(tmA, tmB, p, g.max_ctas, stream))  \
+         : g.passes == 4 ? (epi == 2   ? launch<BN, 4, 2>(tmA, tmB, p, g.max_ctas, stream) \
+                            : epi == 3 ? launch<BN, 4, 3>(tmA, tmB, p, g.max_ctas, stream) \
+                                       : launch<BN, 4, 0>(tmA, tmB, p, g.max_ctas, stream)) \
                          : launch<BN, 1>(tmA, tmB, p, g.max_ctas, stream)
   if (block_n == 256) { ACLIP_LAUNCH_SINGLE(256); }
   if (block_n == 128) { ACLIP_LAUNCH_SINGLE(128); }

@@ -384,11 +384,94 @@ __device__ __forceinline__ void epilogue_tile_encoded(const GemmParams& p, uint3
   sat_report(p.sat, amax);
 }
 
-// 1 / 2 when the launch qualifies for the encoded-output epilogue with f16f8 / fp16 planes, else 0
+// 1 / 2 when the launch qualifies for the encoded-output epilogue with f16f8 / fp16 planes, 3 for
+// the residual epilogue (fp32 output + fp32 residual, identity row map), else 0 (generic)
 inline int encoded_epilogue_kind(const GemmParams& p) {
-  const bool ok = p.out_f32 == nullptr && p.out_split != nullptr && p.out_enc != 0 &&
-                  p.residual == nullptr && p.row_group_stride == 0 && p.peer_world == 0;
-  return ok ? p.out_enc : 0;
+  if (p.row_group_stride != 0 || p.peer_world != 0) return 0;
+  if (p.out_f32 == nullptr && p.out_split != nullptr && p.out_enc != 0 && p.residual == nullptr)
+    return p.out_enc;
+  if (p.out_f32 != nullptr && p.out_split == nullptr && p.residual != nullptr && p.res_mod == 0) return 3;
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
+// Residual epilogue (EPI == 3): out_f32 = act(acc * scale + bias) + residual, fp32 only, identity row
+// map -- out_proj, c_proj, the axial to_out and conv2.  These launches read and write a full fp32
+// residual tile per output tile and are bound by the bytes they keep in flight: the generic path
+// issues a chunk's residual loads only when it reaches that chunk (32 KB per CTA outstanding).  Here
+// the residual rows of chunk c + 1 are requested before chunk c is processed, which doubles the
+// bytes in flight.  Same transposed, row-contiguous access pattern as the generic path.
+__device__ __forceinline__ void epilogue_tile_residual(const GemmParams& p, uint32_t t_row, int n0,
+                                                       int chunks, int m_base, int lane, uint8_t* stage) {
+  if (m_base >= p.M) return;  // warp-uniform: the whole 32-row block is padding
+  const int piece = lane & 7, rsub = lane >> 3;
+  const int colp = piece * 4;
+  long long roff[8];   // element offset of this lane's 8 rows (row i*4 + rsub), -1 = beyond M
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int m = m_base + i * 4 + rsub;
+    roff[i] = m < p.M ? static_cast<long long>(m + p.row_offset) : -1;
+  }
+  auto load_res = [&](float4 (&dst)[8], int n) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i)
+      dst[i] = roff[i] >= 0 ? *reinterpret_cast<const float4*>(p.residual + roff[i] * p.ldr + n + colp)
+                            : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  float4 cur[8], nxt[8];
+  uint32_t raw[32];
+  ptx::tmem_ld_32x32(t_row, raw);
+  load_res(cur, n0);
+  const float sc = p.out_scale;
+#pragma unroll 1
+  for (int c = 0; c < chunks; ++c) {
+    const int n = n0 + c * 32;
+    const bool more = c + 1 < chunks && n + 32 < p.N;
+    if (more) load_res(nxt, n + 32);
+    float4 b4[8];
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ptx::tmem_ld_wait();
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), sc, b4[j].x);
+      v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), sc, b4[j].y);
+      v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), sc, b4[j].z);
+      v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), sc, b4[j].w);
+    }
+    if (more) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, raw);   // raw is dead: next chunk's accumulator
+    if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
+    } else if (p.act == ACT_LEAKYRELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
+    }
+    __syncwarp();  // the previous chunk's readers are done with the staging buffer
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      *reinterpret_cast<float4*>(stage + lane * 128 + ((j ^ (lane & 7)) << 4)) =
+          make_float4(v[4 * j + 0], v[4 * j + 1], v[4 * j + 2], v[4 * j + 3]);
+    __syncwarp();
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      const int row = i * 4 + rsub;
+      if (roff[i] >= 0) {
+        const float4 a = *reinterpret_cast<const float4*>(stage + row * 128 + ((piece ^ (row & 7)) << 4));
+        *reinterpret_cast<float4*>(p.out_f32 + roff[i] * p.ldc + n + colp) =
+            make_float4(a.x + cur[i].x, a.y + cur[i].y, a.z + cur[i].z, a.w + cur[i].w);
+      }
+    }
+    if (!more) break;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) cur[i] = nxt[i];
+  }
 }
 
 // End of a GEMM whose epilogue stored into peer memory: called by every thread after its last
@@ -412,7 +495,7 @@ __device__ __forceinline__ void peer_publish(const GemmParams& p) {
 }
 
 // EPI: epilogue compiled into the instantiation -- 0 generic (epilogue_chunk), 1 / 2 encoded-output
-// only with f16f8 / fp16 planes (epilogue_tile_encoded).  One path per instantiation keeps the code
+// only with f16f8 / fp16 planes (epilogue_tile_encoded), 3 fp32 + residual (epilogue_tile_residual).  One path per instantiation keeps the code
 // and the register allocation of each small (all paths in one kernel cost the generic one 23 %).
 template <int BLOCK_N, int PASSES, int EPI>
 __global__ void __launch_bounds__(192, 1)
@@ -542,7 +625,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
-      if (EPI != 0) {
+      if (EPI == 3) {
+        epilogue_tile_residual(p, t_row, n0, BLOCK_N / 32, m_base, lane, stage);
+      } else if (EPI != 0) {
         epilogue_tile_encoded<EPI>(p, t_row, n0, BLOCK_N / 32, m_base, lane, stage);
       } else {
 #pragma unroll 1
@@ -782,7 +867,9 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * Cfg::BLOCK_N + col_half * 128 +
                              (static_cast<uint32_t>(quarter * 32) << 16);
-      if (EPI != 0) {
+      if (EPI == 3) {
+        epilogue_tile_residual(p, t_row, n0, 4, m_base, lane, stage);
+      } else if (EPI != 0) {
         epilogue_tile_encoded<EPI>(p, t_row, n0, 4, m_base, lane, stage);
       } else {
 #pragma unroll 1
