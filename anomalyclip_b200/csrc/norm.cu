@@ -214,7 +214,8 @@ head_kernel(const float* __restrict__ x1, const float* __restrict__ x2, long lon
 // Stream-side wait of the fused gather: spin until every rank's flag has reached `epoch`.
 // Bounded: after ~5 s of GPU clocks without progress (a peer died) the kernel gives up and records
 // the missing rank in flags[world + r] = 1 instead of hanging the device.
-__global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, unsigned int epoch) {
+__global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, unsigned int epoch,
+                                 long long max_cycles) {
   const int r = threadIdx.x;
   if (r < world) {
     const long long t0 = clock64();
@@ -222,7 +223,7 @@ __global__ void peer_wait_kernel(unsigned int* __restrict__ flags, int world, un
     for (;;) {
       asm volatile("ld.acquire.sys.global.u32 %0, [%1];" : "=r"(v) : "l"(flags + r) : "memory");
       if (static_cast<int>(v - epoch) >= 0) break;
-      if (clock64() - t0 > 10000000000ll) { flags[world + r] = 1u; break; }
+      if (clock64() - t0 > max_cycles) { flags[world + r] = 1u; break; }
       __nanosleep(200);
     }
   }
@@ -313,7 +314,13 @@ int score_head(const float* x1, const float* x2, long long rows, int E, const fl
 
 int peer_wait(unsigned int* local_flags, int world, unsigned int epoch, cudaStream_t stream) {
   ACLIP_REQUIRE(local_flags != nullptr && world >= 1 && world <= 8 && epoch > 0, "peer_wait: bad arguments");
-  peer_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch);
+  // bound of the wait in SM cycles (~5 s at 1.9 GHz by default); ACLIP_PEER_WAIT_CYCLES overrides it
+  static const long long max_cycles = [] {
+    const char* e = getenv("ACLIP_PEER_WAIT_CYCLES");
+    const long long v = e != nullptr ? atoll(e) : 0;
+    return v > 0 ? v : 10000000000ll;
+  }();
+  peer_wait_kernel<<<1, 32, 0, stream>>>(local_flags, world, epoch, max_cycles);
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

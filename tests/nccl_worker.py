@@ -101,6 +101,26 @@ def main():
     want = feats_all.double().mean(0).float()
     err = ((got.double() - want.double()).norm() / want.double().norm()).item()
     assert err < 1e-6, f"sharded ncentroid differs from the single-rank mean: {err:.3e}"
+
+    # a peer that never shows up is REPORTED, not waited for forever and not papered over: rank 1 skips
+    # one exchange; rank 0's stream-side wait gives up after its bound (ACLIP_PEER_WAIT_CYCLES, set
+    # to ~1 s by the test) and the next check() raises
+    from anomalyclip_b200._lib import AclipError
+    late = PeerRowGather(cfg.unit, cfg.num_classes, dev)
+    if rank == 0:
+        one = syn.make_features(cfg, 1, seed=77).reshape(-1, 512).to(dev)
+        scorer(one, 1, peer=late)
+        late.wait()
+        torch.cuda.synchronize()
+        assert late.timed_out() == [1]
+        try:
+            late.check()
+        except AclipError as exc:
+            assert "rank(s) [1]" in str(exc)
+        else:
+            raise AssertionError("the timed-out exchange was not reported")
+        assert late.timed_out() == []          # marks are cleared once reported
+    dist.barrier()
     dist.destroy_process_group()
     print("rank", rank, "ok")
 

@@ -164,7 +164,7 @@ def test_two_rank_nccl_sharding_matches_single_rank():
     import subprocess
     import sys
     script = ROOT / "tests" / "nccl_worker.py"
-    env = dict(os.environ, ACLIP_ROOT=str(ROOT))
+    env = dict(os.environ, ACLIP_ROOT=str(ROOT), ACLIP_PEER_WAIT_CYCLES="2000000000")   # ~1 s
     res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
                           "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
                          env=env, capture_output=True, text=True, timeout=300)
