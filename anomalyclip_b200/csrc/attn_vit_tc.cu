@@ -41,10 +41,12 @@ constexpr int PLO_OFF = S_STRIDE / 2;   // packed lo plane starts here inside a 
 constexpr int MAX_LP = 208 + 16;        // 224 keys at most
 constexpr int Q_PLANE = TILE_Q * 128;   // bytes of one bf16 plane of a Q tile
 constexpr int SOFTMAX_WARPS = 8;
-// warps 0..7 softmax, 8..9 idle (they keep the two single-thread roles off the schedulers of the
-// busiest softmax warps: warp w issues on scheduler w % 4), 10 = TMA producer, 11 = MMA issuer
-constexpr int PRODUCER_WARP = 10, MMA_WARP = 11;
-constexpr int ATT_THREADS = 12 * 32;
+// warps 0..7 softmax (two per TMEM lane quarter, half of the keys each), 8..11 output (one per lane
+// quarter: O / rowsum -> encoded rows in global memory, while the softmax warps already work on the
+// next tile), 12 = TMA producer, 13 = MMA issuer.
+constexpr int OUTPUT_WARP0 = 8, OUTPUT_WARPS = 4;
+constexpr int PRODUCER_WARP = 12, MMA_WARP = 13;
+constexpr int ATT_THREADS = 14 * 32;
 constexpr int HALF_GROUPS = MAX_LP / 32;  // 16-key groups per softmax warp (7)
 
 struct AttnTcParams {
@@ -207,6 +209,8 @@ __device__ __forceinline__ float softmax_group_f16(uint32_t (&v)[16], int key0, 
 // GROUPS: number of 16-key groups when known at compile time (13 for the ViT-B/16's 197 tokens: the
 // per-group tests of the softmax loop then fold away, about a quarter of its instructions), 0 = read
 // it from the parameters.
+// 14 warps are allocated as 16 (warp allocation granularity 4): 128 registers per thread.  The softmax
+// path wants ~140; the few spilled words (<= 60 bytes per thread) cost less than the output warps save.
 template <int ENC, int GROUPS>
 __global__ void __launch_bounds__(ATT_THREADS, 1)
 vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
@@ -246,7 +250,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       ptx::mbar_init(&q_full[i], 1);  ptx::mbar_init(&q_empty[i], 1);
       ptx::mbar_init(&s_full[i], 1);  ptx::mbar_init(&p_full[i], SOFTMAX_WARPS);
     }
-    ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, SOFTMAX_WARPS);
+    ptx::mbar_init(o_full, 1);  ptx::mbar_init(o_empty, OUTPUT_WARPS);
     ptx::fence_mbar_init();
   }
   if (warp == MMA_WARP) {
@@ -366,126 +370,6 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     const int g_begin = half == 0 ? 0 : g_split;
     const int g_count = half == 0 ? g_split : groups - g_split;
 
-    auto write_output = [&](int J) {  // O_J / rowsum -> global split rows (32 of the 64 dims)
-      ptx::mbar_wait(o_full, J & 1);
-      ptx::tc_fence_after();
-      uint32_t o[32];
-      ptx::tmem_ld_32x32(tmem_base + O_COL + 32 * half + lane_off, o);
-      ptx::tmem_ld_wait();
-      ptx::tc_fence_before();
-      __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(o_empty);
-      const int it = J >> 1, q = J & 1;
-      const int item = blockIdx.x + it * gridDim.x;
-      const int b = item / p.heads, h = item - b * p.heads;
-      const float* sb = sum_buf + (J & 1) * 2 * TILE_Q;
-      const float inv_sum = 1.0f / (sb[row_in_tile] + sb[TILE_Q + row_in_tile]);
-      // Stage this warp's 32 rows x 32 dims (hi and lo) in shared memory next to the other half's
-      // 32 dims, then write whole 128-byte rows: 4 rows per store instruction instead of 32
-      // scattered 16-byte pieces.  16-byte chunks are XOR-swizzled by the row to avoid conflicts.
-      uint8_t* stage = out_stage + quarter * (2 * 32 * 128);
-      if (ENC == 2) {
-        // fp16 rows: the accumulator already carries the 2^4 of the V operand, so o / rowsum is the
-        // encoded value; this warp's 32 dims are 64 bytes of the 128-byte row
-        float amax = 0.f;
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint32_t h[4];
-#pragma unroll
-          for (int j = 0; j < 4; ++j) {
-            const float a = __uint_as_float(o[8 * c + 2 * j]) * inv_sum;
-            const float bb = __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum;
-            amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(bb)));
-            asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(bb), "f"(a));
-          }
-          const int chunk = (half * 4 + c) ^ (lane & 7);
-          *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(h[0], h[1], h[2], h[3]);
-        }
-        if (p.sat != nullptr && !(amax <= 65504.0f)) atomicAdd(p.sat, 1u);
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        const int row_base = q * TILE_Q + quarter * 32;
-        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
-        const long long off0 = (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = half * 16 + i * 4 + (lane >> 3);
-          const int chunk = lane & 7;
-          if (row_base + row < p.L) {
-            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
-            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) =
-                *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) * 16));
-          }
-        }
-        return;
-      }
-      if (ENC == 1) {
-        // f16f8: buffer 0 holds the fp16 rows (128 B), buffer 1 the e4m3 rows [L 64 B | C 64 B]
-#pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          uint2 h0, h1;
-          uint32_t l0, l1, c0, c1;
-          f16f8_pack4(__uint_as_float(o[8 * c + 0]) * inv_sum, __uint_as_float(o[8 * c + 1]) * inv_sum,
-                      __uint_as_float(o[8 * c + 2]) * inv_sum, __uint_as_float(o[8 * c + 3]) * inv_sum,
-                      kActScaleMain, kActScaleRes, kActScaleCoarse, h0, l0, c0);
-          f16f8_pack4(__uint_as_float(o[8 * c + 4]) * inv_sum, __uint_as_float(o[8 * c + 5]) * inv_sum,
-                      __uint_as_float(o[8 * c + 6]) * inv_sum, __uint_as_float(o[8 * c + 7]) * inv_sum,
-                      kActScaleMain, kActScaleRes, kActScaleCoarse, h1, l1, c1);
-          const int chunk = (half * 4 + c) ^ (lane & 7);
-          *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(h0.x, h0.y, h1.x, h1.y);
-          const int lchunk = (half * 2 + (c >> 1)) ^ (lane & 7);   // 8 dims = 8 bytes of L and of C
-          const int cchunk = (4 + half * 2 + (c >> 1)) ^ (lane & 7);
-          *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + lchunk * 16 + (c & 1) * 8) = make_uint2(l0, l1);
-          *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + cchunk * 16 + (c & 1) * 8) = make_uint2(c0, c1);
-        }
-        asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-        const int row_base = q * TILE_Q + quarter * 32;
-        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
-        const long long off0 = (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = half * 16 + i * 4 + (lane >> 3);
-          const int chunk = lane & 7;
-          if (row_base + row < p.L) {
-            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
-            const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
-            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) = *reinterpret_cast<const uint4*>(src);
-            // chunks 0..3 of buffer 1 -> L plane, chunks 4..7 -> C plane (16 values each)
-            uint8_t* dst8 = ob + (chunk < 4 ? 2 : 3) * p.out_plane_stride + off + (chunk & 3) * 16;
-            *reinterpret_cast<uint4*>(dst8) = *reinterpret_cast<const uint4*>(src + 4096);
-          }
-        }
-        return;
-      }
-#pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        uint32_t hi[4], lo[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          split_pack2(__uint_as_float(o[8 * c + 2 * j]) * inv_sum,
-                      __uint_as_float(o[8 * c + 2 * j + 1]) * inv_sum, hi[j], lo[j]);
-        const int chunk = (half * 4 + c) ^ (lane & 7);
-        *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-        *reinterpret_cast<uint4*>(stage + 4096 + lane * 128 + chunk * 16) =
-            make_uint4(lo[0], lo[1], lo[2], lo[3]);
-      }
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      if (!(p.debug & 2)) {
-        const int row_base = q * TILE_Q + quarter * 32;
-        __nv_bfloat16* out_rows = p.out + (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-          const int row = half * 16 + i * 4 + (lane >> 3);   // this warp stores 16 of the 32 rows
-          const int chunk = lane & 7;
-          if (row_base + row < p.L) {
-            const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
-            __nv_bfloat16* dst = out_rows + static_cast<long long>(row) * p.ld_out + chunk * 8;
-            *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
-            *reinterpret_cast<uint4*>(dst + p.out_plane_stride) = *reinterpret_cast<const uint4*>(src + 4096);
-          }
-        }
-      }
-    };
-
     // The tile loop, instantiated per (group count, first group) of this warp's half of the keys:
     // GC = 0 reads both from g_count / g_begin at run time.
     auto softmax_tiles = [&](auto gc_tag, auto gb_tag) {
@@ -547,10 +431,7 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
       tmem_st_wait();
       ptx::tc_fence_before();
       __syncwarp();
-      if (lane == 0) ptx::mbar_arrive(&p_full[slot]);
-      // the previous tile's output is ready by now: normalise and store it.  (Its row sums were
-      // written before the barrier above by both halves.)
-      if (J > 0) write_output(J - 1);
+      if (lane == 0) ptx::mbar_arrive(&p_full[slot]);   // (the row sums above are published with it)
     }
     };
     using std::integral_constant;
@@ -561,9 +442,136 @@ vit_attention_tc_kernel(const __grid_constant__ CUtensorMap tmQ,
     } else {
       softmax_tiles(integral_constant<int, 0>{}, integral_constant<int, 0>{});
     }
-    if (my_tiles > 0) {
-      asm volatile("bar.sync %0, 64;" ::"r"(1 + quarter) : "memory");
-      write_output(my_tiles - 1);
+  } else if (warp >= OUTPUT_WARP0 && warp < OUTPUT_WARP0 + OUTPUT_WARPS) {
+    // ------------------------------------------------------------------ output warps
+    // One warp per TMEM lane quarter: 32 query rows x 64 dims of O per tile.  Running here instead
+    // of at the tail of the softmax loop takes normalise + encode + store off the softmax warps'
+    // critical path (per tile they were softmax + output in sequence, the tensor pipe idling).
+    const int quarter = warp & 3;
+    const uint32_t lane_off = static_cast<uint32_t>(quarter * 32) << 16;
+    const int row_in_tile = quarter * 32 + lane;
+    uint8_t* stage = out_stage + quarter * (2 * 32 * 128);
+    for (int J = 0; J < my_tiles; ++J) {
+      ptx::mbar_wait(o_full, J & 1);
+      ptx::tc_fence_after();
+      uint32_t o[2][32];
+      ptx::tmem_ld_32x32(tmem_base + O_COL + lane_off, o[0]);
+      ptx::tmem_ld_32x32(tmem_base + O_COL + 32 + lane_off, o[1]);
+      // the row sums of tile J: read before O is handed back (the hand-back is what allows tile
+      // J + 2's softmax, the next writer of this slot, to start)
+      const float* sb = sum_buf + (J & 1) * 2 * TILE_Q;
+      const float inv_sum = 1.0f / (sb[row_in_tile] + sb[TILE_Q + row_in_tile]);
+      ptx::tmem_ld_wait();
+      ptx::tc_fence_before();
+      __syncwarp();
+      if (lane == 0) ptx::mbar_arrive(o_empty);
+      const int it = J >> 1, q = J & 1;
+      const int item = blockIdx.x + it * gridDim.x;
+      const int b = item / p.heads, h = item - b * p.heads;
+      const int row_base = q * TILE_Q + quarter * 32;
+      const long long off0 = (static_cast<long long>(b) * p.L + row_base) * p.ld_out + h * HD;
+      // Stage the warp's 32 rows x 64 dims, then write whole rows: 4 rows x 128 B per store
+      // instruction.  16-byte chunks are XOR-swizzled by the row to avoid bank conflicts.
+      __syncwarp();   // the previous tile's readers are done with the staging buffer
+      if (ENC == 2) {
+        // fp16 rows: the accumulator already carries the 2^4 of the V operand, so o / rowsum is the
+        // encoded value
+        float amax = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hh[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float a = __uint_as_float(o[half][8 * c + 2 * j]) * inv_sum;
+              const float bb = __uint_as_float(o[half][8 * c + 2 * j + 1]) * inv_sum;
+              amax = fmaxf(amax, fmaxf(fabsf(a), fabsf(bb)));
+              asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hh[j]) : "f"(bb), "f"(a));
+            }
+            const int chunk = (half * 4 + c) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(hh[0], hh[1], hh[2], hh[3]);
+          }
+        if (p.sat != nullptr && !(amax <= 65504.0f)) atomicAdd(p.sat, 1u);
+        __syncwarp();
+        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          const int chunk = lane & 7;
+          if (row_base + row < p.L) {
+            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
+            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) =
+                *reinterpret_cast<const uint4*>(stage + row * 128 + ((chunk ^ (row & 7)) * 16));
+          }
+        }
+      } else if (ENC == 1) {
+        // f16f8: buffer 0 holds the fp16 rows (128 B), buffer 1 the e4m3 rows [L 64 B | C 64 B]
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint2 h0, h1;
+            uint32_t l0, l1, c0, c1;
+            f16f8_pack4(__uint_as_float(o[half][8 * c + 0]) * inv_sum, __uint_as_float(o[half][8 * c + 1]) * inv_sum,
+                        __uint_as_float(o[half][8 * c + 2]) * inv_sum, __uint_as_float(o[half][8 * c + 3]) * inv_sum,
+                        kActScaleMain, kActScaleRes, kActScaleCoarse, h0, l0, c0);
+            f16f8_pack4(__uint_as_float(o[half][8 * c + 4]) * inv_sum, __uint_as_float(o[half][8 * c + 5]) * inv_sum,
+                        __uint_as_float(o[half][8 * c + 6]) * inv_sum, __uint_as_float(o[half][8 * c + 7]) * inv_sum,
+                        kActScaleMain, kActScaleRes, kActScaleCoarse, h1, l1, c1);
+            const int chunk = (half * 4 + c) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(h0.x, h0.y, h1.x, h1.y);
+            const int lchunk = (half * 2 + (c >> 1)) ^ (lane & 7);   // 8 dims = 8 bytes of L and of C
+            const int cchunk = (4 + half * 2 + (c >> 1)) ^ (lane & 7);
+            *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + lchunk * 16 + (c & 1) * 8) = make_uint2(l0, l1);
+            *reinterpret_cast<uint2*>(stage + 4096 + lane * 128 + cchunk * 16 + (c & 1) * 8) = make_uint2(c0, c1);
+          }
+        __syncwarp();
+        uint8_t* ob = reinterpret_cast<uint8_t*>(p.out);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          const int row = i * 4 + (lane >> 3);
+          const int chunk = lane & 7;
+          if (row_base + row < p.L) {
+            const long long off = off0 + static_cast<long long>(row) * p.ld_out;
+            const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
+            *reinterpret_cast<uint4*>(ob + 2 * (off + chunk * 8)) = *reinterpret_cast<const uint4*>(src);
+            // chunks 0..3 of buffer 1 -> L plane, chunks 4..7 -> C plane (16 values each)
+            uint8_t* dst8 = ob + (chunk < 4 ? 2 : 3) * p.out_plane_stride + off + (chunk & 3) * 16;
+            *reinterpret_cast<uint4*>(dst8) = *reinterpret_cast<const uint4*>(src + 4096);
+          }
+        }
+      } else {
+#pragma unroll
+        for (int half = 0; half < 2; ++half)
+#pragma unroll
+          for (int c = 0; c < 4; ++c) {
+            uint32_t hi[4], lo[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+              split_pack2(__uint_as_float(o[half][8 * c + 2 * j]) * inv_sum,
+                          __uint_as_float(o[half][8 * c + 2 * j + 1]) * inv_sum, hi[j], lo[j]);
+            const int chunk = (half * 4 + c) ^ (lane & 7);
+            *reinterpret_cast<uint4*>(stage + lane * 128 + chunk * 16) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+            *reinterpret_cast<uint4*>(stage + 4096 + lane * 128 + chunk * 16) =
+                make_uint4(lo[0], lo[1], lo[2], lo[3]);
+          }
+        __syncwarp();
+        if (!(p.debug & 2)) {
+          __nv_bfloat16* out_rows = p.out + off0;
+#pragma unroll
+          for (int i = 0; i < 8; ++i) {
+            const int row = i * 4 + (lane >> 3);
+            const int chunk = lane & 7;
+            if (row_base + row < p.L) {
+              const uint8_t* src = stage + row * 128 + ((chunk ^ (row & 7)) * 16);
+              __nv_bfloat16* dst = out_rows + static_cast<long long>(row) * p.ld_out + chunk * 8;
+              *reinterpret_cast<uint4*>(dst) = *reinterpret_cast<const uint4*>(src);
+              *reinterpret_cast<uint4*>(dst + p.out_plane_stride) = *reinterpret_cast<const uint4*>(src + 4096);
+            }
+          }
+        }
+      }
     }
   }
 
