@@ -140,7 +140,7 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
   ACLIP_CUDA_OK(launch_pdl(kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tmA, tmB,
                            tmA8, tmB8, p));
   {
-    const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : 2.0;
+    const double planes = (PASSES == 1 || PASSES == 4) ? 1.0 : PASSES == 6 ? 1.5 : 2.0;
     const double out_b = (p.out_f32 ? 4.0 : 0.0) + (p.out_split ? (p.out_enc == 2 ? 2.0 : 4.0) : 0.0) +
                          (p.residual ? 4.0 : 0.0);
     const double a_elems = p.a_mode == 1 ? (double)p.M * (p.K / 9) : (double)p.M * p.K;
@@ -155,7 +155,8 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
-  ACLIP_REQUIRE(g.passes >= 1 && g.passes <= 4, "gemm: passes must be 1, 2, 3 or 4 (got %d)", g.passes);
+  ACLIP_REQUIRE((g.passes >= 1 && g.passes <= 4) || g.passes == 6,
+                "gemm: passes must be 1, 2, 3, 4 or 6 (got %d)", g.passes);
   ACLIP_REQUIRE(g.out_enc >= 0 && g.out_enc <= 2,
                 "gemm: out_enc must be 0 (bf16 hi/lo), 1 (f16f8) or 2 (fp16 plane)");
   if (g.passes == 4) {
@@ -163,9 +164,10 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     // weight packed with aclip_encode_f16f8
     ACLIP_REQUIRE(g.out_scale > 0.0f, "gemm: passes=4 needs out_scale = 2^-(e_act + e_weight)");
   }
-  if (g.passes == 2) {
+  const bool f16f8 = g.passes == 2 || g.passes == 6;   // 6: without the weight-residual cross term
+  if (f16f8) {
     // f16f8 operands (split.cuh): CTA-pair kernel only
-    ACLIP_REQUIRE(g.a_mode == 0 || g.a_mode == 1, "gemm: unknown a_mode %d", g.a_mode);
+    ACLIP_REQUIRE(g.a_mode == 0 || (g.a_mode == 1 && g.passes == 2), "gemm: unsupported a_mode %d", g.a_mode);
     ACLIP_REQUIRE(g.N % 256 == 0 && g.kernel != 1,
                   "gemm: passes=2 (f16f8 operands) runs on the CTA-pair kernel: N %% 256 == 0 (N=%d)", g.N);
     ACLIP_REQUIRE(g.lda % 16 == 0 && g.ldw % 16 == 0 && g.a_plane_stride % 16 == 0 &&
@@ -201,7 +203,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2,
                 "gemm: kernel must be 0 (auto), 1 (single CTA) or 2 (CTA pair)");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
-  const bool pair = g.kernel == 2 || g.passes == 2 ||
+  const bool pair = g.kernel == 2 || f16f8 ||
                     (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
@@ -269,7 +271,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                 "gemm: an f16f8 output needs a pitch and plane stride that are multiples of 16");
 
   CUtensorMap tmA, tmB, tmA8, tmB8;
-  if (g.passes == 2) {
+  if (f16f8) {
     // fp16 plane: [1][rows][ld] (128-byte swizzle rows of 64 values); e4m3 planes L, C: one
     // [2][rows][ld] byte tensor starting 2 * plane_stride bytes in (64-byte swizzle rows)
     for (int op = (g.a_mode == 1 ? 1 : 0); op < 2; ++op) {
@@ -284,7 +286,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                           CU_TENSOR_MAP_DATA_TYPE_FLOAT16, CU_TENSOR_MAP_SWIZZLE_128B));
       cuuint64_t dims_8[3] = {(cuuint64_t)g.K, rows, 2};
       cuuint64_t str_8[2] = {ld, ps};
-      cuuint32_t box_8[3] = {64, 128u, 2u};
+      cuuint32_t box_8[3] = {64, 128u, g.passes == 6 ? 1u : 2u};   // 6: one plane per box (L of A, C of W)
       ACLIP_TRY(make_tmap(op == 0 ? &tmA8 : &tmB8, static_cast<const uint8_t*>(base) + 2 * ps, 3,
                           dims_8, str_8, box_8, CU_TENSOR_MAP_DATA_TYPE_UINT8,
                           CU_TENSOR_MAP_SWIZZLE_64B));
@@ -315,6 +317,9 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                           CU_TENSOR_MAP_DATA_TYPE_UINT8, CU_TENSOR_MAP_SWIZZLE_64B));
     }
     const int epi = encoded_epilogue_kind(p);
+    if (g.passes == 6)
+      return epi == 3 ? launch_pair<6, 3>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
+                      : launch_pair<6, 0>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream);
     return epi == 1   ? launch_pair<2, 1>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
            : epi == 2 ? launch_pair<2, 2>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)
            : epi == 3 ? launch_pair<2, 3>(tmA, tmB, tmA8, tmB8, p, g.max_ctas, stream)

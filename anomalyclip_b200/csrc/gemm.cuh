@@ -10,6 +10,9 @@
 //   PASSES == 2  "f16f8": fp16 main plane + e4m3 residual and coarse planes; one kind::f16 MMA
 //                (K = 16) per K step plus two kind::f8f6f4 MMAs (K = 32, twice the rate) for the
 //                cross terms: two bf16-pass equivalents, ~2^-16 as well (CTA-pair kernels only)
+//   PASSES == 6  f16f8 WITHOUT the weight-residual term: x_H w_H + x_L w_C only (A travels as H + L,
+//                W as H + C: 3 bytes per element each, 1.5 pass-equivalents); the weights are then
+//                effectively fp16, ~1.9e-4 on the ViT features when used for ONE MLP GEMM (CTA pairs)
 //   PASSES == 1  plain bf16 (hi plane only)
 //   PASSES == 4  "f16": the fp16 main plane only, one kind::f16 MMA per K step (both kernels);
 //                ~2^-12 relative per product, selected by the host after calibration (split.cuh)
@@ -676,7 +679,11 @@ struct Gemm2Cfg {
   static constexpr int PLANES = (PASSES_ == 1 || PASSES_ == 4) ? 1 : 2;
   static constexpr int A_PLANE_BYTES = CTA_M * 128;
   static constexpr int B_PLANE_BYTES = CTA_N * 128;
-  static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
+  // bytes of one stage's A and W regions: main plane + second plane (bf16 lo, or the e4m3 L | C
+  // pair) -- PASSES == 6 carries ONE e4m3 plane per operand (L of A, C of W), half a plane's bytes
+  static constexpr int A_REGION = PASSES_ == 6 ? A_PLANE_BYTES + A_PLANE_BYTES / 2 : PLANES * A_PLANE_BYTES;
+  static constexpr int B_REGION = PASSES_ == 6 ? B_PLANE_BYTES + B_PLANE_BYTES / 2 : PLANES * B_PLANE_BYTES;
+  static constexpr int STAGE_BYTES = A_REGION + B_REGION;
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 512;
@@ -714,7 +721,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   if (warp == 0 && lane == 0) {
     ptx::prefetch_tmap(&tmA);
     ptx::prefetch_tmap(&tmB);
-    if (PASSES == 2) {
+    if (PASSES == 2 || PASSES == 6) {
       ptx::prefetch_tmap(&tmA8);
       ptx::prefetch_tmap(&tmB8);
     }
@@ -759,8 +766,17 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          uint8_t* sb = sa + Cfg::A_REGION;
           if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
+          if (PASSES == 6) {
+            // linear A only: fp16 planes + plane L of A (index 0) and plane C of W (index 1)
+            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+            ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+            ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 1);
+            if (++stage == STAGES) { stage = 0; phase ^= 1; }
+            continue;
+          }
           if (PASSES == 2) {
             // f16f8 operands: fp16 plane (128 B rows, SWIZZLE_128B) + the two e4m3 planes in one
             // box (64 B rows, SWIZZLE_64B); same bytes per stage as two bf16 planes
@@ -798,7 +814,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     if (rank == 0) {
       const bool leader = ptx::elect_one();
       // kind::f16 with fp16 operands and kind::f8f6f4 with e4m3 operands both encode format 0
-      constexpr uint32_t idesc = (PASSES == 2 || PASSES == 4)
+      constexpr uint32_t idesc = (PASSES == 2 || PASSES == 4 || PASSES == 6)
                                      ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, Cfg::BLOCK_N)
                                      : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, Cfg::BLOCK_N);
       const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
@@ -814,9 +830,20 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           ptx::tc_fence_after();
           // descriptor low word counts 16-byte units: stage / plane / K-step offsets are adds
           const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+          const uint64_t b_hi0 = a_hi0 + (Cfg::A_REGION >> 4);
           if (p.debug & 1) {
             // feed-rate experiment: consume the stage without issuing MMAs
+          } else if (PASSES == 6) {
+            // x_H w_H: four K=16 fp16 MMAs; x_L w_C: two K=32 e4m3 MMAs
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
+              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
+                                       (kb | k) != 0 ? 1u : 0u);
+            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
+            const uint64_t b_c0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_REGION + Cfg::B_PLANE_BYTES) >> 4);
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k)
+              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_c0 + 2 * k, idesc, 1u);
           } else if (PASSES == 2) {
             // x_H w_H: four K=16 fp16 MMAs; x_L w_C and x_C w_L: two K=32 e4m3 MMAs each (the
             // e4m3 tile sits behind the fp16 tile)
@@ -827,7 +854,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                                          (kb | k) != 0 ? 1u : 0u);
             }
             const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
-            const uint64_t b_l0 = a_l0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+            const uint64_t b_l0 = a_l0 + (Cfg::A_REGION >> 4);
             constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
             if (!(p.debug & 2))
 #pragma unroll

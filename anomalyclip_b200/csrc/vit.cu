@@ -105,12 +105,15 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
   ACLIP_TRY(check_weights(w));
   ACLIP_REQUIRE(frames != nullptr && features_out != nullptr, "vit_forward: null frames/output");
   ACLIP_REQUIRE(num_frames >= 0 && micro_batch > 0, "vit_forward: bad frame count / micro-batch");
-  ACLIP_REQUIRE(passes >= 1 && passes <= 5, "vit_forward: passes must be 1 .. 5");
+  ACLIP_REQUIRE(passes >= 1 && passes <= 6, "vit_forward: passes must be 1 .. 6");
   ACLIP_REQUIRE(passes == 1 || passes == 3 || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
                                                (3 * w.patch * w.patch) % 16 == 0),
                 "vit_forward: passes=%d (fp16-based operands) needs width and output_dim multiples of 256",
                 passes);
   // operand mode of the attention side (in_proj, attention, out_proj) and of everything else
+  // 6 = 5 with c_proj issued WITHOUT its weight-residual cross term (x_H w_H + x_L w_C, gemm.cuh)
+  const int p_cproj = passes == 6 ? 6 : 0;
+  if (passes == 6) passes = 5;
   const int p_att = passes == 5 ? 4 : passes;
   const int p_mlp = passes == 5 ? 2 : passes;
   const bool f16 = p_att == 4;                       // fp16 q | k | v, one-pass attention and out_proj
@@ -196,6 +199,7 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
       }
       {
         AclipGemmArgs g = linear(BIG, bp, M, 4 * W, 4 * W, b.proj_w, W, passes, b.proj_s);
+        if (p_cproj != 0) g.passes = p_cproj;
         g.bias = b.proj_b;
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;

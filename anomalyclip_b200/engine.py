@@ -58,10 +58,12 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #   5  mixed: in_proj / attention / out_proj as 4, MLP pair + patch embedding + projection as 2
 #             ~1e-4, ~1.6 pass-equivalents (the MLP GEMMs carry 8x the error variance of the
 #             attention side per scripts/numerics_passes.py, so they keep their cross terms)
+#   6  mixed with c_proj issued without its weight-residual cross term (weights of that GEMM
+#             effectively fp16): ~2e-4, ~1.5 pass-equivalents; explicit opt-in
 #   "auto"  calibrate on the first frames: the fastest of 4, 5 that agrees with 2 on this checkpoint
 #           within `calib_tol` with no fp16 saturation, else 2
 #   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
-FP16_PACKED_MODES = (2, 4, 5, "auto")
+FP16_PACKED_MODES = (2, 4, 5, 6, "auto")
 AUTO_CANDIDATES = (4, 5)       # fastest first
 
 
@@ -146,8 +148,8 @@ class VitEncoder:
         if passes not in (1, 3) + FP16_PACKED_MODES:
             raise ValueError(f"VitEncoder: unknown operand mode passes={passes!r}")
         if (passes in FP16_PACKED_MODES) != packed.f16f8:
-            raise _lib.AclipError("VitEncoder: passes=2/4/5/'auto' need weights packed with "
-                                  "PackedVit(passes=2/4/5/'auto') (and only then)")
+            raise _lib.AclipError("VitEncoder: passes=2/4/5/6/'auto' need weights packed with "
+                                  "PackedVit(passes=2/4/5/6/'auto') (and only then)")
         self.packed = packed
         self.micro_batch = micro_batch
         self.passes = passes                              # as requested
@@ -394,7 +396,7 @@ class TemporalScorer:
         shape and replayed (the small-batch path is launch-bound: ~35 kernels and their tensor-map
         encodes per call); 0 disables."""
         self.packed = packed
-        self.passes = "auto" if passes in (5, "auto") else passes
+        self.passes = "auto" if passes in (5, 6, "auto") else passes
         self.mode = None if self.passes == "auto" else self.passes
         self.calib_tol = calib_tol
         self.calibration: Optional[dict] = None

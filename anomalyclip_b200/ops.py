@@ -144,9 +144,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.a_plane_stride, g.w_plane_stride = a.numel(), w.plane_stride
         g.out_scale = 2.0 ** -(ACT_EXP[0] + w.exp)
         dev = a.device
-    elif passes == 2:
+    elif passes in (2, 6):   # 6: f16f8 operands without the weight-residual cross term
         if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
-            raise TypeError("gemm(passes=2) needs F16F8 operands")
+            raise TypeError("gemm(passes=2 / 6) needs F16F8 operands")
         M, N = a.rows, w.rows
         Kk = K if K is not None else a.ld
         g.lda, g.ldw = a.ld, w.ld

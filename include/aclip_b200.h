@@ -128,7 +128,9 @@ typedef struct AclipGemmArgs {
   long long a_plane_stride, w_plane_stride; /* elements between hi and lo plane          */
   int passes;     /* 3 = split-bf16 (fp32-faithful), 1 = plain bf16 (hi plane only),
                      2 = f16f8 operands (fp32-faithful, CTA-pair kernel, N % 256 == 0),
-                     4 = fp16 operands, one pass (CTA-pair kernel, N % 256 == 0)           */
+                     4 = fp16 operands, one pass,
+                     6 = f16f8 operands without the weight-residual cross term (1.5
+                         pass-equivalents; the weights are then effectively fp16)            */
   int a_mode;     /* 0 linear, 1 conv3x3 (zero padding 1, stride 1)                      */
   int conv_c, conv_h, conv_w, conv_s; /* conv3x3: channels, grid height, width, images  */
   /* epilogue: out = act(acc + bias) + residual */
@@ -230,7 +232,8 @@ size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
  * been packed with aclip_encode_f16f8 and width / output_dim must be multiples of 256);
  * passes = 4: fp16 operands end to end, one pass per product (same packed weights plus out_w16);
  * passes = 5: "mixed" -- in_proj, attention and out_proj as passes = 4, the MLP pair, the patch
- * embedding and the output projection as passes = 2 (~1e-4 on the features). */
+ * embedding and the output projection as passes = 2 (~1e-4 on the features);
+ * passes = 6: as 5, with c_proj issued without its weight-residual cross term (~2e-4). */
 int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
                       long long num_frames, int micro_batch, const float* mean3_host,
                       const float* std3_host, float* features_out, void* workspace,

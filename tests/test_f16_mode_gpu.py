@@ -200,3 +200,32 @@ def test_saturation_is_counted_not_silent():
     with pytest.raises(AclipError):
         _encoder(sd, passes="auto")(frames * 1e4)
     _lib.saturation_count(reset=True)
+
+
+def test_gemm_f16f8_without_weight_residual_term(ops):
+    """passes=6: x_H w_H + x_L w_C only -- the activation is carried to ~2^-16, the weight only to its
+    fp16 plane: exact (to fp32 accumulation) against fp64 products of decode(activation) x fp16(weight)."""
+    torch.manual_seed(9)
+    M, N, K = 1000, 768, 3072
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    ea, ew = ops.encode_f16f8(a), ops.encode_f16f8(w, weight=True)
+    wh = ew.planes()[0].double() * 2.0 ** -ew.exp
+    ref = a.double() @ wh.T + bias.double() + res.double()
+    out = ops.gemm(ea, ew, bias=bias, residual=res, passes=6)
+    full = ops.gemm(ea, ew, bias=bias, residual=res, passes=2)
+    true = a.double() @ w.double().T + bias.double() + res.double()
+    e6, e_true, e2 = _rel(out, ref), _rel(out, true), _rel(full, true)
+    print(f"passes=6: vs fp16-weight products {e6:.3e}, vs fp64 {e_true:.3e} (passes=2: {e2:.3e})")
+    assert e6 < 3e-5 and e_true < 4e-4 and e2 < 3e-5
+
+
+def test_vit_b16_mode6(vitb16):
+    sd = vitb16
+    enc6 = _encoder(sd, passes=6)
+    u8 = make_frames_u8(5, seed=3)
+    e = assert_parity(enc6(u8.cuda()), oracle.vit_forward(sd, normalise_frames(u8)),
+                      "ViT-B/16 features from uint8 frames, mode 6", rtol=3e-4)
+    print(f"mode 6 rel-L2 vs oracle: {e:.3e}")

@@ -200,16 +200,17 @@ def _argmax_flips_outside_band(probs, probs_ref, band):
     return int((differs & (margin > band)).sum()), int(differs.sum())
 
 
-@pytest.mark.parametrize("passes", [None, 2, 5, 4])
+@pytest.mark.parametrize("passes", [None, 2, 5, 6, 4])
 def test_mirror_net_on_raw_frames_matches_oracle(sht_unit_oracle, passes):
     """configs[2] through the reference-facing class: AnomalyCLIP(load_from_features=False) on one
     512-frame unit of uint8 frames (ViT-B/16, 12 layers) against the CPU oracle, in the default
     operand mode ("auto"), the fp32-faithful f16f8 mode, the mixed mode and the one-pass fp16 mode.
     Bar: 1e-3 (rel-L2 and max error) with bit-exact class indices in the default, f16f8 and mixed
-    modes.  The one-pass fp16 mode is the explicit fast mode OUTSIDE that contract: measured here at
-    ~4e-4 rel-L2 / ~1e-3 max error on the class probabilities, so it is held to 2e-3, and its class
-    indices may differ only where the reference's own top-2 probabilities are a tie within that
-    tolerance ("auto" never selects it unless its features calibrate within 3e-4 of f16f8)."""
+    modes.  Modes 6 (mixed, c_proj without its weight-residual term: 1.8e-4 on the class
+    probabilities) and 4 (fp16 everywhere: ~4e-4 rel-L2 / ~1e-3 max error, held to 2e-3) are
+    explicit opt-ins OUTSIDE that contract: each flips ONE class index of the 512 -- at a row whose
+    reference top-2 probabilities tie within the tolerance -- which is why "auto" never selects
+    them; their class indices may differ only at such ties."""
     cfg, sd, text, m, u8, sim_ref, sc_ref, probs_ref = sht_unit_oracle
     net = _net(cfg, load_from_features=False, **({} if passes is None else {"passes": passes}))
     missing, unexpected = net.load_state_dict(sd, strict=False)
@@ -226,7 +227,7 @@ def test_mirror_net_on_raw_frames_matches_oracle(sht_unit_oracle, passes):
     outside, flips = _argmax_flips_outside_band(net.class_probs, probs_ref, band=2 * bar)
     print(f"{tag}: {flips} of {probs_ref.shape[0]} class indices differ, {outside} outside the tolerance band")
     assert outside == 0
-    if mode != 4:
+    if mode not in (4, 6):
         assert flips == 0, "class indices must be bit-exact in this operand mode"
 
 
