@@ -60,11 +60,13 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #             attention side per scripts/numerics_passes.py, so they keep their cross terms)
 #   6  mixed with c_proj issued without its weight-residual cross term (weights of that GEMM
 #             effectively fp16): ~2e-4, ~1.5 pass-equivalents; explicit opt-in
-#   "auto"  calibrate on the first frames: the fastest of 4, 5 that agrees with 2 on this checkpoint
-#           within `calib_tol` with no fp16 saturation, else 2
+#   "auto"  calibrate on the first frames: mode 5 if it agrees with 2 on this checkpoint within
+#           `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
+#           automatically: each flips a class index at a reference tie in the end-to-end test, and a
+#           calibration on features cannot vouch for class indices.
 #   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
 FP16_PACKED_MODES = (2, 4, 5, 6, "auto")
-AUTO_CANDIDATES = (4, 5)       # fastest first
+AUTO_CANDIDATES = (5,)         # fastest first
 
 
 class PackedVit:
@@ -163,9 +165,9 @@ class VitEncoder:
     def calibrate(self, frames: torch.Tensor) -> dict:
         """Decide the operand mode of an "auto" encoder on THIS checkpoint and THESE frames: encode
         the first `calib_frames` frames with f16f8 operands (fp32-faithful, mode 2) and with the
-        faster modes; the fastest one that agrees with mode 2 within `calib_tol` (relative L2 of the
-        features; their relative max error within 2x that) with no activation outside the fp16 range
-        is taken, else mode 2."""
+        candidate modes (AUTO_CANDIDATES, fastest first); the first one that agrees with mode 2 within
+        `calib_tol` (relative L2 of the features; their relative max error within 2x that) with no
+        activation outside the fp16 range is taken, else mode 2."""
         k = max(1, min(self.calib_frames, frames.shape[0]))
         with torch.cuda.device(frames.device):
             _lib.saturation_count(reset=True)

@@ -742,8 +742,8 @@ def main() -> None:
     ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, 5, 6, "auto"), default="auto",
                     help="GEMM operand mode of the image encoder: 3 = split-bf16 x3, 2 = fp16 + e4m3 cross "
                          "terms (both ~1e-5 on the features), 4 = fp16 operands in one pass (~4e-4), 5 = mixed "
-                         "(attention side as 4, MLP side as 2, ~1e-4), auto = the fastest of 4, 5 whose "
-                         "calibration on this checkpoint agrees with 2 within 3e-4, else 2")
+                         "(attention side as 4, MLP side as 2, ~1e-4), 6 = 5 with c_proj at 1.5 passes, auto = 5 if "
+                         "its calibration on this checkpoint agrees with 2 within 3e-4, else 2")
     ap.add_argument("--ncu", action="store_true",
                     help="profiling aid: warm-up + 1 step between cudaProfilerStart/Stop, no JSON")
     args = ap.parse_args()

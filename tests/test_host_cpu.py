@@ -115,6 +115,45 @@ def test_sharded_run_gathers_all_rows_in_unit_order_gloo(units):
     assert rows[: first * 4, 2].eq(0).all() and rows[first * 4:, 2].eq(1).all()
 
 
+def _mode_worker(rank, world, port, modes, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from anomalyclip_b200.distributed import agree_on_mode
+    q.put((rank, agree_on_mode(modes[rank], torch.device("cpu"))))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("modes,agreed", [((4, 4), 4), ((4, 5), 5), ((5, 2), 2), ((2, 4), 2)])
+def test_ranks_agree_on_the_most_conservative_operand_mode_gloo(modes, agreed):
+    """Ranks calibrate an "auto" encoder on their own frames; everybody then runs the most conservative
+    of the selected modes (4 fastest, then 5, then 2), so a sharded video is scored in ONE mode."""
+    from anomalyclip_b200.distributed import agree_on_mode
+    assert agree_on_mode(5, torch.device("cpu")) == 5          # no process group: unchanged
+    world, port = 2, _free_port()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_mode_worker, args=(r, world, port, modes, q)) for r in range(world)]
+    for p in procs:
+        p.start()
+    got = dict(q.get(timeout=120) for _ in range(world))
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got == {0: agreed, 1: agreed}
+
+
+def test_operand_mode_bookkeeping_needs_no_gpu():
+    """The host-side mode table: which `passes` values share the fp16-based weight pack, what "auto"
+    tries and in which order, how the image encoder's mode maps to the temporal stage's."""
+    from anomalyclip_b200 import engine
+    assert set(engine.FP16_PACKED_MODES) == {2, 4, 5, 6, "auto"}
+    assert engine.AUTO_CANDIDATES == (5,)         # 6 and 4 flip a class index at a reference tie: opt-in only
+    scorer = engine.TemporalScorer.__new__(engine.TemporalScorer)
+    for given, mapped in ((3, 3), (2, 2), (4, 4), (5, "auto"), (6, "auto"), ("auto", "auto")):
+        engine.TemporalScorer.__init__(scorer, packed=None, passes=given)
+        assert scorer.passes == mapped and (scorer.mode is None) == (mapped == "auto")
+
+
 def test_eot_positions_without_tokenizer():
     from anomalyclip_b200.models import eot_positions
     torch.manual_seed(0)
