@@ -562,6 +562,9 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           img = mt / tiles_per_img;
           h0 = (mt % tiles_per_img) * (Cfg::BLOCK_M / p.conv_w);
         }
+        // conv3x3: (tap, channel block) advance incrementally -- the divisions by the run-time
+        // channel-block count cost this single thread more per K block than the TMA issue itself
+        int cb = 0, dy = -1, dx = -1;
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
@@ -570,10 +573,11 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           if (p.a_mode == 0) {
             ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
           } else {
-            const int tap = kb / p.conv_cin_kb;
-            const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            ptx::tma_load_5d(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+            ptx::tma_load_5d(sa, &tmA, &full_bar[stage], cb * Cfg::BLOCK_K, dx, h0 + dy, img, 0);
+            if (++cb == p.conv_cin_kb) {
+              cb = 0;
+              if (++dx > 1) { dx = -1; ++dy; }
+            }
           }
           ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
@@ -582,9 +586,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     }
   } else if (warp == 1) {
     // ------------------------------------------------------------ MMA issuer
-    if (lane == 0) {
+    // The warp stays converged; one elected lane issues (descriptors in uniform registers, offsets
+    // are adds on the descriptor's low word, which counts 16-byte units).
+    {
+      const bool leader = ptx::elect_one();
       constexpr uint32_t idesc = PASSES == 4 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, BLOCK_N)   // fp16
                                              : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, BLOCK_N);
+      const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
       uint32_t stage = 0, phase = 0;
       uint32_t acc = 0, acc_phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
@@ -594,25 +602,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint32_t a_base = ptx::smem_u32(smem + stage * Cfg::STAGE_BYTES);
-          const uint32_t b_base = a_base + Cfg::PLANES * Cfg::A_PLANE_BYTES;
+          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
 #pragma unroll
           for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-            const uint32_t koff = k * Cfg::UMMA_K * 2;  // bytes along K inside the swizzle row
-            const uint64_t a_hi = ptx::make_kmajor_sw128_desc(a_base + koff);
-            const uint64_t b_hi = ptx::make_kmajor_sw128_desc(b_base + koff);
-            ptx::mma_bf16_ss(d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
+            const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;   // 32 bytes along K per step
+            ptx::mma_f16_ss_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
             if (PASSES == 3) {
-              const uint64_t a_lo = ptx::make_kmajor_sw128_desc(a_base + Cfg::A_PLANE_BYTES + koff);
-              const uint64_t b_lo = ptx::make_kmajor_sw128_desc(b_base + Cfg::B_PLANE_BYTES + koff);
-              ptx::mma_bf16_ss(d_tmem, a_lo, b_hi, idesc, 1u);
-              ptx::mma_bf16_ss(d_tmem, a_hi, b_lo, idesc, 1u);
+              ptx::mma_f16_ss_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+              ptx::mma_f16_ss_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
             }
           }
-          ptx::mma_commit(&empty_bar[stage]);  // smem slot is free once these MMAs retire
+          ptx::mma_commit_if(leader, &empty_bar[stage]);  // smem slot is free once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
-        ptx::mma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        ptx::mma_commit_if(leader, &tfull_bar[acc]);  // accumulator complete -> epilogue
         acc ^= 1;
         if (acc == 0) acc_phase ^= 1;
       }

@@ -132,6 +132,32 @@ __device__ __forceinline__ void mma_bf16_ss(uint32_t d_tmem, uint64_t a_desc, ui
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate)
       : "memory");
 }
+// Predicated forms for a CONVERGED issuing warp (single-CTA kernels): every lane runs the
+// warp-uniform control flow and descriptor arithmetic (which then lives in uniform registers), only
+// the lane with `issue` set executes the instruction.  An issuer that branches to one lane first
+// spends ~150 cycles of scalar descriptor arithmetic per MMA, more than an N = 64 MMA takes.
+__device__ __forceinline__ void mma_f16_ss_if(bool issue, uint32_t d_tmem, uint64_t a_desc,
+                                              uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %5, 0;\n\t"
+      "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
+__device__ __forceinline__ void mma_commit_if(bool issue, uint64_t* bar) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %1, 0;\n\t"
+      "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t"
+      "}\n" ::"r"(smem_u32(bar)),
+      "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
 // Arrive on an mbarrier once every previously issued tcgen05.mma of this thread has retired.
 // (Implies tcgen05.fence::before_thread_sync.)
 __device__ __forceinline__ void mma_commit(uint64_t* bar) {
