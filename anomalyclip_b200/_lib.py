@@ -38,6 +38,7 @@ class GemmArgs(C.Structure):
         ("max_ctas", C.c_int), ("kernel", C.c_int),
         ("out_scale", C.c_float), ("out_enc", C.c_int),
         ("gather", vp), ("gather_signal", C.c_int), ("gather_row0", C.c_longlong),
+        ("tile", C.c_int),
     ]
 
 

@@ -85,11 +85,11 @@ static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint6
   return ACLIP_OK;
 }
 
-template <int BLOCK_N, int PASSES, int EPI = 0>
+template <int BLOCK_N, int PASSES, int EPI = 0, int BLOCK_M = 128, int KATOMS = 1>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                   int max_ctas, cudaStream_t stream) {
-  using Cfg = GemmCfg<BLOCK_N, PASSES>;
-  auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES, EPI>;
+  using Cfg = GemmCfg<BLOCK_N, PASSES, BLOCK_M, KATOMS>;
+  auto kernel = gemm_tcgen05_kernel<BLOCK_N, PASSES, EPI, BLOCK_M, KATOMS>;
   static PerDeviceOnce once;
   int once_dev;
   if (once.need(once_dev)) {
@@ -203,12 +203,19 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.kernel == 0 || g.kernel == 1 || g.kernel == 2,
                 "gemm: kernel must be 0 (auto), 1 (single CTA) or 2 (CTA pair)");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
+  ACLIP_REQUIRE(g.tile >= 0 && g.tile <= 2, "gemm: tile must be 0 (auto), 1 (128 rows) or 2 (64 x 32)");
   const bool pair = g.kernel == 2 || f16f8 ||
                     (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
   // more SMs share the K loop.  128 is also preferred when it wastes fewer padded columns.
+  // Below a quarter of a wave of 128 x 64 tiles (one or two sub-videos of the temporal stage) the
+  // tile shrinks to 64 x 32 with four K atoms per barrier round: these GEMMs are bound by the
+  // number of L2 round trips of their K loop, not by bytes or flops.  Same accumulation order per
+  // element: results do not depend on the tile choice.  tile = 1 / 2 forces 128-row / 64-row tiles
+  // (tests).
   int block_n = 128;  // rows of W per TMA box (the pair kernel loads 128 per CTA)
+  int block_m = 128;  // rows of A per TMA box
   if (!pair) {
     const int m_tiles = (g.M + 127) / 128;
     const int want = sm_count() / 2;
@@ -217,6 +224,11 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     if (!narrow && tiles(256) >= want) block_n = 256;
     else if (tiles(128) >= want) block_n = 128;
     else block_n = 64;
+    const bool small_ok = (g.passes == 3 || g.passes == 4) && g.gather == nullptr &&
+                          (g.a_mode == 0 || (g.conv_w > 0 && 64 % g.conv_w == 0 &&
+                                             (g.conv_h * g.conv_w) % 64 == 0));
+    const bool small_auto = block_n == 64 && tiles(64) < sm_count() / 4;
+    if (small_ok && g.tile != 1 && (g.tile == 2 || small_auto)) { block_m = 64; block_n = 32; }
   }
 
   GemmParams p{};
@@ -330,7 +342,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     cuuint64_t dims[3] = {(cuuint64_t)g.K, (cuuint64_t)g.M, (cuuint64_t)planes};
     cuuint64_t strides[2] = {(cuuint64_t)g.lda * 2, (cuuint64_t)g.a_plane_stride * 2};
     if (planes == 1) strides[1] = (cuuint64_t)g.lda * 2 * (cuuint64_t)g.M;
-    cuuint32_t box[3] = {64, 128, (cuuint32_t)planes};
+    cuuint32_t box[3] = {64, (cuuint32_t)block_m, (cuuint32_t)planes};
     ACLIP_REQUIRE(planes == 1 || (g.a_plane_stride % 8 == 0 && g.a_plane_stride > 0),
                   "gemm: a_plane_stride must be a positive multiple of 8");
     ACLIP_TRY(make_tmap(&tmA, g.a, 3, dims, strides, box, op_dtype));
@@ -348,7 +360,7 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
     cuuint64_t dims[5] = {C, W, H, S, (cuuint64_t)planes};
     cuuint64_t strides[4] = {C * 2, W * C * 2, H * W * C * 2,
                              planes == 1 ? S * H * W * C * 2 : (cuuint64_t)g.a_plane_stride * 2};
-    cuuint32_t box[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(128 / g.conv_w), 1,
+    cuuint32_t box[5] = {64, (cuuint32_t)g.conv_w, (cuuint32_t)(block_m / g.conv_w), 1,
                          (cuuint32_t)planes};
     ACLIP_TRY(make_tmap(&tmA, g.a, 5, dims, strides, box, op_dtype));
   } else {
@@ -384,6 +396,11 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                             : epi == 3 ? launch<BN, 4, 3>(tmA, tmB, p, g.max_ctas, stream) \
                                        : launch<BN, 4, 0>(tmA, tmB, p, g.max_ctas, stream)) \
                          : launch<BN, 1>(tmA, tmB, p, g.max_ctas, stream)
+  if (block_m == 64) {
+    // 64 x 32 tiles: the generic epilogue handles every output kind
+    return g.passes == 3 ? launch<32, 3, 0, 64, 4>(tmA, tmB, p, g.max_ctas, stream)
+                         : launch<32, 4, 0, 64, 4>(tmA, tmB, p, g.max_ctas, stream);
+  }
   if (block_n == 256) { ACLIP_LAUNCH_SINGLE(256); }
   if (block_n == 128) { ACLIP_LAUNCH_SINGLE(128); }
   ACLIP_LAUNCH_SINGLE(64);

@@ -84,9 +84,13 @@ struct GemmParams {
                     // (operand feed + epilogue only; results are wrong by construction)
 };
 
-template <int BLOCK_N_, int PASSES_>
+// KATOMS: 64-wide K atoms (one 128-byte swizzle row each) per barrier round.  A round costs the SM
+// one L2 round trip whatever it carries (measured: ~230 ns per round for 12 KB and for 24 KB, for
+// one TMA operation and for two, with the operand ring 3 or 12 deep, with or without MMAs), so the
+// small tile moves four atoms per round.
+template <int BLOCK_N_, int PASSES_, int BLOCK_M_ = 128, int KATOMS_ = 1>
 struct GemmCfg {
-  static constexpr int BLOCK_M = 128;
+  static constexpr int BLOCK_M = BLOCK_M_;   // 128, or 64 (accumulator rows in lanes 0..15 of each quarter)
   static constexpr int BLOCK_N = BLOCK_N_;
   static constexpr int BLOCK_K = 64;  // 64 bf16 = one 128-byte swizzle row
   static constexpr int UMMA_K = 16;
@@ -94,7 +98,11 @@ struct GemmCfg {
   static constexpr int PLANES = (PASSES_ == 1 || PASSES_ == 4) ? 1 : 2;
   static constexpr int A_PLANE_BYTES = BLOCK_M * 128;
   static constexpr int B_PLANE_BYTES = BLOCK_N * 128;
-  static constexpr int STAGE_BYTES = PLANES * (A_PLANE_BYTES + B_PLANE_BYTES);
+  static constexpr int KATOMS = KATOMS_;
+  static constexpr int A_ATOM_BYTES = PLANES * A_PLANE_BYTES;   // one TMA box of A
+  static constexpr int B_ATOM_BYTES = PLANES * B_PLANE_BYTES;   // one TMA box of W
+  static constexpr int ATOM_BYTES = A_ATOM_BYTES + B_ATOM_BYTES;
+  static constexpr int STAGE_BYTES = KATOMS * ATOM_BYTES;       // [A atoms][W atoms]
   static constexpr int SMEM_BUDGET = 200 * 1024;
   static constexpr int STAGES_RAW = SMEM_BUDGET / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
@@ -105,8 +113,10 @@ struct GemmCfg {
       STAGES * STAGE_BYTES + BAR_BYTES + EPI_WARPS * 32 * 128 + 1024;  // +1024 align slack
   static constexpr int THREADS = 192;
   static_assert(STAGES >= 2, "need at least a double buffer");
-  static_assert(TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
+  static_assert(TMEM_COLS == 64 || TMEM_COLS == 128 || TMEM_COLS == 256 || TMEM_COLS == 512,
                 "TMEM columns must be a power of two");
+  static_assert(BLOCK_M_ == 128 || BLOCK_M_ == 64, "UMMA M of one CTA is 64 or 128");
+  static_assert(2 * 8 * STAGES + 4 * 8 + 4 <= BAR_BYTES, "barrier region too small");
 };
 
 // x * sigmoid(1.702 x) = x / (1 + 2^(-1.702 log2(e) x))   (reference: clip/model.py:183-185)
@@ -169,8 +179,10 @@ __device__ __forceinline__ void epilogue_store(const GemmParams& p, const int (&
   if (SPLIT >= 2) sat_report(p.sat, amax);
 }
 
+// m_end: first row this warp does NOT own (p.M, or m_base + 16 with 64-row tiles, whose accumulator
+// keeps 16 rows in the first 16 lanes of every TMEM lane quarter).
 __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t taddr, int n,
-                                               int m_base, int lane, uint8_t* stage) {
+                                               int m_base, int lane, uint8_t* stage, int m_end) {
   uint32_t raw[32];
   ptx::tmem_ld_32x32(taddr, raw);
   // ---- everything that does not depend on the accumulator, while the TMEM load is in flight
@@ -189,13 +201,13 @@ __device__ __forceinline__ void epilogue_chunk(const GemmParams& p, uint32_t tad
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = m_base + i * 4 + (lane >> 3);
-      orow[i] = m < p.M ? (m / p.row_group) * p.row_group_stride + (m % p.row_group) + p.row_offset : -1;
+      orow[i] = m < m_end ? (m / p.row_group) * p.row_group_stride + (m % p.row_group) + p.row_offset : -1;
     }
   } else {
 #pragma unroll
     for (int i = 0; i < 8; ++i) {
       const int m = m_base + i * 4 + (lane >> 3);
-      orow[i] = m < p.M ? m + p.row_offset : -1;
+      orow[i] = m < m_end ? m + p.row_offset : -1;
     }
   }
   float4 val[8];    // residual (out_f32 may alias it: each lane reads exactly what it later writes)
@@ -500,11 +512,16 @@ __device__ __forceinline__ void peer_publish(const GemmParams& p) {
 // EPI: epilogue compiled into the instantiation -- 0 generic (epilogue_chunk), 1 / 2 encoded-output
 // only with f16f8 / fp16 planes (epilogue_tile_encoded), 3 fp32 + residual (epilogue_tile_residual).  One path per instantiation keeps the code
 // and the register allocation of each small (all paths in one kernel cost the generic one 23 %).
-template <int BLOCK_N, int PASSES, int EPI>
+// BLOCK_M = 64 (with BLOCK_N = 32, KATOMS = 4): the tile of the SMALL problems (one or two
+// sub-videos of the temporal stage): four times the CTAs of the 128 x 64 tiling, and four K atoms
+// per barrier round (see GemmCfg).  Per element the accumulation order along K is the same, so
+// results are bit-identical to the 128-row tiles.
+template <int BLOCK_N, int PASSES, int EPI, int BLOCK_M = 128, int KATOMS = 1>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {
-  using Cfg = GemmCfg<BLOCK_N, PASSES>;
+  using Cfg = GemmCfg<BLOCK_N, PASSES, BLOCK_M, KATOMS>;
+  static_assert(BLOCK_M == 128 || EPI == 0, "64-row tiles use the generic epilogue");
   constexpr int STAGES = Cfg::STAGES;
 
   extern __shared__ uint8_t smem_raw[];
@@ -547,6 +564,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + BLOCK_N - 1) / BLOCK_N;
   const int total_tiles = m_tiles * n_tiles;
+  const int rounds = (p.num_kb + KATOMS - 1) / KATOMS;   // barrier rounds per tile
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer
@@ -563,23 +581,32 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           h0 = (mt % tiles_per_img) * (Cfg::BLOCK_M / p.conv_w);
         }
         // conv3x3: (tap, channel block) advance incrementally -- the divisions by the run-time
-        // channel-block count cost this single thread more per K block than the TMA issue itself
+        // channel-block count cost this single thread more per K atom than the TMA issue itself
         int cb = 0, dy = -1, dx = -1;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        int kb = 0;
+        for (int r = 0; r < rounds; ++r) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::PLANES * Cfg::A_PLANE_BYTES;
-          ptx::mbar_expect_tx(&full_bar[stage], Cfg::STAGE_BYTES);
-          if (p.a_mode == 0) {
-            ptx::tma_load_3d(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-          } else {
-            ptx::tma_load_5d(sa, &tmA, &full_bar[stage], cb * Cfg::BLOCK_K, dx, h0 + dy, img, 0);
-            if (++cb == p.conv_cin_kb) {
-              cb = 0;
-              if (++dx > 1) { dx = -1; ++dy; }
+          uint8_t* sb = sa + KATOMS * Cfg::A_ATOM_BYTES;
+          const int atoms = min(KATOMS, p.num_kb - kb);   // the last round may be short
+          ptx::mbar_expect_tx(&full_bar[stage], atoms * Cfg::ATOM_BYTES);
+#pragma unroll
+          for (int j = 0; j < KATOMS; ++j) {
+            if (j < atoms) {
+              if (p.a_mode == 0) {
+                ptx::tma_load_3d(sa + j * Cfg::A_ATOM_BYTES, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
+              } else {
+                ptx::tma_load_5d(sa + j * Cfg::A_ATOM_BYTES, &tmA, &full_bar[stage], cb * Cfg::BLOCK_K, dx,
+                                 h0 + dy, img, 0);
+                if (++cb == p.conv_cin_kb) {
+                  cb = 0;
+                  if (++dx > 1) { dx = -1; ++dy; }
+                }
+              }
+              ptx::tma_load_3d(sb + j * Cfg::B_ATOM_BYTES, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
+              ++kb;
             }
           }
-          ptx::tma_load_3d(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -590,6 +617,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     // are adds on the descriptor's low word, which counts 16-byte units).
     {
       const bool leader = ptx::elect_one();
+      const bool issue = leader && (p.debug & 1) == 0;   // debug: profiling experiments only
       constexpr uint32_t idesc = PASSES == 4 ? ptx::make_idesc_fmt0_f32(Cfg::BLOCK_M, BLOCK_N)   // fp16
                                              : ptx::make_idesc_bf16_f32(Cfg::BLOCK_M, BLOCK_N);
       const uint64_t desc0 = ptx::make_kmajor_sw128_desc(ptx::smem_u32(smem));
@@ -599,20 +627,29 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        int kb = 0;
+        for (int r = 0; r < rounds; ++r) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t b_hi0 = a_hi0 + ((Cfg::PLANES * Cfg::A_PLANE_BYTES) >> 4);
+          const uint64_t a_st = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
+          const uint64_t b_st = a_st + ((KATOMS * Cfg::A_ATOM_BYTES) >> 4);
 #pragma unroll
-          for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-            const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;   // 32 bytes along K per step
-            ptx::mma_f16_ss_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-            if (PASSES == 3) {
-              ptx::mma_f16_ss_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
-              ptx::mma_f16_ss_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+          for (int j = 0; j < KATOMS; ++j) {
+            const uint64_t a_hi0 = a_st + j * (Cfg::A_ATOM_BYTES >> 4);
+            const uint64_t b_hi0 = b_st + j * (Cfg::B_ATOM_BYTES >> 4);
+            const bool atom = issue && kb + j < p.num_kb;   // the last round may be short
+#pragma unroll
+            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+              const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;   // 32 bytes along K per step
+              const bool go = atom && (k == 0 || (p.debug & 2) == 0);
+              ptx::mma_f16_ss_if(go, d_tmem, a_hi, b_hi, idesc, (kb | j | k) != 0 ? 1u : 0u);
+              if (PASSES == 3) {
+                ptx::mma_f16_ss_if(go, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+                ptx::mma_f16_ss_if(go, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+              }
             }
           }
+          kb += KATOMS;
           ptx::mma_commit_if(leader, &empty_bar[stage]);  // smem slot is free once these MMAs retire
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -628,7 +665,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
     uint32_t acc = 0, acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       const int n0 = (t % n_tiles) * BLOCK_N;
-      const int m_base = (t / n_tiles) * Cfg::BLOCK_M + quarter * 32;
+      const int m_base = (t / n_tiles) * Cfg::BLOCK_M + quarter * (Cfg::BLOCK_M / 4);
+      const int m_end = BLOCK_M == 128 ? p.M : min(p.M, m_base + 16);
       ptx::mbar_wait(&tfull_bar[acc], acc_phase);
       ptx::tc_fence_after();
       const uint32_t t_row = tmem_base + acc * BLOCK_N + (static_cast<uint32_t>(quarter * 32) << 16);
@@ -641,7 +679,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int c = 0; c < BLOCK_N / 32; ++c) {
           const int n = n0 + c * 32;
           if (n >= p.N) break;  // warp-uniform
-          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage, m_end);
         }
       }
       // hand the accumulator buffer back to the MMA warp
@@ -907,7 +945,7 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         for (int c = 0; c < 4; ++c) {
           const int n = n0 + c * 32;
           if (n >= p.N) break;  // warp-uniform
-          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage);
+          epilogue_chunk(p, t_row + c * 32, n, m_base, lane, stage, p.M);
         }
       }
       ptx::tc_fence_before();

@@ -118,7 +118,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
          out_f32: Optional[torch.Tensor] = None, out_split: Optional[torch.Tensor] = None,
          want_split: bool = False, passes: int = 3, K: Optional[int] = None,
          conv: Optional[tuple] = None, row_map: Optional[tuple] = None, out_rows: Optional[int] = None,
-         max_ctas: int = 0, kernel: int = 0, out_enc: int = 0) -> torch.Tensor:
+         max_ctas: int = 0, kernel: int = 0, out_enc: int = 0, tile: int = 0) -> torch.Tensor:
     """out = act(A @ W^T + bias) + residual on the tcgen05 GEMM.
 
     a: split [2, M, lda] (linear) or split NHWC grid [2, S, H, W, C] with conv=(S, H, W, C).
@@ -206,6 +206,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.row_group, g.row_group_stride, g.row_offset = row_map
     g.max_ctas = max_ctas
     g.kernel = kernel
+    g.tile = tile
     _lib.check(lib.aclip_gemm(C.byref(g), _stream()))
     return out_f32 if out_f32 is not None else out_split
 

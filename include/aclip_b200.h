@@ -159,6 +159,8 @@ typedef struct AclipGemmArgs {
   const struct AclipPeerGather* gather;
   int gather_signal;
   long long gather_row0;
+  int tile;              /* single-CTA kernel: 0 = auto, 1 = 128-row tiles, 2 = 64 x 32 tiles (the
+                            small-problem tile; passes 3 / 4, no gather); results do not depend on it */
 } AclipGemmArgs;
 
 /* tcgen05 / TMA GEMM with fused epilogue. N must be a multiple of 32, K a multiple of 8. */

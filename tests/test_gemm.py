@@ -276,3 +276,67 @@ def test_conv3x3_implicit_gemm_f16f8(ops, S, Cin, Cout):
     enc = ops.gemm(a, wk, bias=b, act=ops.ACT_LEAKYRELU, conv=(S, H, W, Cin), passes=2,
                    want_split=True, out_enc=1)
     assert _rel(enc.decode(), torch.nn.functional.leaky_relu(ref, 0.01)) < 3e-5
+
+
+@pytest.mark.parametrize("M,N,K", [(512, 256, 9216), (64, 32, 64), (130, 96, 200), (1000, 768, 768),
+                                   (515, 256, 512)])
+def test_small_tile_is_bit_identical_to_the_128_row_tile(ops, M, N, K):
+    """The 64 x 32 tile of the small problems (tile=2) against the 128-row tiles (tile=1): the
+    accumulation order along K is per element, so every output bit must agree -- split-bf16 x3 and
+    fp16 one-pass operands, bias / activation / residual / row remap / encoded outputs, ragged M."""
+    torch.manual_seed(M + 7 * N + K)
+    Kp = (K + 7) // 8 * 8
+    a = torch.randn(M, Kp, device="cuda")
+    w = torch.randn(N, Kp, device="cuda") * 0.05
+    a[:, K:] = 0
+    w[:, K:] = 0
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    sa, sw = ops.split(a), ops.split(w)
+    big = ops.gemm(sa, sw, bias=bias, act=ops.ACT_QUICKGELU, residual=res, kernel=1, tile=1)
+    small = ops.gemm(sa, sw, bias=bias, act=ops.ACT_QUICKGELU, residual=res, kernel=1, tile=2)
+    assert torch.equal(big, small)
+    z = a.double() @ w.double().T + bias.double()
+    assert _rel(small, z * torch.sigmoid(1.702 * z) + res.double()) < 5e-5
+    sb = ops.gemm(sa, sw, want_split=True, kernel=1, tile=1)
+    ss = ops.gemm(sa, sw, want_split=True, kernel=1, tile=2)
+    assert torch.equal(sb, ss)
+    # row remap (groups of 16 rows -> pitch 17, offset 1), in place over a prefilled output
+    if M % 16 == 0:
+        o1 = torch.full((M // 16 * 17, N), 7.0, device="cuda")
+        o2 = o1.clone()
+        ops.gemm(sa, sw, out_f32=o1, row_map=(16, 17, 1), kernel=1, tile=1)
+        ops.gemm(sa, sw, out_f32=o2, row_map=(16, 17, 1), kernel=1, tile=2)
+        assert torch.equal(o1, o2) and torch.all(o2[::17] == 7.0)
+    # fp16 one-pass operands, fp32 and fp16-plane outputs
+    ea, ew = ops.encode_f16(a), ops.encode_f16f8(w, weight=True)
+    f1 = ops.gemm(ea, ew, bias=bias, residual=res, passes=4, kernel=1, tile=1)
+    f2 = ops.gemm(ea, ew, bias=bias, residual=res, passes=4, kernel=1, tile=2)
+    assert torch.equal(f1, f2)
+    h1 = ops.gemm(ea, ew, bias=bias, act=ops.ACT_LEAKYRELU, passes=4, want_split=True, out_enc=2, kernel=1, tile=1)
+    h2 = ops.gemm(ea, ew, bias=bias, act=ops.ACT_LEAKYRELU, passes=4, want_split=True, out_enc=2, kernel=1, tile=2)
+    assert torch.equal(h1, h2)
+
+
+@pytest.mark.parametrize("S,Cin,Cout", [(1, 1024, 256), (1, 256, 1024), (3, 128, 96)])
+def test_small_tile_conv3x3_is_bit_identical(ops, S, Cin, Cout):
+    torch.manual_seed(5)
+    H, W = 32, 16
+    x = torch.randn(S * H * W, Cin, device="cuda")
+    wk = torch.randn(Cout, 9 * Cin, device="cuda") * 0.02
+    b = torch.randn(Cout, device="cuda")
+    res = torch.randn(S * H * W, Cout, device="cuda")
+    sa, sw = ops.split(x), ops.split(wk)
+    c1 = ops.gemm(sa, sw, bias=b, residual=res, conv=(S, H, W, Cin), kernel=1, tile=1)
+    c2 = ops.gemm(sa, sw, bias=b, residual=res, conv=(S, H, W, Cin), kernel=1, tile=2)
+    assert torch.equal(c1, c2)
+    ref = torch.nn.functional.conv2d(x.reshape(S, H, W, Cin).permute(0, 3, 1, 2).double(),
+                                     wk.reshape(Cout, 3, 3, Cin).permute(0, 3, 1, 2).double(), b.double(),
+                                     padding=1).permute(0, 2, 3, 1).reshape(S * H * W, Cout) + res.double()
+    assert _rel(c2, ref) < 3e-5
+    ea, ew = ops.encode_f16(x), ops.encode_f16f8(wk, weight=True)
+    f1 = ops.gemm(ea, ew, bias=b, residual=res, conv=(S, H, W, Cin), passes=4, kernel=1, tile=1)
+    f2 = ops.gemm(ea, ew, bias=b, residual=res, conv=(S, H, W, Cin), passes=4, kernel=1, tile=2)
+    assert torch.equal(f1, f2)
+    # and the automatic choice (small problems pick the small tile) agrees as well
+    assert torch.equal(ops.gemm(ea, ew, bias=b, residual=res, conv=(S, H, W, Cin), passes=4), f1)
