@@ -85,7 +85,8 @@ static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint6
   return ACLIP_OK;
 }
 
-template <int BLOCK_N, int PASSES, int EPI = 0, int BLOCK_M = 128, int KATOMS = 1>
+template <int BLOCK_N, int PASSES, int EPI = 0, int BLOCK_M = 128,
+          int KATOMS = default_katoms(BLOCK_N, PASSES, BLOCK_M)>
 static int launch(const CUtensorMap& tmA, const CUtensorMap& tmB, const GemmParams& p,
                   int max_ctas, cudaStream_t stream) {
   using Cfg = GemmCfg<BLOCK_N, PASSES, BLOCK_M, KATOMS>;
@@ -204,8 +205,11 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                 "gemm: kernel must be 0 (auto), 1 (single CTA) or 2 (CTA pair)");
   ACLIP_REQUIRE(g.kernel != 2 || g.N % 256 == 0, "gemm: the CTA-pair kernel needs N %% 256 == 0");
   ACLIP_REQUIRE(g.tile >= 0 && g.tile <= 2, "gemm: tile must be 0 (auto), 1 (128 rows) or 2 (64 x 32)");
+  // (a K-heavy, narrow GEMM -- conv2 of 8..16 sub-videos: N = 256 -- has too few 256 x 256 tiles to
+  // occupy the machine: it stays on single-CTA tiles until a quarter of the SMs would be paired)
+  const long long pair_tiles = ((g.M + 255) / 256) * (long long)((g.N + 255) / 256);
   const bool pair = g.kernel == 2 || f16f8 ||
-                    (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096);
+                    (g.kernel == 0 && g.N % 256 == 0 && g.M >= 4096 && pair_tiles >= sm_count() / 4);
   // Single-CTA kernel: the widest tile (256, 128 or 64 columns) that still yields at least half a
   // wave of tiles; small problems (the temporal path at a few sub-videos) get narrow tiles so that
   // more SMs share the K loop.  128 is also preferred when it wastes fewer padded columns.
@@ -398,8 +402,8 @@ int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
                          : launch<BN, 1>(tmA, tmB, p, g.max_ctas, stream)
   if (block_m == 64) {
     // 64 x 32 tiles: the generic epilogue handles every output kind
-    return g.passes == 3 ? launch<32, 3, 0, 64, 4>(tmA, tmB, p, g.max_ctas, stream)
-                         : launch<32, 4, 0, 64, 4>(tmA, tmB, p, g.max_ctas, stream);
+    return g.passes == 3 ? launch<32, 3, 0, 64>(tmA, tmB, p, g.max_ctas, stream)
+                         : launch<32, 4, 0, 64>(tmA, tmB, p, g.max_ctas, stream);
   }
   if (block_n == 256) { ACLIP_LAUNCH_SINGLE(256); }
   if (block_n == 128) { ACLIP_LAUNCH_SINGLE(128); }

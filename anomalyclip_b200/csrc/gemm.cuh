@@ -84,11 +84,22 @@ struct GemmParams {
                     // (operand feed + epilogue only; results are wrong by construction)
 };
 
+#ifndef ACLIP_KATOMS_NARROW
+#define ACLIP_KATOMS_NARROW 2
+#endif
+
 // KATOMS: 64-wide K atoms (one 128-byte swizzle row each) per barrier round.  A round costs the SM
 // one L2 round trip whatever it carries (measured: ~230 ns per round for 12 KB and for 24 KB, for
 // one TMA operation and for two, with the operand ring 3 or 12 deep, with or without MMAs), so the
 // small tile moves four atoms per round.
-template <int BLOCK_N_, int PASSES_, int BLOCK_M_ = 128, int KATOMS_ = 1>
+// Tiles whose MMAs per atom take less than a round (one product per atom on a tile of <= 128
+// columns) carry two atoms per round, the 64 x 32 tile four.
+constexpr int default_katoms(int block_n, int passes, int block_m) {
+  return block_m == 64 ? 4 : ((passes == 1 || passes == 4) && block_n <= 128) ? ACLIP_KATOMS_NARROW : 1;
+}
+
+template <int BLOCK_N_, int PASSES_, int BLOCK_M_ = 128,
+          int KATOMS_ = default_katoms(BLOCK_N_, PASSES_, BLOCK_M_)>
 struct GemmCfg {
   static constexpr int BLOCK_M = BLOCK_M_;   // 128, or 64 (accumulator rows in lanes 0..15 of each quarter)
   static constexpr int BLOCK_N = BLOCK_N_;
@@ -516,7 +527,8 @@ __device__ __forceinline__ void peer_publish(const GemmParams& p) {
 // sub-videos of the temporal stage): four times the CTAs of the 128 x 64 tiling, and four K atoms
 // per barrier round (see GemmCfg).  Per element the accumulation order along K is the same, so
 // results are bit-identical to the 128-row tiles.
-template <int BLOCK_N, int PASSES, int EPI, int BLOCK_M = 128, int KATOMS = 1>
+template <int BLOCK_N, int PASSES, int EPI, int BLOCK_M = 128,
+          int KATOMS = default_katoms(BLOCK_N, PASSES, BLOCK_M)>
 __global__ void __launch_bounds__(192, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
                     const __grid_constant__ CUtensorMap tmB, const GemmParams p) {

@@ -1,9 +1,21 @@
 #!/usr/bin/env python
 """Experiment: what bounds the K loop of a SMALL GEMM (M = 512, N = 256, K = 9 216, fp16 operands,
+one tile per CTA)?  128 x 64 tiles (16 CTAs; 24 KB and 4 MMAs per 64-wide K atom, KATOMS atoms per
+barrier round) against 64 x 32 tiles (64 CTAs, 12 KB per atom, four atoms per round).  Run three
+times: ACLIP_GEMM_DEBUG unset / 1 (no MMAs: feed + barriers only) / 2 (one MMA per atom instead of
+four), each with ACLIP_PROFILING_EXPERIMENTS=1.  Times are per launch with 20 launches queued back
+to back (no host latency in the number).  Record: profiles/r2_small_gemm_round_trip_experiments.txt
+(taken when every tile carried one atom per round)."""Experiment: what bounds the K loop of a SMALL GEMM (M = 512, N = 256, K = 9 216, fp16 operands,
 one tile per CTA)?  Per K block a CTA moves 24 KB (128 x 64 tile) or 12 KB (64 x 32 tile) and issues
 4 MMAs.  Run three times: ACLIP_GEMM_DEBUG unset / 1 (no MMAs: feed only) / 2 (one MMA per K block
 instead of four), each with ACLIP_PROFILING_EXPERIMENTS=1.  Times are per launch with 20 launches
-queued back to back (no host latency in the number)."""
+queued back to back (no host latency in the number)."""Experiment: what bounds the K loop of a SMALL GEMM (M = 512, N = 256, K = 9 216, fp16 operands,
+one tile per CTA)?  128 x 64 tiles (16 CTAs; 24 KB and 4 MMAs per 64-wide K atom, KATOMS atoms per
+barrier round) against 64 x 32 tiles (64 CTAs, 12 KB per atom, four atoms per round).  Run three
+times: ACLIP_GEMM_DEBUG unset / 1 (no MMAs: feed + barriers only) / 2 (one MMA per atom instead of
+four), each with ACLIP_PROFILING_EXPERIMENTS=1.  Times are per launch with 20 launches queued back
+to back (no host latency in the number).  Record: profiles/r2_small_gemm_round_trip_experiments.txt
+(taken when every tile carried one atom per round)."""
 import os, sys, statistics, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from anomalyclip_b200 import ops
