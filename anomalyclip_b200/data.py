@@ -150,8 +150,8 @@ class FrameVideoDataset(torch.utils.data.Dataset):
                                       "the random training sampler is out of scope")
         if output not in ("uint8", "normalised", "raw"):
             raise ValueError(f"FrameVideoDataset: unknown output '{output}'")
-        if ncrops != 1:
-            raise NotImplementedError("FrameVideoDataset: the reference's raw-frame test transform has one crop")
+        if ncrops < 1:
+            raise ValueError("FrameVideoDataset: ncrops must be >= 1")
         self.root_path, self.annotationfile_path = root_path, annotationfile_path
         self.normal_id, self.num_segments, self.frames_per_segment = normal_id, num_segments, frames_per_segment
         self.imagefile_template, self.transform, self.stride, self.ncrops = imagefile_template, transform, stride, ncrops
@@ -177,7 +177,8 @@ class FrameVideoDataset(torch.utils.data.Dataset):
 
     def __getitem__(self, i: int):
         rec = self.video_list[i]
-        labels = frame_labels(rec.num_frames, rec.start_frame, rec.label, self.normal_id,
+        # ncrops only shortens the label vector here (video_dataset.py:323); the frames are not cropped
+        labels = frame_labels(rec.num_frames // self.ncrops, rec.start_frame, rec.label, self.normal_id,
                               self.annotations.get(Path(rec.path).stem, ()))
         idx, segment_size = test_mode_indices(rec.num_frames, self.num_segments,
                                               self.frames_per_segment, self.stride)

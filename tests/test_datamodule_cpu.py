@@ -92,6 +92,28 @@ def test_frame_dataset_matches_the_reference_transform_and_loops(frame_videos):
             assert (rlab, rseg, rpath) == (lab, segment_size, path)
 
 
+def test_frame_dataset_ncrops_only_shortens_the_labels_like_the_reference(frame_videos):
+    """video_dataset.py:323: with ncrops = c the raw-frame dataset returns labels for num_frames // c
+    frames and the same images."""
+    root, spec = frame_videos
+    kw = dict(root_path=str(root / "frames"), annotationfile_path=str(root / "test.txt"), normal_id=7,
+              num_segments=2, frames_per_segment=4, imagefile_template="{:06d}.png", test_mode=True,
+              temporal_annotation_file=str(root / "temporal.txt"))
+    one, two = data.FrameVideoDataset(ncrops=1, **kw), data.FrameVideoDataset(ncrops=2, **kw)
+    ref_mod = _load_reference("video_dataset")
+    ref = ref_mod.VideoFrameDataset(transform=_reference_transform(), ncrops=2, **kw) if ref_mod is not None else None
+    for i, (name, (start, end, label, _)) in enumerate(spec.items()):
+        frames = end - start + 1
+        x1, l1, *_ = one[i]
+        x2, l2, lab, seg, path = two[i]
+        assert torch.equal(x1, x2) and len(l2) == frames // 2 and l2.tolist() == l1.tolist()[: frames // 2]
+        if ref is not None:
+            rx, rl, rlab, rseg, rpath = ref[i]
+            assert rl.tolist() == l2.tolist() and (rlab, rseg, rpath) == (lab, seg, path)
+    with pytest.raises(ValueError):
+        data.FrameVideoDataset(ncrops=0, **kw)
+
+
 def test_frame_dataset_refuses_what_is_out_of_scope(frame_videos):
     root, _ = frame_videos
     kw = dict(root_path=str(root / "frames"), annotationfile_path=str(root / "test.txt"), normal_id=7)
