@@ -87,6 +87,9 @@ struct GemmParams {
 #ifndef ACLIP_KATOMS_NARROW
 #define ACLIP_KATOMS_NARROW 2
 #endif
+#ifndef ACLIP_KATOMS_PAIR
+#define ACLIP_KATOMS_PAIR 1
+#endif
 
 // KATOMS: 64-wide K atoms (one 128-byte swizzle row each) per barrier round.  A round costs the SM
 // one L2 round trip whatever it carries (measured: ~230 ns per round for 12 KB and for 24 KB, for
@@ -737,7 +740,13 @@ struct Gemm2Cfg {
   // pair) -- PASSES == 6 carries ONE e4m3 plane per operand (L of A, C of W), half a plane's bytes
   static constexpr int A_REGION = PASSES_ == 6 ? A_PLANE_BYTES + A_PLANE_BYTES / 2 : PLANES * A_PLANE_BYTES;
   static constexpr int B_REGION = PASSES_ == 6 ? B_PLANE_BYTES + B_PLANE_BYTES / 2 : PLANES * B_PLANE_BYTES;
-  static constexpr int STAGE_BYTES = A_REGION + B_REGION;
+  // K atoms per barrier round.  Even in the one-pass modes the four 131-clk MMAs of an atom outlast
+  // a round (~450 clk, see GemmCfg): two atoms per round (3 stages instead of 6) measured 1.5-3 %
+  // SLOWER on in_proj / c_fc / the temporal convs (profiles/r2_small_gemm_round_trip_experiments.txt),
+  // so the pair kernel keeps one (-DACLIP_KATOMS_PAIR=2 rebuilds the variant).
+  static constexpr int KATOMS = (PASSES_ == 1 || PASSES_ == 4) ? ACLIP_KATOMS_PAIR : 1;
+  static constexpr int ATOM_BYTES = A_REGION + B_REGION;
+  static constexpr int STAGE_BYTES = KATOMS * ATOM_BYTES;       // [A atoms][W atoms]
   static constexpr int STAGES_RAW = (200 * 1024) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 6 ? 6 : STAGES_RAW;
   static constexpr int TMEM_COLS = 512;
@@ -802,6 +811,8 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
   const int m_tiles = (p.M + Cfg::BLOCK_M - 1) / Cfg::BLOCK_M;
   const int n_tiles = (p.N + Cfg::BLOCK_N - 1) / Cfg::BLOCK_N;
   const int total_tiles = m_tiles * n_tiles;
+  constexpr int KA = Cfg::KATOMS;
+  const int rounds = (p.num_kb + KA - 1) / KA;   // barrier rounds per tile
 
   if (warp == 0) {
     // ------------------------------------------------------------ TMA producer (both CTAs)
@@ -817,47 +828,50 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
           img = mt / tiles_per_img;
           h0 = (mt % tiles_per_img) * (Cfg::CTA_M / p.conv_w);
         }
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        // conv3x3: (tap, channel block) advance incrementally (no divisions in this single thread)
+        int cb = 0, dy = -1, dx = -1;
+        int kb = 0;
+        for (int r = 0; r < rounds; ++r) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
-          uint8_t* sa = smem + stage * Cfg::STAGE_BYTES;
-          uint8_t* sb = sa + Cfg::A_REGION;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::STAGE_BYTES);
-          if (PASSES == 6) {
-            // linear A only: fp16 planes + plane L of A (index 0) and plane C of W (index 1)
-            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-            ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-            ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
-            ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 1);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
-          }
-          if (PASSES == 2) {
-            // f16f8 operands: fp16 plane (128 B rows, SWIZZLE_128B) + the two e4m3 planes in one
-            // box (64 B rows, SWIZZLE_64B); same bytes per stage as two bf16 planes
-            if (p.a_mode == 0) {
-              ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-              ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-            } else {  // conv3x3: the same shifted, zero-filled boxes for the fp16 and the e4m3 planes
-              const int tap = kb / p.conv_cin_kb;
-              const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
-              const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-              ptx::tma_load_5d_pair(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
-              ptx::tma_load_5d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], c0, dx, h0 + dy, img, 0);
+          uint8_t* sa0 = smem + stage * Cfg::STAGE_BYTES;
+          uint8_t* sb0 = sa0 + KA * Cfg::A_REGION;
+          const int atoms = min(KA, p.num_kb - kb);   // the last round may be short
+          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * atoms * Cfg::ATOM_BYTES);
+#pragma unroll
+          for (int j = 0; j < KA; ++j) {
+            if (j >= atoms) break;
+            uint8_t* sa = sa0 + j * Cfg::A_REGION;
+            uint8_t* sb = sb0 + j * Cfg::B_REGION;
+            const int k0 = kb * Cfg::BLOCK_K;
+            if (PASSES == 6) {
+              // linear A only: fp16 planes + plane L of A (index 0) and plane C of W (index 1)
+              ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
+              ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], k0, m0, 0);
+              ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], k0, n0, 0);
+              ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], k0, n0, 1);
+            } else {
+              // PASSES == 2, f16f8 operands: fp16 plane (128 B rows, SWIZZLE_128B) + the two e4m3
+              // planes in one box (64 B rows, SWIZZLE_64B); same bytes per atom as two bf16 planes
+              if (p.a_mode == 0) {
+                ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], k0, m0, 0);
+                if (PASSES == 2)
+                  ptx::tma_load_3d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], k0, m0, 0);
+              } else {  // conv3x3: the same shifted, zero-filled boxes for every plane
+                ptx::tma_load_5d_pair(sa, &tmA, &full_bar[stage], cb * Cfg::BLOCK_K, dx, h0 + dy, img, 0);
+                if (PASSES == 2)
+                  ptx::tma_load_5d_pair(sa + Cfg::A_PLANE_BYTES, &tmA8, &full_bar[stage], cb * Cfg::BLOCK_K, dx,
+                                        h0 + dy, img, 0);
+                if (++cb == p.conv_cin_kb) {
+                  cb = 0;
+                  if (++dx > 1) { dx = -1; ++dy; }
+                }
+              }
+              ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], k0, n0, 0);
+              if (PASSES == 2)
+                ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], k0, n0, 0);
             }
-            ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
-            ptx::tma_load_3d_pair(sb + Cfg::B_PLANE_BYTES, &tmB8, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
-            if (++stage == STAGES) { stage = 0; phase ^= 1; }
-            continue;
+            ++kb;
           }
-          if (p.a_mode == 0) {
-            ptx::tma_load_3d_pair(sa, &tmA, &full_bar[stage], kb * Cfg::BLOCK_K, m0, 0);
-          } else {
-            const int tap = kb / p.conv_cin_kb;
-            const int c0 = (kb - tap * p.conv_cin_kb) * Cfg::BLOCK_K;
-            const int dy = tap / 3 - 1, dx = tap % 3 - 1;
-            ptx::tma_load_5d_pair(sa, &tmA, &full_bar[stage], c0, dx, h0 + dy, img, 0);
-          }
-          ptx::tma_load_3d_pair(sb, &tmB, &full_bar[stage], kb * Cfg::BLOCK_K, n0, 0);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
       }
@@ -879,54 +893,61 @@ gemm2_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA,
         ptx::mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         ptx::tc_fence_after();
         const uint32_t d_tmem = tmem_base + acc * Cfg::BLOCK_N;
-        for (int kb = 0; kb < p.num_kb; ++kb) {
+        int kb = 0;
+        for (int r = 0; r < rounds; ++r) {
           ptx::mbar_wait(&full_bar[stage], phase);
           ptx::tc_fence_after();
-          // descriptor low word counts 16-byte units: stage / plane / K-step offsets are adds
-          const uint64_t a_hi0 = desc0 + ((stage * Cfg::STAGE_BYTES) >> 4);
-          const uint64_t b_hi0 = a_hi0 + (Cfg::A_REGION >> 4);
-          if (p.debug & 1) {
-            // feed-rate experiment: consume the stage without issuing MMAs
-          } else if (PASSES == 6) {
-            // x_H w_H: four K=16 fp16 MMAs; x_L w_C: two K=32 e4m3 MMAs
 #pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
-                                       (kb | k) != 0 ? 1u : 0u);
-            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
-            const uint64_t b_c0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_REGION + Cfg::B_PLANE_BYTES) >> 4);
-#pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k)
-              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_c0 + 2 * k, idesc, 1u);
-          } else if (PASSES == 2) {
-            // x_H w_H: four K=16 fp16 MMAs; x_L w_C and x_C w_L: two K=32 e4m3 MMAs each (the
-            // e4m3 tile sits behind the fp16 tile)
-            if (!(p.debug & 4)) {
+          for (int j = 0; j < KA; ++j) {
+            // descriptor low word counts 16-byte units: stage / atom / plane / K-step offsets are adds
+            const uint32_t a_off = stage * Cfg::STAGE_BYTES + j * Cfg::A_REGION;
+            const uint32_t b_off = stage * Cfg::STAGE_BYTES + KA * Cfg::A_REGION + j * Cfg::B_REGION;
+            const uint64_t a_hi0 = desc0 + (a_off >> 4);
+            const uint64_t b_hi0 = desc0 + (b_off >> 4);
+            const bool go = leader && (KA == 1 || kb + j < p.num_kb);   // the last round may be short
+            const uint32_t first = (kb | j) != 0 ? 1u : 0u;
+            if (p.debug & 1) {
+              // feed-rate experiment: consume the stage without issuing MMAs
+            } else if (PASSES == 6) {
+              // x_H w_H: four K=16 fp16 MMAs; x_L w_C: two K=32 e4m3 MMAs
 #pragma unroll
               for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
-                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc,
-                                         (kb | k) != 0 ? 1u : 0u);
-            }
-            const uint64_t a_l0 = desc8 + ((stage * Cfg::STAGE_BYTES + Cfg::A_PLANE_BYTES) >> 4);
-            const uint64_t b_l0 = a_l0 + (Cfg::A_REGION >> 4);
-            constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
-            if (!(p.debug & 2))
+                ptx::mma_bf16_ss_pair_if(go, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc, k != 0 ? 1u : first);
+              const uint64_t a_l0 = desc8 + ((a_off + Cfg::A_PLANE_BYTES) >> 4);
+              const uint64_t b_c0 = desc8 + ((b_off + Cfg::B_PLANE_BYTES) >> 4);
 #pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
-              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
-              ptx::mma_f8_ss_pair_if(leader, d_tmem, a_l0 + kCoarse + 2 * k, b_l0 + 2 * k, idesc, 1u);
-            }
-          } else {
+              for (int k = 0; k < Cfg::BLOCK_K / 32; ++k)
+                ptx::mma_f8_ss_pair_if(go, d_tmem, a_l0 + 2 * k, b_c0 + 2 * k, idesc, 1u);
+            } else if (PASSES == 2) {
+              // x_H w_H: four K=16 fp16 MMAs; x_L w_C and x_C w_L: two K=32 e4m3 MMAs each (the
+              // e4m3 tile sits behind the fp16 tile)
+              if (!(p.debug & 4)) {
 #pragma unroll
-            for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
-              const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
-              ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi, idesc, (kb | k) != 0 ? 1u : 0u);
-              if (PASSES == 3) {
-                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
-                ptx::mma_bf16_ss_pair_if(leader, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+                for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k)
+                  ptx::mma_bf16_ss_pair_if(go, d_tmem, a_hi0 + 2 * k, b_hi0 + 2 * k, idesc, k != 0 ? 1u : first);
+              }
+              const uint64_t a_l0 = desc8 + ((a_off + Cfg::A_PLANE_BYTES) >> 4);
+              const uint64_t b_l0 = desc8 + ((b_off + Cfg::B_PLANE_BYTES) >> 4);
+              constexpr uint64_t kCoarse = (Cfg::A_PLANE_BYTES / 2) >> 4;
+              if (!(p.debug & 2))
+#pragma unroll
+              for (int k = 0; k < Cfg::BLOCK_K / 32; ++k) {
+                ptx::mma_f8_ss_pair_if(go, d_tmem, a_l0 + 2 * k, b_l0 + kCoarse + 2 * k, idesc, 1u);
+                ptx::mma_f8_ss_pair_if(go, d_tmem, a_l0 + kCoarse + 2 * k, b_l0 + 2 * k, idesc, 1u);
+              }
+            } else {
+#pragma unroll
+              for (int k = 0; k < Cfg::BLOCK_K / Cfg::UMMA_K; ++k) {
+                const uint64_t a_hi = a_hi0 + 2 * k, b_hi = b_hi0 + 2 * k;
+                ptx::mma_bf16_ss_pair_if(go, d_tmem, a_hi, b_hi, idesc, k != 0 ? 1u : first);
+                if (PASSES == 3) {
+                  ptx::mma_bf16_ss_pair_if(go, d_tmem, a_hi + (Cfg::A_PLANE_BYTES >> 4), b_hi, idesc, 1u);
+                  ptx::mma_bf16_ss_pair_if(go, d_tmem, a_hi, b_hi + (Cfg::B_PLANE_BYTES >> 4), idesc, 1u);
+                }
               }
             }
           }
+          kb += KA;
           ptx::mma_commit_pair_if(leader, &empty_bar[stage], 0x3);  // frees the slot in both CTAs
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
