@@ -92,7 +92,7 @@ int run_core(const AclipTemporalWeights& w, long long cs, float* P, float* A1, v
   // GEMMs (94 % of this stage's flops; ~9e-5 on the scores, which scale every class alike and so
   // cannot change a class index) at any chunk size; every other GEMM of this stage runs three passes
   const bool want8 = passes == 2 && E % 256 == 0 && rows >= 4096;
-  const bool want16 = passes == 4 && E % 256 == 0;
+  const bool want16 = passes == 4 && E % 64 == 0;   // single-CTA tiles serve any N % 32 (XD: E = 128)
   if (passes == 2 || passes == 4) passes = 3;
   const float* x1 = P;  // both reversible streams start as the same tensor
   for (int d = 0; d < w.depth; ++d) {

@@ -349,7 +349,9 @@ class PackedTemporal:
                 w2 = sd[q + "3.weight"].to(torch.float32).permute(0, 2, 3, 1).reshape(E, 36 * E)
                 c.conv1_w, c.conv1_b = spl(w1), f32t(sd[q + "1.bias"])
                 c.conv2_w, c.conv2_b = spl(w2), f32t(sd[q + "3.bias"])
-                if E % 256 == 0:  # f16f8 copies for passes = 2 calls on large chunks (CTA-pair kernel)
+                # f16f8 copies: passes = 2 calls on large chunks (CTA-pair kernel, E % 256 == 0) read
+                # all three planes, passes = 4 (one pass, any tile) the fp16 plane
+                if E % 64 == 0:
                     for name, wt in (("conv1", w1), ("conv2", w2)):
                         e8 = ops.encode_f16f8(_dev_f32(wt, device), weight=True)
                         keep.append(e8)

@@ -265,7 +265,8 @@ typedef struct AclipConvFFWeights {   /* ChanLayerNorm -> conv3x3 -> LeakyReLU -
   const void* conv1_w; const float* conv1_b; /* split [2][4E][9*E], k = (ky*3+kx)*E + c */
   const void* conv2_w; const float* conv2_b; /* split [2][E][9*4E] */
   /* optional (NULL = absent): the same two weights as f16f8 planes and their accumulator scales
-   * 2^-(4 + e_weight); used by passes = 2 calls whose chunk has >= 4096 rows and E % 256 == 0 */
+   * 2^-(4 + e_weight); used by passes = 2 calls whose chunk has >= 4096 rows and E % 256 == 0
+   * (all three planes) and by passes = 4 calls with E % 64 == 0 (the fp16 plane, one pass) */
   const void* conv1_w8; const void* conv2_w8;
   float conv1_s, conv2_s;
 } AclipConvFFWeights;

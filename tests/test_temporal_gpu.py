@@ -123,7 +123,7 @@ def test_f16f8_conv_mode_on_a_large_chunk_matches_oracle(name):
 
 
 @pytest.mark.parametrize("name,units", [("ucfcrime", 1), ("ucfcrime", 3), ("shanghaitech", 2),
-                                        ("ucfcrime", 64)])
+                                        ("ucfcrime", 64), ("xdviolence", 1), ("xdviolence", 9)])
 def test_fp16_conv_mode_matches_oracle(name, units):
     """passes=4: the conv feed-forward GEMMs (94 % of the stage's flops) on fp16 operands in ONE pass
     at any chunk size (single-CTA kernel for a few sub-videos, CTA pairs from 8 up).  Scores stay
