@@ -18,7 +18,7 @@
 //                ~2^-12 relative per product, selected by the host after calibration (split.cuh)
 //
 // Two kernels share the producer / issuer / epilogue code:
-//   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile                    (192 threads)
+//   gemm_tcgen05_kernel   one CTA per 128 x {64,128,256} tile, or per 64 x 32    (192 threads)
 //   gemm2_tcgen05_kernel  a CTA pair (cta_group::2) per 256 x 256 tile           (320 threads per CTA)
 // (A four-CTA variant sharing the W tile by TMA multicast was measured in round 1: ~8 % faster per
 // SM but only 33 clusters of four are co-resident on 148 SMs, a net loss; removed.)
@@ -91,12 +91,12 @@ struct GemmParams {
 #define ACLIP_KATOMS_PAIR 1
 #endif
 
-// KATOMS: 64-wide K atoms (one 128-byte swizzle row each) per barrier round.  A round costs the SM
-// one L2 round trip whatever it carries (measured: ~230 ns per round for 12 KB and for 24 KB, for
-// one TMA operation and for two, with the operand ring 3 or 12 deep, with or without MMAs), so the
-// small tile moves four atoms per round.
-// Tiles whose MMAs per atom take less than a round (one product per atom on a tile of <= 128
-// columns) carry two atoms per round, the 64 x 32 tile four.
+// KATOMS: 64-wide K atoms (one 128-byte swizzle row each) per barrier round of the operand ring.
+// A round (TMA -> mbarrier -> MMA -> commit -> producer) costs an SM ~230 ns whatever it carries:
+// measured the same for 12 KB and 24 KB, one TMA operation and two, a ring 3 or 12 deep, with MMAs
+// or none, 1 or 128 CTAs on the machine (profiles/r2_small_gemm_round_trip_experiments.txt).
+// Tiles whose MMAs per atom are shorter than that (one product per atom on <= 128 columns) carry
+// two atoms per round, the 64 x 32 tile four.
 constexpr int default_katoms(int block_n, int passes, int block_m) {
   return block_m == 64 ? 4 : ((passes == 1 || passes == 4) && block_n <= 128) ? ACLIP_KATOMS_NARROW : 1;
 }
