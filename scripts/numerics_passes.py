@@ -10,6 +10,9 @@ kind (in_proj, out_proj, c_fc, c_proj, proj) this script selects
     xh     drop x_L w_C: the activations travel as fp16 only 1.5
     h      fp16 x fp16 only                                  1
     b3     split-bf16 x3 (what out_proj runs today)          3
+    mx4    both cross terms as MXFP4 (e2m1 elements, one power-of-two scale per 32 values along K:
+           tcgen05 kind::mxf4, 4x the fp16 rate)             1.5   -- a study of the NEXT operand
+           mode, not something the kernels implement
 
 and prints the rel-L2 / max error of the final features against the plain fp32 oracle.
 
@@ -43,6 +46,23 @@ def _bf16(v):
     return v.to(torch.bfloat16).to(torch.float64)
 
 
+_E2M1 = torch.tensor([0, .5, 1, 1.5, 2, 3, 4, 6], dtype=torch.float64)
+
+
+def _mxfp4(v, block=32):
+    """[rows, K] -> MXFP4 along K: per (row, 32 values) a power-of-two scale chosen so that the
+    block maximum fits (<= 6), elements rounded to the nearest e2m1 value."""
+    r, k = v.shape
+    pad = (-k) % block
+    if pad:
+        v = torch.cat((v, v.new_zeros(r, pad)), 1)
+    b = v.reshape(r, -1, block)
+    s = torch.exp2(torch.ceil(torch.log2(b.abs().amax(-1, keepdim=True).clamp_min(1e-300) / 6.0)))
+    q = b / s
+    idx = (q.abs().unsqueeze(-1) - _E2M1).abs().argmin(-1)
+    return (torch.sign(q) * _E2M1[idx] * s).reshape(r, -1)[:, :k]
+
+
 def kind_of(w: torch.Tensor, width: int) -> str:
     n, k = w.shape
     if (n, k) == (3 * width, width):
@@ -66,6 +86,11 @@ def emulate(x, w, mode):
     xs, ws = x64 * 2.0 ** SX, w64 * 2.0 ** sw
     xh, wh = xs.float().half().double(), ws.float().half().double()
     acc = xh @ wh.T
+    if mode == "mx4":
+        lead = xs.shape[:-1]
+        x2, xh2 = xs.reshape(-1, xs.shape[-1]), xh.reshape(-1, xs.shape[-1])
+        acc2 = _mxfp4(x2 - xh2) @ _mxfp4(ws).T + _mxfp4(x2) @ _mxfp4(ws - wh).T
+        return (acc + acc2.reshape(*lead, -1)) * 2.0 ** -(SX + sw)
     if mode in ("full", "wh"):
         xl = _e4m3((xs - xh) * 2.0 ** TX)
         wc = _e4m3(w64 * 2.0 ** (sw - TX))
@@ -109,6 +134,11 @@ def main() -> None:
              "all wh (1.5)": {k: "wh" for k in kinds},
              "all xh (1.5)": {k: "xh" for k in kinds},
              "all h (1.0)": {k: "h" for k in kinds}}
+    att_h = {"in_proj": "h", "out_proj": "h"}
+    cases["mixed = mode 5: attention side h, MLP full (1.64)"] = {**att_h, "c_fc": "full", "c_proj": "full"}
+    cases["mode 6: mode 5 with c_proj wh (1.48)"] = {**att_h, "c_fc": "full", "c_proj": "wh"}
+    cases["NEXT: attention side h, MLP mx4 (1.33)"] = {**att_h, "c_fc": "mx4", "c_proj": "mx4"}
+    cases["NEXT: every GEMM mx4 (1.5)"] = {k: "mx4" for k in kinds}
     for k in kinds:
         for m in ("wh", "xh", "h"):
             cases[f"only {k} -> {m}"] = {**{q: "full" for q in kinds}, k: m}
