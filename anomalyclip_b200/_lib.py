@@ -99,6 +99,8 @@ SIGNATURES = {
     "aclip_split_f32": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong, vp]),
     "aclip_encode_f16f8": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_longlong,
                                      C.c_int, C.c_int, C.c_int, vp]),
+    "aclip_f16mx_bytes": (C.c_longlong, [C.c_longlong, C.c_int]),
+    "aclip_encode_f16mx": (C.c_int, [vp, C.c_longlong, C.c_int, C.c_int, vp, C.c_int, C.c_int, vp]),
     "aclip_center_regroup": (C.c_int, [vp, C.c_longlong, C.c_int, vp, C.c_int, C.c_int, C.c_int, vp,
                                        C.c_int, C.c_longlong, vp]),
     "aclip_patchify": (C.c_int, [vp, C.c_int, C.c_int, C.c_int, C.c_int, C.POINTER(C.c_float),

@@ -23,6 +23,8 @@ int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, i
               long long plane_stride, cudaStream_t stream);
 int encode_f16f8(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
                  long long plane_stride, int e_main, int e_res, int e_coarse, cudaStream_t stream);
+int encode_f16mx(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out, int e_main,
+                 cudaStream_t stream);
 int layernorm(const float* x, long long rows, int D, long long ldx, const float* gamma,
               const float* beta, float eps, int mode, float* out_f32, long long ld_f32,
               void* out_split, long long ld_split, long long plane_stride, int out_enc,

@@ -78,6 +78,62 @@ class F16F8:
         return (h.double() + l.to(torch.float32).double() * 2.0 ** -e_res) * 2.0 ** -self.exp
 
 
+_E2M1 = (0.0, 0.5, 1.0, 1.5, 2.0, 3.0, 4.0, 6.0)
+
+
+class F16MX:
+    """An fp32 [rows, ld] tensor in the f16mx operand encoding (csrc/mx.cuh): one zero-initialised
+    uint8 buffer = fp16 plane H | packed e2m1 planes L4, C4 | chunked UE8M0 scale bytes."""
+
+    def __init__(self, rows: int, ld: int, device, exp: int = ACT_EXP[0]) -> None:
+        if ld % 64 != 0:
+            raise ValueError("f16mx rows must be a multiple of 64 elements wide")
+        self.rows, self.ld, self.exp = rows, ld, exp
+        self.row_blocks = (rows + 127) // 128
+        self.buf = torch.zeros(3 * rows * ld + (ld // 64) * self.row_blocks * 512, dtype=torch.uint8, device=device)
+
+    @property
+    def plane_stride(self) -> int:
+        return self.rows * self.ld
+
+    def data_ptr(self) -> int:
+        return self.buf.data_ptr()
+
+    def planes(self):
+        """(H fp16 [rows, ld], L4 values, C4 values as fp64 [rows, ld] with their block scales applied)."""
+        P, rows, ld = self.plane_stride, self.rows, self.ld
+        h = self.buf[: 2 * P].view(torch.float16).reshape(rows, ld)
+        grid = torch.tensor(_E2M1 + tuple(-v for v in _E2M1), dtype=torch.float64, device=self.buf.device)
+        sf = self.buf[3 * P:].reshape(ld // 64, self.row_blocks, 32, 4, 4).double()   # [atom][block][m & 31][m >> 5][byte]
+        m = torch.arange(rows, device=self.buf.device)
+        out = []
+        for plane, byte0 in ((0, 0), (1, 2)):
+            q = self.buf[2 * P + plane * (P // 2): 2 * P + (plane + 1) * (P // 2)].reshape(rows, ld // 2)
+            nib = torch.stack((q & 15, q >> 4), dim=-1).reshape(rows, ld).long()
+            vals = grid[nib]
+            s = sf[:, m >> 7, m & 31, (m >> 5) & 3][..., byte0:byte0 + 2]            # [atom][rows][2]
+            s = torch.exp2(s - 127.0).permute(1, 0, 2).reshape(rows, ld // 32)       # per 32-value block
+            out.append(vals * s.repeat_interleave(32, dim=1))
+        return h, out[0], out[1]
+
+    def decode(self) -> torch.Tensor:
+        """H + L4 back to fp64 values (what the GEMM effectively multiplies)."""
+        h, l4, _ = self.planes()
+        return (h.double() + l4) * 2.0 ** -self.exp
+
+
+def encode_f16mx(x: torch.Tensor, *, weight: bool = False, ld_out: Optional[int] = None) -> F16MX:
+    """fp32 [rows, cols] -> f16mx planes; weight=True picks the per-tensor exponent."""
+    x = _f32c(x, "x")
+    rows, cols = x.reshape(-1, x.shape[-1]).shape
+    ld = ld_out if ld_out is not None else (cols + 63) // 64 * 64
+    out = F16MX(rows, ld, x.device, weight_exponent(x) if weight else ACT_EXP[0])
+    lib = _lib.load()
+    assert lib.aclip_f16mx_bytes(rows, ld) == out.buf.numel()
+    _lib.check(lib.aclip_encode_f16mx(x.data_ptr(), rows, cols, cols, out.data_ptr(), ld, out.exp, _stream()))
+    return out
+
+
 def weight_exponent(w: torch.Tensor) -> int:
     """e_main of a weight tensor: max|w| * 2^e in (2^14, 2^15]  (fp16 main plane stays finite)."""
     m = float(w.abs().max())

@@ -92,6 +92,16 @@ int aclip_encode_f16f8(const float* in, long long rows, int cols, int ld_in, voi
                        int ld_out, long long plane_stride, int e_main, int e_res, int e_coarse,
                        void* stream);
 
+/* fp32 [rows][cols] -> an f16mx tensor [rows][ld_out] (ld_out % 64 == 0): fp16 plane of
+ * v * 2^e_main, two MXFP4 planes (residual of the fp16 plane; coarse copy: e2m1 elements, one
+ * UE8M0 scale per 32 values along a row) and the scale bytes in the chunked layout the block-scaled
+ * tensor-core instruction reads (csrc/mx.cuh).  `out` holds aclip_f16mx_bytes(rows, ld_out) bytes
+ * and must be zero-filled by the caller before the first use (scale bytes of rows that do not
+ * exist stay 0).  Operand of aclip_gemm with passes = 7. */
+long long aclip_f16mx_bytes(long long rows, int ld);
+int aclip_encode_f16mx(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
+                       int e_main, void* stream);
+
 /* (x - centroid) of fp32 feature rows [rows][D] -> split-bf16 rows of pitch ld_out, regrouped from
  * the caller's "(b n s l)" order to sub-video order "(b s) n l" (temporal_model.py:46-53);
  * n = s = l = 1 keeps the order.  Replaces the two centroid subtractions of the reference

@@ -1,0 +1,64 @@
+"""The f16mx operand encoding (csrc/mx.cuh: fp16 plane + two MXFP4 planes with UE8M0 block scales)
+and the GEMM that multiplies it (aclip_gemm passes = 7)."""
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def ops():
+    from anomalyclip_b200 import ops as _ops
+    return _ops
+
+
+def _emulate_planes(x, e_main):
+    """torch restatement of mx_pack32: H, L4, C4 as fp64 values in units of 2^e_main."""
+    grid = torch.tensor([0, .5, 1, 1.5, 2, 3, 4, 6], dtype=torch.float64, device=x.device)
+    xs = (x.float() * 2.0 ** e_main)
+    h = xs.half().double()
+    def mx(v):
+        r, k = v.shape
+        b = v.reshape(r, k // 32, 32)
+        amax = b.abs().amax(-1, keepdim=True)
+        t = (amax.float() * torch.tensor(1.0 / 6.0, dtype=torch.float32, device=x.device))
+        bits = t.view(torch.int32)
+        e = (bits >> 23) + ((bits & 0x7fffff) != 0).int()
+        s = torch.exp2(e.double() - 127.0)
+        q = (b / s).float().double()
+        a = q.abs().clamp(max=6.0)
+        # round to nearest, ties to even mantissa (cvt.rn): candidates sorted, pick nearest; ties -> even index
+        d = (a.unsqueeze(-1) - grid).abs()
+        idx = d.argmin(-1)
+        lo = (idx - 1).clamp(min=0)
+        tie_lo = (d.gather(-1, lo.unsqueeze(-1)).squeeze(-1) == d.gather(-1, idx.unsqueeze(-1)).squeeze(-1)) & (lo != idx)
+        idx = torch.where(tie_lo & (lo % 2 == 0), lo, idx)
+        hi = (idx + 1).clamp(max=7)
+        tie_hi = (d.gather(-1, hi.unsqueeze(-1)).squeeze(-1) == d.gather(-1, idx.unsqueeze(-1)).squeeze(-1)) & (hi != idx)
+        idx = torch.where(tie_hi & (hi % 2 == 0), hi, idx)
+        return (torch.sign(q) * grid[idx] * s).reshape(r, k)
+    return h, mx((xs.double() - h).float().double()), mx(xs.double())
+
+
+@pytest.mark.parametrize("rows,cols", [(128, 64), (300, 768), (197, 3072), (1, 100)])
+def test_encode_f16mx_planes(ops, rows, cols):
+    torch.manual_seed(rows + cols)
+    x = torch.randn(rows, cols, device="cuda") * torch.logspace(-2, 1, cols, device="cuda")
+    enc = ops.encode_f16mx(x)
+    ld = enc.ld
+    xp = torch.zeros(rows, ld, device="cuda")
+    xp[:, :cols] = x
+    h, l4, c4 = enc.planes()
+    eh, el4, ec4 = _emulate_planes(xp, enc.exp)
+    assert torch.equal(h.double(), eh)
+    # scale bytes and elements follow the restatement (ties of the e2m1 rounding may differ by one grid step)
+    for got, want, name in ((l4, el4, "L4"), (c4, ec4, "C4")):
+        bad = (got != want).double().mean().item()
+        assert bad < 2e-3, f"{name}: {bad:.2e} of the elements differ from the restatement"
+    # H + L4 reconstructs the value to a quarter of an fp16 ulp of its 32-block's residual range
+    rec = enc.decode()[:, :cols]
+    rel = ((rec - x.double()).norm() / x.double().norm()).item()
+    assert rel < 1.2e-4, rel
+    assert ((c4 * 2.0 ** -enc.exp)[:, :cols] - x.double()).norm() / x.double().norm() < 0.2
+    w = ops.encode_f16mx(x * 1e-3, weight=True)
+    assert ((w.decode()[:, :cols] - (x * 1e-3).double()).norm() / (x * 1e-3).double().norm()).item() < 1.2e-4
