@@ -18,6 +18,7 @@ int sm_count();
 unsigned int* saturation_counter();
 extern std::atomic<long long> g_launches;  // kernels launched by this library
 int gemm(const AclipGemmArgs& g, cudaStream_t stream);
+int gemm_mx(const AclipGemmArgs& g, cudaStream_t stream);   // passes == 7
 struct RowMap;
 int split_f32(const float* in, long long rows, int cols, int ld_in, void* out, int ld_out,
               long long plane_stride, cudaStream_t stream);

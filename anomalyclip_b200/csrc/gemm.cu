@@ -69,10 +69,10 @@ static EncodeTiledFn encode_tiled_fn() {
 
 // bf16 tensor map with the 128-byte swizzle; dims/strides innermost first, strides in bytes for
 // dims 1..rank-1.
-static int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
-                     const cuuint64_t* strides_bytes, const cuuint32_t* box,
-                     CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
-                     CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
+int make_tmap(CUtensorMap* map, const void* base, int rank, const cuuint64_t* dims,
+              const cuuint64_t* strides_bytes, const cuuint32_t* box,
+              CUtensorMapDataType dtype = CU_TENSOR_MAP_DATA_TYPE_BFLOAT16,
+              CUtensorMapSwizzle swizzle = CU_TENSOR_MAP_SWIZZLE_128B) {
   EncodeTiledFn fn = encode_tiled_fn();
   if (fn == nullptr) return fail(ACLIP_ERR_CUDA, "cuTensorMapEncodeTiled is not available");
   cuuint32_t elem_strides[5] = {1, 1, 1, 1, 1};
@@ -156,8 +156,9 @@ static int launch_pair(const CUtensorMap& tmA, const CUtensorMap& tmB, const CUt
 int gemm(const AclipGemmArgs& g, cudaStream_t stream) {
   ACLIP_REQUIRE(g.a != nullptr && g.w != nullptr, "gemm: null operand");
   ACLIP_REQUIRE(g.M > 0 && g.N > 0 && g.K > 0, "gemm: empty problem M=%d N=%d K=%d", g.M, g.N, g.K);
+  if (g.passes == 7) return gemm_mx(g, stream);   // f16mx operands (gemm_mx.cu)
   ACLIP_REQUIRE((g.passes >= 1 && g.passes <= 4) || g.passes == 6,
-                "gemm: passes must be 1, 2, 3, 4 or 6 (got %d)", g.passes);
+                "gemm: passes must be 1, 2, 3, 4, 6 or 7 (got %d)", g.passes);
   ACLIP_REQUIRE(g.out_enc >= 0 && g.out_enc <= 2,
                 "gemm: out_enc must be 0 (bf16 hi/lo), 1 (f16f8) or 2 (fp16 plane)");
   if (g.passes == 4) {

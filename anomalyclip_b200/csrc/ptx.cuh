@@ -296,6 +296,35 @@ __device__ __forceinline__ void mma_f8_ss_pair_if(bool issue, uint32_t d_tmem, u
       "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(static_cast<uint32_t>(issue))
       : "memory");
 }
+// Block-scaled MXFP4 (kind::mxf4: packed e2m1 operands, one UE8M0 scale per 32 values along K,
+// K = 64 per instruction, four times the kind::f16 rate); the scale factors of A and B sit in TMEM
+// at tsfa / tsfb (csrc/mx.cuh), the byte pair they occupy there is selected in the descriptor.
+__device__ __forceinline__ void mma_mxf4_ss_pair_if(bool issue, uint32_t d_tmem, uint64_t a_desc,
+                                                    uint64_t b_desc, uint32_t idesc, uint32_t tsfa,
+                                                    uint32_t tsfb, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred p, q;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "setp.ne.b32 q, %7, 0;\n\t"
+      "@q tcgen05.mma.cta_group::2.kind::mxf4.block_scale.block32 [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+      "}\n" ::"r"(d_tmem),
+      "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate), "r"(tsfa), "r"(tsfb),
+      "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
+// Shared memory -> TMEM copy of one 32 x 16-byte chunk (scale factors of 128 rows), replicated into
+// the four lane quarters, in BOTH CTAs of the pair from their own shared memory at `sdesc`.
+__device__ __forceinline__ void tmem_cp_32x128b_pair_if(bool issue, uint32_t taddr, uint64_t sdesc) {
+  asm volatile(
+      "{\n\t"
+      ".reg .pred q;\n\t"
+      "setp.ne.b32 q, %2, 0;\n\t"
+      "@q tcgen05.cp.cta_group::2.32x128b.warpx4 [%0], %1;\n\t"
+      "}\n" ::"r"(taddr),
+      "l"(sdesc), "r"(static_cast<uint32_t>(issue))
+      : "memory");
+}
 __device__ __forceinline__ void mma_commit_pair_if(bool issue, uint64_t* bar, uint16_t cta_mask) {
   asm volatile(
       "{\n\t"
@@ -341,6 +370,36 @@ __device__ __forceinline__ uint64_t make_kmajor_sw64_desc(uint32_t smem_addr) {
   d |= static_cast<uint64_t>(1) << 46;
   d |= static_cast<uint64_t>(4) << 61;
   return d;
+}
+
+// Rows of 32 B (64 packed e2m1 values) stored with the 32-byte swizzle (TMA SWIZZLE_32B): the swizzle
+// atom is 8 rows x 32 B = 256 B, so SBO = 256 B.  Layout type 6 = SWIZZLE_32B.
+__device__ __forceinline__ uint64_t make_kmajor_sw32_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(1) << 16;
+  d |= static_cast<uint64_t>(256 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  d |= static_cast<uint64_t>(6) << 61;
+  return d;
+}
+// Unswizzled 32 rows x 16 B chunk (source of tcgen05.cp 32x128b): rows 16 B apart, 8-row groups
+// 128 B apart (SBO), a single 16-byte column (LBO unused).
+__device__ __forceinline__ uint64_t make_chunk16_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= static_cast<uint64_t>((smem_addr & 0x3FFFF) >> 4);
+  d |= static_cast<uint64_t>(128 >> 4) << 32;
+  d |= static_cast<uint64_t>(1) << 46;
+  return d;
+}
+
+// Instruction descriptor of the block-scaled kind::mxf4 MMA: e2m1 x e2m1 (format code 1), UE8M0
+// scales, both operands K-major, K = 64; a_sf / b_sf = first byte (0 or 2) of the scale pair in the
+// operand's TMEM scale columns.
+__host__ __device__ constexpr uint32_t make_idesc_mxf4(int m, int n, int a_sf, int b_sf) {
+  return (static_cast<uint32_t>(b_sf) << 4) | (1u << 7) | (1u << 10) |
+         (static_cast<uint32_t>(n >> 3) << 17) | (1u << 23) | (static_cast<uint32_t>(m >> 4) << 24) |
+         (static_cast<uint32_t>(a_sf) << 29);
 }
 
 // Instruction descriptor with operand format code 0 for A and B: fp16 x fp16 under kind::f16,

@@ -200,6 +200,17 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.a_plane_stride, g.w_plane_stride = a.numel(), w.plane_stride
         g.out_scale = 2.0 ** -(ACT_EXP[0] + w.exp)
         dev = a.device
+    elif passes == 7:        # f16mx operands (fp16 plane + two MXFP4 cross-term planes)
+        if not (isinstance(a, F16MX) and isinstance(w, F16MX)):
+            raise TypeError("gemm(passes=7) needs F16MX operands")
+        if conv is not None:
+            raise ValueError("gemm(passes=7): linear operands only")
+        M, N = a.rows, w.rows
+        Kk = K if K is not None else a.ld
+        g.lda, g.ldw = a.ld, w.ld
+        g.a_plane_stride, g.w_plane_stride = a.plane_stride, w.plane_stride
+        g.out_scale = 2.0 ** -(a.exp + w.exp)
+        dev = a.buf.device
     elif passes in (2, 6):   # 6: f16f8 operands without the weight-residual cross term
         if not (isinstance(a, F16F8) and isinstance(w, F16F8)):
             raise TypeError("gemm(passes=2 / 6) needs F16F8 operands")
@@ -239,7 +250,9 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
         g.residual, g.ldr = residual.data_ptr(), residual.stride(-2)
     rows = out_rows if out_rows is not None else M
     if out_f32 is None and out_split is None:
-        if want_split and out_enc == 1:
+        if want_split and out_enc == 3:
+            out_split = F16MX(rows, N, dev)
+        elif want_split and out_enc == 1:
             out_split = F16F8(rows, N, dev)
         elif want_split and out_enc == 2:
             out_split = torch.empty((rows, N), dtype=torch.float16, device=dev)
@@ -249,7 +262,7 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
             out_f32 = torch.empty((rows, N), dtype=torch.float32, device=dev)
     if out_f32 is not None:
         g.out_f32, g.ldc = out_f32.data_ptr(), out_f32.stride(-2)
-    if isinstance(out_split, F16F8):
+    if isinstance(out_split, (F16F8, F16MX)):
         g.out_split, g.ld_split = out_split.data_ptr(), out_split.ld
         g.split_plane_stride = out_split.plane_stride
     elif out_split is not None and out_split.dtype == torch.float16:

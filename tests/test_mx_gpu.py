@@ -62,3 +62,38 @@ def test_encode_f16mx_planes(ops, rows, cols):
     assert ((c4 * 2.0 ** -enc.exp)[:, :cols] - x.double()).norm() / x.double().norm() < 0.2
     w = ops.encode_f16mx(x * 1e-3, weight=True)
     assert ((w.decode()[:, :cols] - (x * 1e-3).double()).norm() / (x * 1e-3).double().norm()).item() < 1.2e-4
+
+
+def _rel(a, b):
+    a, b = a.double(), b.double()
+    return ((a - b).norm() / b.norm().clamp_min(1e-30)).item()
+
+
+def _effective(enc):
+    """What the three MMA products of the GEMM see: (H, L4, C4) as fp64 in real units."""
+    h, l4, c4 = enc.planes()
+    s = 2.0 ** -enc.exp
+    return h.double() * s, l4 * s, c4 * s
+
+
+@pytest.mark.parametrize("M,N,K", [(256, 192, 64), (256, 384, 256), (300, 192, 768), (1000, 768, 3072),
+                                   (197 * 8, 3072, 768), (129, 576, 128)])
+def test_gemm_f16mx(ops, M, N, K):
+    """x_H w_H + x_L4 w_C4 + x_C4 w_L4 on the CTA-pair kernel: against the same three products in
+    fp64 from the decoded planes (tight: checks the operand/scale-factor plumbing), and against the
+    fp64 product of the inputs (the accuracy the mode buys: ~5e-5, fp16 alone ~3e-4)."""
+    torch.manual_seed(M + N + K)
+    a = torch.randn(M, K, device="cuda") * torch.logspace(-1, 1, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    ea, ew = ops.encode_f16mx(a), ops.encode_f16mx(w, weight=True)
+    out = ops.gemm(ea, ew, passes=7)
+    torch.cuda.synchronize()
+    ah, al, ac = _effective(ea)
+    wh, wl, wc = _effective(ew)
+    exact_planes = ah @ wh.T + al @ wc.T + ac @ wl.T
+    e1 = _rel(out, exact_planes)
+    e2 = _rel(out, a.double() @ w.double().T)
+    eh = _rel(ah @ wh.T, a.double() @ w.double().T)
+    print(f"f16mx gemm M={M} N={N} K={K}: vs decoded planes {e1:.2e}, vs fp64 {e2:.2e} (fp16 planes alone {eh:.2e})")
+    assert e1 < 3e-6
+    assert e2 < 1e-4 and e2 < 0.4 * eh
