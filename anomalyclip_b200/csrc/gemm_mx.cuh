@@ -40,45 +40,89 @@ struct GemmMxCfg {
   static_assert(STAGES >= 3, "operand ring too shallow");
 };
 
-// Epilogue of one 32-row x 32-column chunk whose output is an f16mx tensor (the A operand of the
-// next GEMM): a lane holds one row's 32 consecutive columns, which is exactly one scale block of
-// that operand, so packing needs no exchange between lanes.
-__device__ __forceinline__ float epilogue_chunk_mx(const GemmParams& p, const MxOut& out, uint32_t taddr, int n,
-                                                   int m_base, int lane) {
-  uint32_t raw[32];
-  ptx::tmem_ld_32x32(taddr, raw);
-  float4 b4[8];
-  if (p.bias != nullptr) {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
-  } else {
-#pragma unroll
-    for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
-  }
-  ptx::tmem_ld_wait();
+// Epilogue of a warp's 32 rows x (chunks x 32) columns whose output is an f16mx tensor (the A
+// operand of the next GEMM).  A lane holds one row's 32 consecutive columns of a chunk, which is
+// exactly one scale block of that operand, so packing needs no exchange between lanes.  The next
+// chunk's accumulator is requested from TMEM before the current one is processed; the fp16 plane
+// (64 B per row and chunk) goes through the warp's staging buffer so that a store instruction
+// writes 8 rows x 64 contiguous bytes instead of 32 rows x 16; the two e2m1 planes (16 B per row and
+// chunk each) and the scale bytes are stored by the owning lane.
+__device__ __forceinline__ float epilogue_tile_mx(const GemmParams& p, const MxOut& out, uint32_t t_row, int n0,
+                                                  int chunks, int m_base, int lane, uint8_t* stage) {
+  if (m_base >= p.M) return 0.f;   // warp-uniform: the whole 32-row block is padding
+  uint32_t raw[2][32];
+  float amax = 0.f;
   const int m = m_base + lane;
-  float v[32];
+  const bool row_ok = m < p.M;
   const float sc = p.out_scale;
+  ptx::tmem_ld_32x32(t_row, raw[0]);
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    v[4 * j + 0] = fmaf(__uint_as_float(raw[4 * j + 0]), sc, b4[j].x);
-    v[4 * j + 1] = fmaf(__uint_as_float(raw[4 * j + 1]), sc, b4[j].y);
-    v[4 * j + 2] = fmaf(__uint_as_float(raw[4 * j + 2]), sc, b4[j].z);
-    v[4 * j + 3] = fmaf(__uint_as_float(raw[4 * j + 3]), sc, b4[j].w);
+  for (int c = 0; c < 3; ++c) {
+    if (c >= chunks) break;
+    const int n = n0 + c * 32;
+    float4 b4[8];
+    if (p.bias != nullptr) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias + n) + j);
+    } else {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) b4[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    ptx::tmem_ld_wait();
+    if (c + 1 < chunks) ptx::tmem_ld_32x32(t_row + (c + 1) * 32, raw[(c + 1) & 1]);
+    const uint32_t (&r)[32] = raw[c & 1];
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      v[4 * j + 0] = fmaf(__uint_as_float(r[4 * j + 0]), sc, b4[j].x);
+      v[4 * j + 1] = fmaf(__uint_as_float(r[4 * j + 1]), sc, b4[j].y);
+      v[4 * j + 2] = fmaf(__uint_as_float(r[4 * j + 2]), sc, b4[j].z);
+      v[4 * j + 3] = fmaf(__uint_as_float(r[4 * j + 3]), sc, b4[j].w);
+    }
+    if (p.act == ACT_QUICKGELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]) * kActScaleMain;
+    } else if (p.act == ACT_LEAKYRELU) {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] = (v[j] > 0.0f ? v[j] : 0.01f * v[j]) * kActScaleMain;
+    } else {
+#pragma unroll
+      for (int j = 0; j < 32; ++j) v[j] *= kActScaleMain;
+    }
+    uint32_t h[16], l4[4], c4[4], sf_l, sf_c;
+    const float mx = mx_pack32(v, h, l4, c4, sf_l, sf_c);
+    if (row_ok) amax = fmaxf(amax, mx);
+    // fp16 plane through the staging buffer: lane = row, 4 pieces of 16 B, XOR-swizzled by the row pair
+    __syncwarp();   // the previous chunk's readers are done
+#pragma unroll
+    for (int j = 0; j < 4; ++j)
+      *reinterpret_cast<uint4*>(stage + lane * 64 + ((j ^ ((lane >> 1) & 3)) << 4)) =
+          make_uint4(h[4 * j], h[4 * j + 1], h[4 * j + 2], h[4 * j + 3]);
+    __syncwarp();
+    const int piece = lane & 3;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int row = i * 8 + (lane >> 2);
+      const int mm = m_base + row;
+      if (mm < p.M) {
+        const uint4 q = *reinterpret_cast<const uint4*>(stage + row * 64 + ((piece ^ ((row >> 1) & 3)) << 4));
+        *reinterpret_cast<uint4*>(out.base + 2 * (static_cast<long long>(mm + p.row_offset) * out.ld + n) + piece * 16) = q;
+      }
+    }
+    if (row_ok) {
+      const long long mo = m + p.row_offset;
+      const long long e = mo * out.ld + n;
+      *reinterpret_cast<uint4*>(out.base + 2 * out.plane + (e >> 1)) = make_uint4(l4[0], l4[1], l4[2], l4[3]);
+      *reinterpret_cast<uint4*>(out.base + 2 * out.plane + (out.plane >> 1) + (e >> 1)) =
+          make_uint4(c4[0], c4[1], c4[2], c4[3]);
+      const int kb = n >> 5;
+      uint8_t* sf = out.base + 3 * out.plane + (static_cast<long long>(kb >> 1) * out.row_blocks + (mo >> 7)) * 512 +
+                    (mo & 31) * 16 + ((mo >> 5) & 3) * 4 + (kb & 1);
+      sf[0] = static_cast<uint8_t>(sf_l);
+      sf[2] = static_cast<uint8_t>(sf_c);
+    }
   }
-  if (p.act == ACT_QUICKGELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = quick_gelu(v[j]);
-  } else if (p.act == ACT_LEAKYRELU) {
-#pragma unroll
-    for (int j = 0; j < 32; ++j) v[j] = v[j] > 0.0f ? v[j] : 0.01f * v[j];
-  }
-#pragma unroll
-  for (int j = 0; j < 32; ++j) v[j] *= kActScaleMain;
-  uint32_t h[16], l4[4], c4[4], sf_l, sf_c;
-  const float amax = mx_pack32(v, h, l4, c4, sf_l, sf_c);
-  if (m < p.M) mx_store32(out, m + p.row_offset, n, h, l4, c4, sf_l, sf_c);
-  return m < p.M ? amax : 0.f;
+  return amax;
 }
 
 // EPI: 0 generic (fp32 / split outputs through epilogue_chunk), 3 fp32 + residual, 4 f16mx output
@@ -219,10 +263,7 @@ gemm2mx_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
       if (EPI == 3) {
         epilogue_tile_residual(p, t_row, n0, 3, m_base, lane, stage);
       } else if (EPI == 4) {
-        if (m_base < p.M) {
-#pragma unroll 1
-          for (int c = 0; c < 3; ++c) amax = fmaxf(amax, epilogue_chunk_mx(p, mx_out, t_row + c * 32, n0 + c * 32, m_base, lane));
-        }
+        amax = fmaxf(amax, epilogue_tile_mx(p, mx_out, t_row, n0, 3, m_base, lane, stage));
       } else {
 #pragma unroll 1
         for (int c = 0; c < 3; ++c) epilogue_chunk(p, t_row + c * 32, n0 + c * 32, m_base, lane, stage, p.M);

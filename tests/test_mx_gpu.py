@@ -97,3 +97,33 @@ def test_gemm_f16mx(ops, M, N, K):
     print(f"f16mx gemm M={M} N={N} K={K}: vs decoded planes {e1:.2e}, vs fp64 {e2:.2e} (fp16 planes alone {eh:.2e})")
     assert e1 < 3e-6
     assert e2 < 1e-4 and e2 < 0.4 * eh
+
+
+def test_gemm_f16mx_epilogues(ops):
+    """bias + QuickGELU into an f16mx output (c_fc -> c_proj's operand), and bias + fp32 residual in
+    place (c_proj), ragged M."""
+    torch.manual_seed(5)
+    M, N, K = 777, 768, 384
+    a = torch.randn(M, K, device="cuda")
+    w = torch.randn(N, K, device="cuda") * 0.05
+    bias = torch.randn(N, device="cuda")
+    res = torch.randn(M, N, device="cuda")
+    ea, ew = ops.encode_f16mx(a), ops.encode_f16mx(w, weight=True)
+    z = a.double() @ w.double().T + bias.double()
+    gelu = z * torch.sigmoid(1.702 * z)
+    enc = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=7, want_split=True, out_enc=3)
+    assert isinstance(enc, ops.F16MX) and enc.rows == M and enc.ld == N
+    assert _rel(enc.decode(), gelu) < 1.5e-4
+    # the encoded output is what the packer would make of the fp32 result of the same GEMM
+    f32 = ops.gemm(ea, ew, bias=bias, act=ops.ACT_QUICKGELU, passes=7)
+    ref = ops.encode_f16mx(f32)
+    h1, l1, c1 = enc.planes()
+    h2, l2, c2 = ref.planes()
+    assert torch.equal(h1, h2) and torch.equal(l1, l2) and torch.equal(c1, c2)
+    out = res.clone()
+    ops.gemm(ea, ew, bias=bias, residual=out, out_f32=out, passes=7)
+    assert _rel(out, z + res.double()) < 1e-4
+    # and it chains: c_fc -> c_proj on the encoded hidden
+    w2 = torch.randn(192, N, device="cuda") * 0.05
+    y = ops.gemm(enc, ops.encode_f16mx(w2, weight=True), passes=7)
+    assert _rel(y, gelu @ w2.double().T) < 1.5e-4
