@@ -8,6 +8,7 @@
 #include "ptx.cuh"
 #include "rowmap.cuh"
 #include "split.cuh"
+#include "mx.cuh"
 
 namespace aclip {
 
@@ -98,6 +99,42 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
           *reinterpret_cast<uint2*>(dst + plane_stride) = make_uint2(l01, l23);
         } else if (ENC == 1) {
           f16f8_store4_act(out_split, plane_stride, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
+          amax = sat_track(amax, y.x, y.y, y.z, y.w);
+        } else if (ENC == 3) {
+          // f16mx (mx.cuh): 8 consecutive lanes hold one 32-value scale block of the row
+          const float v0 = y.x * kActScaleMain, v1 = y.y * kActScaleMain, v2 = y.z * kActScaleMain,
+                      v3 = y.w * kActScaleMain;
+          uint32_t h01, h23;
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v1), "f"(v0));
+          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v3), "f"(v2));
+          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
+          const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
+          const float r0 = v0 - f01.x, r1 = v1 - f01.y, r2 = v2 - f23.x, r3 = v3 - f23.y;
+          float mv = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
+          float mr = fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
+#pragma unroll
+          for (int o = 4; o > 0; o >>= 1) {
+            mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+            mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+          }
+          const uint32_t sf_l = mx_scale_byte(mr), sf_c = mx_scale_byte(mv);
+          const float il = mx_inv_scale(sf_l), ic = mx_inv_scale(sf_c);
+          const uint32_t l4 = mx_e2m1x2(r0 * il, r1 * il) | (mx_e2m1x2(r2 * il, r3 * il) << 8);
+          const uint32_t c4 = mx_e2m1x2(v0 * ic, v1 * ic) | (mx_e2m1x2(v2 * ic, v3 * ic) << 8);
+          uint8_t* base = reinterpret_cast<uint8_t*>(out_split);
+          const long long e = row * ld_split + 4 * c;
+          *reinterpret_cast<uint2*>(base + 2 * e) = make_uint2(h01, h23);
+          *reinterpret_cast<uint16_t*>(base + 2 * plane_stride + (e >> 1)) = static_cast<uint16_t>(l4);
+          *reinterpret_cast<uint16_t*>(base + 2 * plane_stride + (plane_stride >> 1) + (e >> 1)) =
+              static_cast<uint16_t>(c4);
+          if ((lane & 7) == 0) {
+            const int kb = c >> 3;   // 32-value block of the row
+            const long long row_blocks = (rows + 127) >> 7;
+            uint8_t* sf = base + 3 * plane_stride + (static_cast<long long>(kb >> 1) * row_blocks + (row >> 7)) * 512 +
+                          (row & 31) * 16 + ((row >> 5) & 3) * 4 + (kb & 1);
+            sf[0] = static_cast<uint8_t>(sf_l);
+            sf[2] = static_cast<uint8_t>(sf_c);
+          }
           amax = sat_track(amax, y.x, y.y, y.z, y.w);
         } else {
           f16_store4_act(out_split, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
@@ -246,8 +283,11 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
               cudaStream_t stream) {
   ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
   ACLIP_REQUIRE(out_enc == 0 || out_enc == 2 ||
-                    (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0),
-                "layernorm: out_enc=%d unsupported (f16f8 needs 16-element pitches)", out_enc);
+                    (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0) ||
+                    (out_enc == 3 && mode == 0 && D % 128 == 0 && ld_split % 64 == 0 && ld_split >= D &&
+                     plane_stride == rows * ld_split),
+                "layernorm: out_enc=%d unsupported (f16f8 needs 16-element pitches; f16mx: LayerNorm mode, "
+                "D %% 128 == 0, pitch %% 64 == 0, plane_stride = rows * pitch)", out_enc);
   ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
   ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
                     (out_split == nullptr || ld_split % 4 == 0),
@@ -263,7 +303,8 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   ACLIP_CUDA_OK(launch_pdl(layernorm_kernel<MODE, ENC>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, \
                            D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat))
   if (mode == 0) {
-    if (out_enc == 2) ACLIP_LN(0, 2);
+    if (out_enc == 3) ACLIP_LN(0, 3);
+    else if (out_enc == 2) ACLIP_LN(0, 2);
     else if (out_enc == 1) ACLIP_LN(0, 1);
     else ACLIP_LN(0, 0);
   } else {
@@ -273,7 +314,7 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   }
 #undef ACLIP_LN
   timing_end(KIND_LAYERNORM, stream, 8.0 * rows * D,
-             (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? (out_enc == 2 ? 2.0 : 4.0) : 0.0)));
+             (double)rows * D * (4.0 + (out_f32 ? 4.0 : 0.0) + (out_split ? (out_enc == 2 ? 2.0 : out_enc == 3 ? 3.06 : 4.0) : 0.0)));
   ACLIP_CHECK_LAUNCH();
   g_launches.fetch_add(1, std::memory_order_relaxed);
   return ACLIP_OK;

@@ -284,16 +284,18 @@ def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: 
               chan_mode: bool = False, want_f32: bool = True, want_split: bool = False,
               out_enc: int = 0):
     """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std).
-    out_enc=1: the split output is an `F16F8` activation tensor; out_enc=2: an fp16 tensor."""
+    out_enc=1: the split output is an `F16F8` activation tensor; out_enc=2: an fp16 tensor;
+    out_enc=3: an `F16MX` tensor (D % 128 == 0)."""
     x = _f32c(x, "x")
     rows, D = x.reshape(-1, x.shape[-1]).shape
     out_f32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
     out_split = None
     if want_split:
         out_split = F16F8(rows, D, x.device) if out_enc == 1 else \
+            F16MX(rows, D, x.device) if out_enc == 3 else \
             torch.empty((rows, D), dtype=torch.float16, device=x.device) if out_enc == 2 else \
             torch.empty((2, rows, D), dtype=torch.bfloat16, device=x.device)
-    plane = 0 if out_split is None else (out_split.plane_stride if out_enc == 1 else
+    plane = 0 if out_split is None else (out_split.plane_stride if out_enc in (1, 3) else
                                          out_split.numel() if out_enc == 2 else out_split.stride(0))
     lib = _lib.load()
     _lib.check(lib.aclip_layernorm(

@@ -127,3 +127,17 @@ def test_gemm_f16mx_epilogues(ops):
     w2 = torch.randn(192, N, device="cuda") * 0.05
     y = ops.gemm(enc, ops.encode_f16mx(w2, weight=True), passes=7)
     assert _rel(y, gelu @ w2.double().T) < 1.5e-4
+
+
+def test_layernorm_f16mx_output(ops):
+    """LayerNorm straight into the f16mx encoding = the packer applied to the fp32 LayerNorm output."""
+    torch.manual_seed(9)
+    rows, D = 333, 768
+    x = torch.randn(rows, D, device="cuda") * 3 + 0.5
+    g, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
+    f32, enc = ops.layernorm(x, g, b, want_f32=True, want_split=True, out_enc=3)
+    ref = ops.encode_f16mx(f32)
+    for got, want in zip(enc.planes(), ref.planes()):
+        assert torch.equal(got, want)
+    want = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
+    assert _rel(enc.decode(), want) < 1.5e-4
