@@ -46,7 +46,7 @@ class VitBlock(C.Structure):
     _fields_ = [(n, vp) for n in ("ln1_g", "ln1_b", "ln2_g", "ln2_b", "qkv_w", "qkv_b", "out_w",
                                   "out_b", "fc_w", "fc_b", "proj_w", "proj_b")] + \
                [(n, C.c_float) for n in ("qkv_s", "out_s", "fc_s", "proj_s")] + \
-               [("out_w16", vp)]
+               [("out_w16", vp), ("fc_wmx", vp), ("proj_wmx", vp)]
 
 
 class VitWeights(C.Structure):

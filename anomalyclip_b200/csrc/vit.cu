@@ -105,7 +105,14 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
   ACLIP_TRY(check_weights(w));
   ACLIP_REQUIRE(frames != nullptr && features_out != nullptr, "vit_forward: null frames/output");
   ACLIP_REQUIRE(num_frames >= 0 && micro_batch > 0, "vit_forward: bad frame count / micro-batch");
-  ACLIP_REQUIRE(passes >= 1 && passes <= 6, "vit_forward: passes must be 1 .. 6");
+  ACLIP_REQUIRE(passes >= 1 && passes <= 7, "vit_forward: passes must be 1 .. 7");
+  // 7 = 5 with the MLP pair on f16mx operands (fp16 main product + two MXFP4 cross terms, 1.5
+  // pass-equivalents instead of 2; gemm_mx.cuh): ln_2 writes f16mx, c_fc reads and writes it
+  const bool mlp_mx = passes == 7;
+  if (mlp_mx) {
+    ACLIP_REQUIRE(w.width % 192 == 0, "vit_forward: passes=7 needs a width that is a multiple of 192 (and 256)");
+    passes = 5;
+  }
   ACLIP_REQUIRE(passes == 1 || passes == 3 || (w.width % 256 == 0 && w.output_dim % 256 == 0 &&
                                                (3 * w.patch * w.patch) % 16 == 0),
                 "vit_forward: passes=%d (fp16-based operands) needs width and output_dim multiples of 256",
@@ -187,6 +194,25 @@ extern "C" int aclip_vit_forward_ex(const AclipVitWeights* wp, const void* frame
         g.residual = X; g.ldr = W;
         g.out_f32 = X; g.ldc = W;
         ACLIP_TRY(gemm(g, stream));
+      }
+      if (mlp_mx) {
+        ACLIP_REQUIRE(b.fc_wmx != nullptr && b.proj_wmx != nullptr, "vit_forward: block %d lacks its f16mx weights", l);
+        const long long mw = static_cast<long long>(M) * W;
+        ACLIP_TRY(layernorm(X, M, W, W, b.ln2_g, b.ln2_b, 1e-5f, 0, nullptr, 0, H, W, mw, 3, stream));
+        AclipGemmArgs g = linear(H, mw, M, W, W, b.fc_wmx, 4 * W, 7, b.fc_s);
+        g.out_scale = b.fc_s;
+        g.bias = b.fc_b;
+        g.act = ACLIP_ACT_QUICKGELU;
+        g.out_enc = 3;
+        g.out_split = BIG; g.split_plane_stride = 4 * mw; g.ld_split = 4 * W;
+        ACLIP_TRY(gemm(g, stream));
+        AclipGemmArgs q = linear(BIG, 4 * mw, M, 4 * W, 4 * W, b.proj_wmx, W, 7, b.proj_s);
+        q.out_scale = b.proj_s;
+        q.bias = b.proj_b;
+        q.residual = X; q.ldr = W;
+        q.out_f32 = X; q.ldc = W;
+        ACLIP_TRY(gemm(q, stream));
+        continue;
       }
       ACLIP_TRY(layernorm(X, M, W, W, b.ln2_g, b.ln2_b, 1e-5f, 0, nullptr, 0, H, W, hp, enc, stream));
       {

@@ -64,8 +64,11 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #           `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
 #           automatically: each flips a class index at a reference tie in the end-to-end test, and a
 #           calibration on features cannot vouch for class indices.
+#   7  mixed with the MLP pair on f16mx operands (fp16 main product + two block-scaled MXFP4
+#             cross terms, csrc/mx.cuh): ~1e-4 like mode 5 at 1.33 pass-equivalents; needs a width that
+#             is a multiple of 768 (256 x 192 tiles)
 #   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
-FP16_PACKED_MODES = (2, 4, 5, 6, "auto")
+FP16_PACKED_MODES = (2, 4, 5, 6, 7, "auto")
 AUTO_CANDIDATES = (5,)         # fastest first
 
 
@@ -87,6 +90,8 @@ class PackedVit:
         self.f16f8 = passes in FP16_PACKED_MODES
         conv = sd["conv1.weight"]
         self.width, _, self.patch, _ = conv.shape
+        # f16mx copies of the MLP weights (mode 7; "auto" may select it): 256 x 192 tiles
+        self.mx = passes in (7, "auto") and self.width % 768 == 0
         tokens = sd["positional_embedding"].shape[0]
         grid = int(round((tokens - 1) ** 0.5))
         assert grid * grid + 1 == tokens, "positional_embedding is not a square grid + CLS"
@@ -130,6 +135,11 @@ class PackedVit:
                 b.out_w16, b.out_s = spl(sd[p + "attn.out_proj.weight"])
             (b.fc_w, b.fc_s), b.fc_b = spl(sd[p + "mlp.c_fc.weight"]), f32(p + "mlp.c_fc.bias")
             (b.proj_w, b.proj_s), b.proj_b = spl(sd[p + "mlp.c_proj.weight"]), f32(p + "mlp.c_proj.bias")
+            if self.mx:   # same per-tensor exponent as the f16f8 pack: fc_s / proj_s apply
+                for name, key in (("fc_wmx", "mlp.c_fc.weight"), ("proj_wmx", "mlp.c_proj.weight")):
+                    e = ops.encode_f16mx(_dev_f32(sd[p + key], device), weight=True)
+                    keep.append(e)
+                    setattr(b, name, e.data_ptr())
         w = self.struct = _lib.VitWeights()
         w.width, w.layers, w.heads = self.width, self.layers, self.heads
         w.patch, w.resolution, w.output_dim = self.patch, self.resolution, self.output_dim
@@ -150,8 +160,11 @@ class VitEncoder:
         if passes not in (1, 3) + FP16_PACKED_MODES:
             raise ValueError(f"VitEncoder: unknown operand mode passes={passes!r}")
         if (passes in FP16_PACKED_MODES) != packed.f16f8:
-            raise _lib.AclipError("VitEncoder: passes=2/4/5/6/'auto' need weights packed with "
-                                  "PackedVit(passes=2/4/5/6/'auto') (and only then)")
+            raise _lib.AclipError("VitEncoder: passes=2/4/5/6/7/'auto' need weights packed with "
+                                  "PackedVit(passes=2/4/5/6/7/'auto') (and only then)")
+        if passes == 7 and not packed.mx:
+            raise _lib.AclipError("VitEncoder: passes=7 needs PackedVit(passes=7 or 'auto') and a width that is "
+                                  "a multiple of 768")
         self.packed = packed
         self.micro_batch = micro_batch
         self.passes = passes                              # as requested
@@ -179,6 +192,8 @@ class VitEncoder:
                     "(|x| >= 4094) on this checkpoint: use passes=3 (split-bf16 operands)")
             tried, chosen = {}, 2
             for cand in AUTO_CANDIDATES:
+                if cand == 7 and not self.packed.mx:
+                    continue
                 d = self._run(frames[:k], None, cand).double() - ref
                 sat = _lib.saturation_count(reset=True)
                 rel = float(d.norm() / ref.norm())
@@ -400,7 +415,7 @@ class TemporalScorer:
         shape and replayed (the small-batch path is launch-bound: ~35 kernels and their tensor-map
         encodes per call); 0 disables."""
         self.packed = packed
-        self.passes = "auto" if passes in (5, 6, "auto") else passes
+        self.passes = "auto" if passes in (5, 6, 7, "auto") else passes
         self.mode = None if self.passes == "auto" else self.passes
         self.calib_tol = calib_tol
         self.calibration: Optional[dict] = None

@@ -68,6 +68,12 @@ PRECISION = {
         "mixed with c_proj issued as x_H w_H + x_L w_C only (1.5 pass-equivalents; its weights are "
         "effectively fp16): explicit opt-in, one class index of 512 flips in the end-to-end test",
         (1048 * 1.0 + 930 * 2.0 + 930 * 1.5) / 2908),
+    7: ("f16 operands (attention side, one pass) + f16/MXFP4 cross-term operands (MLP side, 1.5 pass-equivalents), "
+        "f32 accumulate/residual/LayerNorm/softmax",
+        "mixed with the MLP pair (c_fc, c_proj) as fp16 main product + two block-scaled MXFP4 cross-term "
+        "products (tcgen05 kind::mxf4, e2m1 elements, one UE8M0 scale per 32 values along K, 4x the fp16 "
+        "rate); patch-embed / proj stay f16f8; 1.33 bf16-pass equivalents per product on average",
+        (1048 * 1.0 + 1860 * 1.5) / 2908),
 }
 
 
@@ -665,7 +671,7 @@ def run_b200(args) -> None:
         # every operand mode of the same build on the same step, with its own parity figure against
         # the oracle features of the cpu_baseline leg (the headline above ran mode `mode`)
         modes = {}
-        for m_ in (2, 5, 6, 4):
+        for m_ in (2, 5, 7, 6, 4):
             net_m = net if m_ == mode else _build_net(cfg, dev, args.micro_batch, m_)
             ms_m = _time_gpu(lambda: net_m(resident[0], None, module.ncentroid, 1, True), iters=5, warmup=2)
             rec = {"frames_per_s": FRAMES_PER_STEP / (ms_m * 1e-3), "ms_per_step": ms_m,
@@ -677,7 +683,8 @@ def run_b200(args) -> None:
             if net_m is not net:
                 del net_m
         extras["operand_modes"] = {"what": "the same 512-frame step in each operand mode of the image encoder "
-                                           "(2 = f16f8, 5 = mixed, 6 = mixed with c_proj at 1.5 passes, 4 = fp16 one pass); 5 timed calls each",
+                                           "(2 = f16f8, 5 = mixed, 7 = mixed with the MLP pair on MXFP4 cross terms, 6 = mixed with c_proj at 1.5 passes, "
+                                           "4 = fp16 one pass); 5 timed calls each",
                                    "selected": mode, **modes}
     if not args.no_extras:
         extras["strong_scaling_xd"] = _strong_scaling_xd(dev, world, rank, args, barrier, max_over_ranks)
@@ -739,7 +746,7 @@ def main() -> None:
                     help="skip the sub-records measured outside the headline (torch GPU baseline, "
                          "features path, ViT block, strong scaling)")
     ap.add_argument("--micro-batch", type=int, default=256, help="ViT micro-batch (frames per encoder pass)")
-    ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, 5, 6, "auto"), default="auto",
+    ap.add_argument("--passes", type=_passes_arg, choices=(2, 3, 4, 5, 6, 7, "auto"), default="auto",
                     help="GEMM operand mode of the image encoder: 3 = split-bf16 x3, 2 = fp16 + e4m3 cross "
                          "terms (both ~1e-5 on the features), 4 = fp16 operands in one pass (~4e-4), 5 = mixed "
                          "(attention side as 4, MLP side as 2, ~1e-4), 6 = 5 with c_proj at 1.5 passes, auto = 5 if "

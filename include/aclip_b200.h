@@ -219,6 +219,10 @@ typedef struct AclipVitBlock {      /* one ResidualAttentionBlock, clip/model.py
   /* passes = 4 only: attn.out_proj.weight as f16f8 / fp16 planes (its fp16 plane is read) with
    * accumulator scale out_s; NULL otherwise. */
   const void* out_w16;
+  /* passes = 7 only: mlp.c_fc.weight / mlp.c_proj.weight as f16mx tensors (aclip_encode_f16mx with
+   * the same per-tensor exponent as the f16f8 pack, so fc_s / proj_s apply); NULL otherwise. */
+  const void* fc_wmx;
+  const void* proj_wmx;
 } AclipVitBlock;
 
 typedef struct AclipVitWeights {    /* VisionTransformer, clip/model.py:233-264 */
@@ -245,7 +249,9 @@ size_t aclip_vit_workspace_bytes(const AclipVitWeights* w, int micro_batch);
  * passes = 4: fp16 operands end to end, one pass per product (same packed weights plus out_w16);
  * passes = 5: "mixed" -- in_proj, attention and out_proj as passes = 4, the MLP pair, the patch
  * embedding and the output projection as passes = 2 (~1e-4 on the features);
- * passes = 6: as 5, with c_proj issued without its weight-residual cross term (~2e-4). */
+ * passes = 6: as 5, with c_proj issued without its weight-residual cross term (~2e-4);
+ * passes = 7: as 5, with the MLP pair on f16mx operands (fp16 main product + two MXFP4 cross terms:
+ * 1.5 instead of 2 pass-equivalents at the same ~1e-4; width must be a multiple of 768). */
 int aclip_vit_forward(const AclipVitWeights* w, const void* frames, int frames_are_u8,
                       long long num_frames, int micro_batch, const float* mean3_host,
                       const float* std3_host, float* features_out, void* workspace,

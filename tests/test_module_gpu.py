@@ -200,7 +200,7 @@ def _argmax_flips_outside_band(probs, probs_ref, band):
     return int((differs & (margin > band)).sum()), int(differs.sum())
 
 
-@pytest.mark.parametrize("passes", [None, 2, 5, 6, 4])
+@pytest.mark.parametrize("passes", [None, 2, 5, 7, 6, 4])
 def test_mirror_net_on_raw_frames_matches_oracle(sht_unit_oracle, passes):
     """configs[2] through the reference-facing class: AnomalyCLIP(load_from_features=False) on one
     512-frame unit of uint8 frames (ViT-B/16, 12 layers) against the CPU oracle, in the default

@@ -141,3 +141,26 @@ def test_layernorm_f16mx_output(ops):
         assert torch.equal(got, want)
     want = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
     assert _rel(enc.decode(), want) < 1.5e-4
+
+
+def test_vit_b16_mx_mode():
+    """passes=7: mode 5 with the MLP pair of every block on f16mx operands (LayerNorm and the c_fc
+    epilogue write the encoding, c_fc and c_proj multiply it)."""
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    from oracle import anomalyclip_oracle as oracle
+    from tests.util_weights import make_frames_u8, make_vit_weights, normalise_frames
+    from tests.parity import assert_parity
+    sd = make_vit_weights()
+    packed = PackedVit(sd, torch.device("cuda"), passes=7)
+    enc7 = VitEncoder(packed, 256, 7)
+    torch.manual_seed(5)
+    frames = torch.randn(3, 3, 224, 224)
+    ref = oracle.vit_forward(sd, frames)
+    e7 = assert_parity(enc7(frames.cuda()), ref, "ViT-B/16 features, MXFP4 cross-term mode", rtol=3e-4)
+    e5 = assert_parity(VitEncoder(packed, 256, 5)(frames.cuda()), ref, "ViT-B/16 features, mixed mode", rtol=3e-4)
+    u8 = make_frames_u8(5, seed=3)
+    e7u = assert_parity(enc7(u8.cuda()), oracle.vit_forward(sd, normalise_frames(u8)),
+                        "ViT-B/16 features from uint8 frames, MXFP4 cross-term mode", rtol=3e-4)
+    print(f"mode 7 rel-L2 vs oracle: {e7:.3e} (fp32 frames), {e7u:.3e} (uint8 frames); mode 5: {e5:.3e}")
+    # micro-batching (ragged last micro-batch: 5 = 2 + 2 + 1 frames) does not change a bit
+    assert torch.equal(enc7(u8.cuda()), VitEncoder(packed, micro_batch=2, passes=7)(u8.cuda()))
