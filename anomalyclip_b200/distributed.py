@@ -94,7 +94,7 @@ def sharded_mean(local_sum: torch.Tensor, local_count: int,
     return (packed[:-1] / packed[-1].clamp_min(1.0)).to(torch.float32).reshape(local_sum.shape)
 
 
-_MODE_SPEED = {4: 2, 5: 1, 2: 0}     # operand modes of the image encoder, fastest = highest
+_MODE_SPEED = {4: 3, 7: 2, 5: 1, 2: 0}     # operand modes of the image encoder, fastest = highest
 
 
 def agree_on_mode(mode: int, device: torch.device, group: Optional[dist.ProcessGroup] = None) -> int:

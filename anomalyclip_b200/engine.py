@@ -60,8 +60,8 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #             attention side per scripts/numerics_passes.py, so they keep their cross terms)
 #   6  mixed with c_proj issued without its weight-residual cross term (weights of that GEMM
 #             effectively fp16): ~2e-4, ~1.5 pass-equivalents; explicit opt-in
-#   "auto"  calibrate on the first frames: mode 5 if it agrees with 2 on this checkpoint within
-#           `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
+#   "auto"  calibrate on the first frames: mode 7, else 5, if it agrees with 2 on this checkpoint
+#           within `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
 #           automatically: each flips a class index at a reference tie in the end-to-end test, and a
 #           calibration on features cannot vouch for class indices.
 #   7  mixed with the MLP pair on f16mx operands (fp16 main product + two block-scaled MXFP4
@@ -69,7 +69,7 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #             is a multiple of 768 (256 x 192 tiles)
 #   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
 FP16_PACKED_MODES = (2, 4, 5, 6, 7, "auto")
-AUTO_CANDIDATES = (5,)         # fastest first
+AUTO_CANDIDATES = (7, 5)       # fastest first (7 only when the f16mx weights exist: width % 768 == 0)
 
 
 class PackedVit:

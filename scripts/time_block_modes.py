@@ -15,8 +15,8 @@ from anomalyclip_b200 import ops  # noqa: E402
 
 arg = lambda k, d: next((a.split("=")[1] for a in sys.argv if a.startswith(f"--{k}=")), d)  # noqa: E731
 MODE, ITERS = int(arg("mode", "5")), int(arg("iters", "15"))
-P_ATT = 4 if MODE == 5 else MODE
-P_MLP = 2 if MODE == 5 else MODE
+P_ATT = 4 if MODE in (5, 7) else MODE
+P_MLP = 2 if MODE == 5 else MODE      # 7: f16mx operands for the MLP pair
 B, L, W = 256, 197, 768
 M = B * L
 dev = "cuda"
@@ -27,7 +27,10 @@ w_qkv, w_out, w_fc, w_proj = wq(3 * W, W), wq(W, W), wq(4 * W, W), wq(W, 4 * W)
 w_out3 = ops.split(torch.randn(W, W, device=dev) * 0.03)
 b3, b1, b4 = torch.randn(3 * W, device=dev), torch.randn(W, device=dev), torch.randn(4 * W, device=dev)
 g, be = torch.ones(W, device=dev), torch.zeros(W, device=dev)
-ENC = {4: 2, 2: 1}
+ENC = {4: 2, 2: 1, 7: 3}
+if MODE == 7:
+    wmx = lambda n, k: ops.encode_f16mx(torch.randn(n, k, device=dev) * 0.03, weight=True)  # noqa: E731
+    w_fc, w_proj = wmx(4 * W, W), wmx(W, 4 * W)
 flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
 h = ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_ATT])

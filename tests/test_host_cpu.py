@@ -123,10 +123,10 @@ def _mode_worker(rank, world, port, modes, q):
     dist.destroy_process_group()
 
 
-@pytest.mark.parametrize("modes,agreed", [((4, 4), 4), ((4, 5), 5), ((5, 2), 2), ((2, 4), 2)])
+@pytest.mark.parametrize("modes,agreed", [((4, 4), 4), ((4, 5), 5), ((5, 2), 2), ((2, 4), 2), ((7, 5), 5), ((7, 7), 7)])
 def test_ranks_agree_on_the_most_conservative_operand_mode_gloo(modes, agreed):
     """Ranks calibrate an "auto" encoder on their own frames; everybody then runs the most conservative
-    of the selected modes (4 fastest, then 5, then 2), so a sharded video is scored in ONE mode."""
+    of the selected modes (4 fastest, then 7, 5, 2), so a sharded video is scored in ONE mode."""
     from anomalyclip_b200.distributed import agree_on_mode
     assert agree_on_mode(5, torch.device("cpu")) == 5          # no process group: unchanged
     world, port = 2, _free_port()
@@ -147,7 +147,7 @@ def test_operand_mode_bookkeeping_needs_no_gpu():
     tries and in which order, how the image encoder's mode maps to the temporal stage's."""
     from anomalyclip_b200 import engine
     assert set(engine.FP16_PACKED_MODES) == {2, 4, 5, 6, 7, "auto"}
-    assert engine.AUTO_CANDIDATES == (5,)         # 6 and 4 flip a class index at a reference tie: opt-in only
+    assert engine.AUTO_CANDIDATES == (7, 5)       # 6 and 4 flip a class index at a reference tie: opt-in only
     scorer = engine.TemporalScorer.__new__(engine.TemporalScorer)
     for given, mapped in ((3, 3), (2, 2), (4, 4), (5, "auto"), (6, "auto"), (7, "auto"), ("auto", "auto")):
         engine.TemporalScorer.__init__(scorer, packed=None, passes=given)
