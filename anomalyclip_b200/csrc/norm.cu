@@ -100,42 +100,6 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
         } else if (ENC == 1) {
           f16f8_store4_act(out_split, plane_stride, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
           amax = sat_track(amax, y.x, y.y, y.z, y.w);
-        } else if (ENC == 3) {
-          // f16mx (mx.cuh): 8 consecutive lanes hold one 32-value scale block of the row
-          const float v0 = y.x * kActScaleMain, v1 = y.y * kActScaleMain, v2 = y.z * kActScaleMain,
-                      v3 = y.w * kActScaleMain;
-          uint32_t h01, h23;
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h01) : "f"(v1), "f"(v0));
-          asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h23) : "f"(v3), "f"(v2));
-          const float2 f01 = __half22float2(*reinterpret_cast<const __half2*>(&h01));
-          const float2 f23 = __half22float2(*reinterpret_cast<const __half2*>(&h23));
-          const float r0 = v0 - f01.x, r1 = v1 - f01.y, r2 = v2 - f23.x, r3 = v3 - f23.y;
-          float mv = fmaxf(fmaxf(fabsf(v0), fabsf(v1)), fmaxf(fabsf(v2), fabsf(v3)));
-          float mr = fmaxf(fmaxf(fabsf(r0), fabsf(r1)), fmaxf(fabsf(r2), fabsf(r3)));
-#pragma unroll
-          for (int o = 4; o > 0; o >>= 1) {
-            mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
-            mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
-          }
-          const uint32_t sf_l = mx_scale_byte(mr), sf_c = mx_scale_byte(mv);
-          const float il = mx_inv_scale(sf_l), ic = mx_inv_scale(sf_c);
-          const uint32_t l4 = mx_e2m1x2(r0 * il, r1 * il) | (mx_e2m1x2(r2 * il, r3 * il) << 8);
-          const uint32_t c4 = mx_e2m1x2(v0 * ic, v1 * ic) | (mx_e2m1x2(v2 * ic, v3 * ic) << 8);
-          uint8_t* base = reinterpret_cast<uint8_t*>(out_split);
-          const long long e = row * ld_split + 4 * c;
-          *reinterpret_cast<uint2*>(base + 2 * e) = make_uint2(h01, h23);
-          *reinterpret_cast<uint16_t*>(base + 2 * plane_stride + (e >> 1)) = static_cast<uint16_t>(l4);
-          *reinterpret_cast<uint16_t*>(base + 2 * plane_stride + (plane_stride >> 1) + (e >> 1)) =
-              static_cast<uint16_t>(c4);
-          if ((lane & 7) == 0) {
-            const int kb = c >> 3;   // 32-value block of the row
-            const long long row_blocks = (rows + 127) >> 7;
-            uint8_t* sf = base + 3 * plane_stride + (static_cast<long long>(kb >> 1) * row_blocks + (row >> 7)) * 512 +
-                          (row & 31) * 16 + ((row >> 5) & 3) * 4 + (kb & 1);
-            sf[0] = static_cast<uint8_t>(sf_l);
-            sf[2] = static_cast<uint8_t>(sf_c);
-          }
-          amax = sat_track(amax, y.x, y.y, y.z, y.w);
         } else {
           f16_store4_act(out_split, row * ld_split + 4 * c, y.x, y.y, y.z, y.w);
           amax = sat_track(amax, y.x, y.y, y.z, y.w);
@@ -144,6 +108,93 @@ layernorm_kernel(const float* __restrict__ x, long long rows, int D, long long l
     }
   }
   if (ENC != 0) sat_report(sat, amax);
+}
+
+// nn.LayerNorm straight into the f16mx encoding (mx.cuh): one warp per row, a lane owns 8
+// consecutive columns of every 256-column slab, so FOUR lanes hold one 32-value scale block (two
+// shuffle steps for its maxima) and the stores are 16 B (fp16 plane) and 4 B (each e2m1 plane) per
+// lane.  D must be a multiple of 256 (<= 768).
+__global__ void __launch_bounds__(kWarpsPerCta * 32)
+layernorm_mx_kernel(const float* __restrict__ x, long long rows, int D, long long ldx,
+                    const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
+                    uint8_t* __restrict__ out, long long ld_out, unsigned int* __restrict__ sat) {
+  ptx::pdl_launch_dependents();
+  ptx::pdl_wait();
+  const int lane = threadIdx.x & 31;
+  const long long row = rows - 1 - (static_cast<long long>(blockIdx.x) * kWarpsPerCta + (threadIdx.x >> 5));
+  if (row < 0) return;
+  constexpr int kSlabs = kMaxVec / 2;   // 256-column slabs
+  const int slabs = D >> 8;
+  const float* xr = x + row * ldx;
+  float v[kSlabs][8];
+  float s = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSlabs; ++i) {
+    if (i < slabs) {
+      const float4 a = *reinterpret_cast<const float4*>(xr + i * 256 + lane * 8);
+      const float4 b = *reinterpret_cast<const float4*>(xr + i * 256 + lane * 8 + 4);
+      v[i][0] = a.x; v[i][1] = a.y; v[i][2] = a.z; v[i][3] = a.w;
+      v[i][4] = b.x; v[i][5] = b.y; v[i][6] = b.z; v[i][7] = b.w;
+      s += ((a.x + a.y) + (a.z + a.w)) + ((b.x + b.y) + (b.z + b.w));
+    }
+  }
+  const float mean = warp_sum(s) / static_cast<float>(D);
+  float q = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSlabs; ++i) {
+    if (i < slabs) {
+#pragma unroll
+      for (int j = 0; j < 8; ++j) { v[i][j] -= mean; q += v[i][j] * v[i][j]; }
+    }
+  }
+  const float rstd = rsqrtf(warp_sum(q) / static_cast<float>(D) + eps);
+  const long long plane = rows * ld_out;
+  const long long row_blocks = (rows + 127) >> 7;
+  float amax = 0.f;
+#pragma unroll
+  for (int i = 0; i < kSlabs; ++i) {
+    if (i < slabs) {
+      const int col = i * 256 + lane * 8;
+      const float4 g0 = __ldg(reinterpret_cast<const float4*>(gamma + col)), g1 = __ldg(reinterpret_cast<const float4*>(gamma + col + 4));
+      const float4 b0 = __ldg(reinterpret_cast<const float4*>(beta + col)), b1 = __ldg(reinterpret_cast<const float4*>(beta + col + 4));
+      const float gg[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+      const float bb[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+      float y[8], r[8];
+      uint32_t h[4];
+      float mv = 0.f, mr = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) y[j] = (v[i][j] * rstd * gg[j] + bb[j]) * kActScaleMain;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(h[j]) : "f"(y[2 * j + 1]), "f"(y[2 * j]));
+        const float2 f = __half22float2(*reinterpret_cast<const __half2*>(&h[j]));
+        r[2 * j] = y[2 * j] - f.x;
+        r[2 * j + 1] = y[2 * j + 1] - f.y;
+        mv = fmaxf(mv, fmaxf(fabsf(y[2 * j]), fabsf(y[2 * j + 1])));
+        mr = fmaxf(mr, fmaxf(fabsf(r[2 * j]), fabsf(r[2 * j + 1])));
+      }
+      amax = fmaxf(amax, mv);
+#pragma unroll
+      for (int o = 2; o > 0; o >>= 1) {
+        mv = fmaxf(mv, __shfl_xor_sync(0xffffffffu, mv, o));
+        mr = fmaxf(mr, __shfl_xor_sync(0xffffffffu, mr, o));
+      }
+      const uint32_t sf_l = mx_scale_byte(mr), sf_c = mx_scale_byte(mv);
+      const uint32_t l4 = mx_e2m1x8(r, mx_inv_scale(sf_l)), c4 = mx_e2m1x8(y, mx_inv_scale(sf_c));
+      const long long e = row * ld_out + col;
+      *reinterpret_cast<uint4*>(out + 2 * e) = make_uint4(h[0], h[1], h[2], h[3]);
+      *reinterpret_cast<uint32_t*>(out + 2 * plane + (e >> 1)) = l4;
+      *reinterpret_cast<uint32_t*>(out + 2 * plane + (plane >> 1) + (e >> 1)) = c4;
+      if ((lane & 3) == 0) {
+        const int kb = col >> 5;
+        uint8_t* sf = out + 3 * plane + (static_cast<long long>(kb >> 1) * row_blocks + (row >> 7)) * 512 +
+                      (row & 31) * 16 + ((row >> 5) & 3) * 4 + (kb & 1);
+        sf[0] = static_cast<uint8_t>(sf_l);
+        sf[2] = static_cast<uint8_t>(sf_c);
+      }
+    }
+  }
+  if (sat != nullptr && !(amax <= 65504.0f)) atomicAdd(sat, 1u);   // also counts NaN
 }
 
 struct PeerDev {            // device-side copy of AclipPeerGather for one head launch
@@ -284,10 +335,10 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   ACLIP_REQUIRE(x != nullptr && gamma != nullptr && beta != nullptr, "layernorm: null pointer");
   ACLIP_REQUIRE(out_enc == 0 || out_enc == 2 ||
                     (out_enc == 1 && ld_split % 16 == 0 && plane_stride % 16 == 0) ||
-                    (out_enc == 3 && mode == 0 && D % 128 == 0 && ld_split % 64 == 0 && ld_split >= D &&
-                     plane_stride == rows * ld_split),
+                    (out_enc == 3 && mode == 0 && D % 256 == 0 && ld_split % 64 == 0 && ld_split >= D &&
+                     plane_stride == rows * ld_split && out_f32 == nullptr),
                 "layernorm: out_enc=%d unsupported (f16f8 needs 16-element pitches; f16mx: LayerNorm mode, "
-                "D %% 128 == 0, pitch %% 64 == 0, plane_stride = rows * pitch)", out_enc);
+                "D %% 256 == 0, pitch %% 64 == 0, plane_stride = rows * pitch, no fp32 output)", out_enc);
   ACLIP_REQUIRE(D > 0 && D % 4 == 0 && D <= 128 * kMaxVec, "layernorm: D=%d unsupported", D);
   ACLIP_REQUIRE(ldx % 4 == 0 && (out_f32 == nullptr || ld_f32 % 4 == 0) &&
                     (out_split == nullptr || ld_split % 4 == 0),
@@ -303,7 +354,9 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
   ACLIP_CUDA_OK(launch_pdl(layernorm_kernel<MODE, ENC>, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, \
                            D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat))
   if (mode == 0) {
-    if (out_enc == 3) ACLIP_LN(0, 3);
+    if (out_enc == 3)
+      ACLIP_CUDA_OK(launch_pdl(layernorm_mx_kernel, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, D, ldx,
+                               gamma, beta, eps, static_cast<uint8_t*>(out_split), ld_split, sat));
     else if (out_enc == 2) ACLIP_LN(0, 2);
     else if (out_enc == 1) ACLIP_LN(0, 1);
     else ACLIP_LN(0, 0);

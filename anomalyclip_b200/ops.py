@@ -282,15 +282,15 @@ def gemm(a: torch.Tensor, w: torch.Tensor, *, bias: Optional[torch.Tensor] = Non
 
 def layernorm(x: torch.Tensor, gamma: torch.Tensor, beta: torch.Tensor, *, eps: float = 1e-5,
               chan_mode: bool = False, want_f32: bool = True, want_split: bool = False,
-              out_enc: int = 0):
+              out_enc: int = 0, out_split=None):
     """Row LayerNorm (chan_mode: axial_attention's ChanLayerNorm, eps added to the std).
     out_enc=1: the split output is an `F16F8` activation tensor; out_enc=2: an fp16 tensor;
-    out_enc=3: an `F16MX` tensor (D % 128 == 0)."""
+    out_enc=3: an `F16MX` tensor (D % 256 == 0, no fp32 output).  out_split: write into this
+    tensor of the matching kind instead of allocating one."""
     x = _f32c(x, "x")
     rows, D = x.reshape(-1, x.shape[-1]).shape
     out_f32 = torch.empty((rows, D), dtype=torch.float32, device=x.device) if want_f32 else None
-    out_split = None
-    if want_split:
+    if want_split and out_split is None:
         out_split = F16F8(rows, D, x.device) if out_enc == 1 else \
             F16MX(rows, D, x.device) if out_enc == 3 else \
             torch.empty((rows, D), dtype=torch.float16, device=x.device) if out_enc == 2 else \

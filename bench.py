@@ -622,7 +622,7 @@ def run_b200(args) -> None:
     achieved = gemm["flops"] / (gemm["ms"] * 1e-3) / 1e12 if gemm["ms"] else 0.0
     traffic = _ncu_traffic()
     roofline = {
-        "kernel": "gemm2_tcgen05_kernel / gemm_tcgen05_kernel (all dense contractions: patch-embed, QKV, "
+        "kernel": "gemm2mx_tcgen05_kernel / gemm2_tcgen05_kernel / gemm_tcgen05_kernel (all dense contractions: patch-embed, QKV, "
                   "out-proj, MLP, selector/projection, axial q|kv/out, 3x3 conv implicit GEMM)",
         "bound": "tensor", "achieved": achieved, "peak": peaks["tf_sustained"], "unit": "TFLOP/s",
         "frac": achieved / peaks["tf_sustained"],

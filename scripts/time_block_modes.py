@@ -44,14 +44,14 @@ hh = ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_MLP]
 fc = ops.gemm(hh, w_fc, bias=b4, act=ops.ACT_QUICKGELU, passes=P_MLP, want_split=True, out_enc=ENC[P_MLP])
 
 steps = {
-    "ln_1": lambda: ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_ATT]),
+    "ln_1": lambda: ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_ATT], out_split=h),
     "in_proj": (lambda: ops.gemm(h, w_qkv, bias=b3, passes=4, out_split=qkv, out_enc=2)) if P_ATT == 4 else
                (lambda: ops.gemm(h, w_qkv, bias=b3, passes=2, out_split=qkv)),
     "attention": (lambda: ops.vit_attention(qkv, B, L, 12, out_enc=2)) if P_ATT == 4 else
                  (lambda: ops.vit_attention(qkv, B, L, 12)),
     "out_proj": (lambda: ops.gemm(o, w_out, bias=b1, residual=x, out_f32=x, passes=4)) if P_ATT == 4 else
                 (lambda: ops.gemm(o, w_out3, bias=b1, residual=x, out_f32=x, passes=3)),
-    "ln_2": lambda: ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_MLP]),
+    "ln_2": lambda: ops.layernorm(x, g, be, want_f32=False, want_split=True, out_enc=ENC[P_MLP], out_split=hh),
     "c_fc": lambda: ops.gemm(hh, w_fc, bias=b4, act=ops.ACT_QUICKGELU, passes=P_MLP, out_split=fc, out_enc=ENC[P_MLP]),
     "c_proj": lambda: ops.gemm(fc, w_proj, bias=b1, residual=x, out_f32=x, passes=P_MLP),
 }

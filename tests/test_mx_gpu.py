@@ -135,10 +135,15 @@ def test_layernorm_f16mx_output(ops):
     rows, D = 333, 768
     x = torch.randn(rows, D, device="cuda") * 3 + 0.5
     g, b = torch.randn(D, device="cuda"), torch.randn(D, device="cuda")
-    f32, enc = ops.layernorm(x, g, b, want_f32=True, want_split=True, out_enc=3)
-    ref = ops.encode_f16mx(f32)
-    for got, want in zip(enc.planes(), ref.planes()):
-        assert torch.equal(got, want)
+    enc = ops.layernorm(x, g, b, want_f32=False, want_split=True, out_enc=3)
+    # against the packer applied to the fp32 LayerNorm output: the two kernels sum a row in different
+    # orders, so an fp16 rounding may flip here and there, no more
+    ref = ops.encode_f16mx(ops.layernorm(x, g, b))
+    h, l4, c4 = enc.planes()
+    rh, rl4, rc4 = ref.planes()
+    assert (h != rh).double().mean().item() < 2e-3
+    assert (c4 != rc4).double().mean().item() < 2e-3
+    assert _rel(enc.decode(), ref.decode()) < 2e-5
     want = torch.nn.functional.layer_norm(x.double(), (D,), g.double(), b.double(), 1e-5)
     assert _rel(enc.decode(), want) < 1.5e-4
 
