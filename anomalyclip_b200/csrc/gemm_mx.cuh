@@ -190,11 +190,15 @@ gemm2mx_tcgen05_kernel(const __grid_constant__ CUtensorMap tmAh, const __grid_co
         for (int kb = 0; kb < p.num_kb; ++kb) {
           ptx::mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* st = smem + stage * Cfg::STAGE_BYTES;
-          if (rank == 0) ptx::mbar_expect_tx(&full_bar[stage], 2 * Cfg::TX_BYTES);
+          const bool skip_q = (p.debug & 16) != 0;   // profiling experiment: no e2m1 planes
+          if (rank == 0)
+            ptx::mbar_expect_tx(&full_bar[stage], 2 * (Cfg::TX_BYTES - (skip_q ? 2 * (Cfg::A_Q_PLANE + Cfg::B_Q_PLANE) : 0)));
           ptx::tma_load_3d_pair(st + Cfg::A_H, &tmAh, &full_bar[stage], kb * 64, m0, 0);
           ptx::tma_load_3d_pair(st + Cfg::B_H, &tmBh, &full_bar[stage], kb * 64, n0, 0);
-          ptx::tma_load_3d_pair(st + Cfg::A_Q, &tmAq, &full_bar[stage], kb * 32, m0, 0);
-          ptx::tma_load_3d_pair(st + Cfg::B_Q, &tmBq, &full_bar[stage], kb * 32, n0, 0);
+          if (!skip_q) {
+            ptx::tma_load_3d_pair(st + Cfg::A_Q, &tmAq, &full_bar[stage], kb * 32, m0, 0);
+            ptx::tma_load_3d_pair(st + Cfg::B_Q, &tmBq, &full_bar[stage], kb * 32, n0, 0);
+          }
           ptx::tma_load_3d_pair(st + Cfg::SFA, &tmAs, &full_bar[stage], 0, mblk, kb);
           ptx::tma_load_3d_pair(st + Cfg::SFB, &tmBs, &full_bar[stage], 0, nblk, kb);
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
