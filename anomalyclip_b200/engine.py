@@ -60,16 +60,18 @@ def _split_weight(t: torch.Tensor, device: torch.device) -> torch.Tensor:
 #             attention side per scripts/numerics_passes.py, so they keep their cross terms)
 #   6  mixed with c_proj issued without its weight-residual cross term (weights of that GEMM
 #             effectively fp16): ~2e-4, ~1.5 pass-equivalents; explicit opt-in
-#   "auto"  calibrate on the first frames: mode 7, else 5, if it agrees with 2 on this checkpoint
-#           within `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
+#   "auto"  calibrate on the first frames: mode 5 if it agrees with 2 on this checkpoint within
+#           `calib_tol` with no fp16 saturation, else 2.  Modes 6 and 4 are never selected
 #           automatically: each flips a class index at a reference tie in the end-to-end test, and a
 #           calibration on features cannot vouch for class indices.
 #   7  mixed with the MLP pair on f16mx operands (fp16 main product + two block-scaled MXFP4
-#             cross terms, csrc/mx.cuh): ~1e-4 like mode 5 at 1.33 pass-equivalents; needs a width that
-#             is a multiple of 768 (256 x 192 tiles)
+#             cross terms, csrc/mx.cuh): ~1e-4 like mode 5 at 1.33 pass-equivalents, 6-7 % faster; needs
+#             a width that is a multiple of 768 (256 x 192 tiles).  Explicit opt-in: in the end-to-end
+#             test its class indices are exact or flip at ONE reference tie depending on rounding
+#             details of the LayerNorm kernel in front of it -- the same fragility as modes 6 and 4
 #   1  plain bf16 (misses the 1e-3 bar; kept for A/B runs)
 FP16_PACKED_MODES = (2, 4, 5, 6, 7, "auto")
-AUTO_CANDIDATES = (7, 5)       # fastest first (7 only when the f16mx weights exist: width % 768 == 0)
+AUTO_CANDIDATES = (5,)         # fastest first; 7 / 6 / 4 are explicit opt-ins (see above)
 
 
 class PackedVit:
@@ -90,8 +92,8 @@ class PackedVit:
         self.f16f8 = passes in FP16_PACKED_MODES
         conv = sd["conv1.weight"]
         self.width, _, self.patch, _ = conv.shape
-        # f16mx copies of the MLP weights (mode 7; "auto" may select it): 256 x 192 tiles
-        self.mx = passes in (7, "auto") and self.width % 768 == 0
+        # f16mx copies of the MLP weights (mode 7): 256 x 192 tiles
+        self.mx = passes == 7 and self.width % 768 == 0
         tokens = sd["positional_embedding"].shape[0]
         grid = int(round((tokens - 1) ** 0.5))
         assert grid * grid + 1 == tokens, "positional_embedding is not a square grid + CLS"
@@ -163,8 +165,8 @@ class VitEncoder:
             raise _lib.AclipError("VitEncoder: passes=2/4/5/6/7/'auto' need weights packed with "
                                   "PackedVit(passes=2/4/5/6/7/'auto') (and only then)")
         if passes == 7 and not packed.mx:
-            raise _lib.AclipError("VitEncoder: passes=7 needs PackedVit(passes=7 or 'auto') and a width that is "
-                                  "a multiple of 768")
+            raise _lib.AclipError("VitEncoder: passes=7 needs PackedVit(passes=7) and a width that is a "
+                                  "multiple of 768")
         self.packed = packed
         self.micro_batch = micro_batch
         self.passes = passes                              # as requested

@@ -71,8 +71,8 @@ class VisionTransformer(nn.Module):
         fp32-faithful, ~1e-5 on the features), 4 = fp16 operands in one pass (~2.5e-4 .. 4e-4),
         5 = mixed (attention side as 4, MLP side as 2, ~1e-4), 7 = 5 with the MLP pair on fp16 + MXFP4
         cross-term operands (1.5 passes, ~1e-4; width % 768 == 0), 6 = 5 with c_proj at 1.5 passes
-        (~1.5e-4), "auto" = 7, else 5, if a calibration on the first frames shows it within 3e-4 of mode 2
-        on this checkpoint with nothing saturating, else 2 (engine.VitEncoder.calibrate; 4 and 6 flip a
+        (~1.5e-4), "auto" = 5 if a calibration on the first frames shows it within 3e-4 of mode 2
+        on this checkpoint with nothing saturating, else 2 (engine.VitEncoder.calibrate; 7, 4 and 6 can flip a
         class index at a reference tie and are opt-in only); 1 = plain bf16.  None picks "auto"
         where the CTA-pair kernel applies (width and output_dim multiples of 256, e.g. every CLIP
         ViT-B/L) else 3."""

@@ -72,7 +72,8 @@ PRECISION = {
         "f32 accumulate/residual/LayerNorm/softmax",
         "mixed with the MLP pair (c_fc, c_proj) as fp16 main product + two block-scaled MXFP4 cross-term "
         "products (tcgen05 kind::mxf4, e2m1 elements, one UE8M0 scale per 32 values along K, 4x the fp16 "
-        "rate); patch-embed / proj stay f16f8; 1.33 bf16-pass equivalents per product on average",
+        "rate); patch-embed / proj stay f16f8; 1.33 bf16-pass equivalents per product on average; explicit "
+        "opt-in: accuracy as mode 5, but a class index at a reference tie can flip",
         (1048 * 1.0 + 1860 * 1.5) / 2908),
 }
 

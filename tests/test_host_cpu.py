@@ -147,7 +147,7 @@ def test_operand_mode_bookkeeping_needs_no_gpu():
     tries and in which order, how the image encoder's mode maps to the temporal stage's."""
     from anomalyclip_b200 import engine
     assert set(engine.FP16_PACKED_MODES) == {2, 4, 5, 6, 7, "auto"}
-    assert engine.AUTO_CANDIDATES == (7, 5)       # 6 and 4 flip a class index at a reference tie: opt-in only
+    assert engine.AUTO_CANDIDATES == (5,)         # 7, 6 and 4 can flip a class index at a reference tie: opt-in only
     scorer = engine.TemporalScorer.__new__(engine.TemporalScorer)
     for given, mapped in ((3, 3), (2, 2), (4, 4), (5, "auto"), (6, "auto"), (7, "auto"), ("auto", "auto")):
         engine.TemporalScorer.__init__(scorer, packed=None, passes=given)
