@@ -108,9 +108,10 @@ inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s
 // Launch with programmatic stream serialization (see ptx.cuh: pdl_wait / pdl_launch_dependents);
 // ACLIP_NO_PDL=1 in the environment launches plainly (A/B runs).
 bool pdl_enabled();
+bool pdl_mx_enabled();   // ACLIP_MX_PDL=1: programmatic launch also for the f16mx kernels (see launch_serial)
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
-                              cudaStream_t stream, Args&&... args) {
+inline cudaError_t launch_with(bool programmatic, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                               cudaStream_t stream, Args&&... args) {
   cudaLaunchConfig_t cfg{};
   cfg.gridDim = grid;
   cfg.blockDim = block;
@@ -120,8 +121,21 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
   attr.id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr.val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = &attr;
-  cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  cfg.numAttrs = programmatic ? 1 : 0;
   return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                              cudaStream_t stream, Args&&... args) {
+  return launch_with(pdl_enabled(), kernel, grid, block, smem, stream, static_cast<Args&&>(args)...);
+}
+// Plain stream-ordered launch (the kernel starts when its predecessor has completed); its own
+// griddepcontrol instructions still let the SUCCESSOR start early.
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_serial(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+                                 cudaStream_t stream, Args&&... args) {
+  return launch_with(pdl_enabled() && pdl_mx_enabled(), kernel, grid, block, smem, stream,
+                     static_cast<Args&&>(args)...);
 }
 
 }  // namespace aclip

@@ -47,6 +47,14 @@ bool pdl_enabled() {
   return on;
 }
 
+bool pdl_mx_enabled() {
+  static const bool on = [] {
+    const char* v = getenv("ACLIP_MX_PDL");
+    return v != nullptr && v[0] == '1';
+  }();
+  return on;
+}
+
 // ------------------------------------------------------------------ tensor maps
 using EncodeTiledFn = CUresult (*)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*,
                                    const cuuint64_t*, const cuuint64_t*, const cuuint32_t*,
