@@ -106,9 +106,11 @@ struct PerDeviceOnce {
 inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 // Launch with programmatic stream serialization (see ptx.cuh: pdl_wait / pdl_launch_dependents);
-// ACLIP_NO_PDL=1 in the environment launches plainly (A/B runs).
+// Opt-in: ACLIP_PDL=1 in the environment (default: plain stream-ordered launches, see pdl_enabled()).
 bool pdl_enabled();
-bool pdl_mx_enabled();   // ACLIP_MX_PDL=1: programmatic launch also for the f16mx kernels (see launch_serial)
+// ACLIP_MX_PDL=1: programmatic launch also for the f16mx kernels (see launch_serial); =ln / =gemm:
+// only for layernorm_mx_kernel / only for gemm2mx_tcgen05_kernel (experiments)
+bool pdl_mx_enabled(int kind);   // kind: 0 = GEMM, 1 = LayerNorm
 template <typename... KArgs, typename... Args>
 inline cudaError_t launch_with(bool programmatic, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                cudaStream_t stream, Args&&... args) {
@@ -132,9 +134,9 @@ inline cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, s
 // Plain stream-ordered launch (the kernel starts when its predecessor has completed); its own
 // griddepcontrol instructions still let the SUCCESSOR start early.
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_serial(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
+inline cudaError_t launch_serial(int kind, void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem,
                                  cudaStream_t stream, Args&&... args) {
-  return launch_with(pdl_enabled() && pdl_mx_enabled(), kernel, grid, block, smem, stream,
+  return launch_with(pdl_enabled() && pdl_mx_enabled(kind), kernel, grid, block, smem, stream,
                      static_cast<Args&&>(args)...);
 }
 

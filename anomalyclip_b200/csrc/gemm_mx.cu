@@ -91,7 +91,7 @@ int launch_mx(const CUtensorMap (&tm)[6], const GemmParams& p, const MxOut& mo, 
   if (clusters > tiles) clusters = tiles;
   if (clusters < 1) clusters = 1;
   timing_begin(KIND_GEMM, stream);
-  ACLIP_CUDA_OK(launch_serial(kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tm[0], tm[1],
+  ACLIP_CUDA_OK(launch_serial(0, kernel, dim3(2 * clusters), dim3(Cfg::THREADS), Cfg::SMEM_BYTES, stream, tm[0], tm[1],
                            tm[2], tm[3], tm[4], tm[5], p, mo));
   {
     const double out_b = (p.out_f32 ? 4.0 : 0.0) + (EPI == 4 ? 3.06 : p.out_split ? 4.0 : 0.0) + (p.residual ? 4.0 : 0.0);

@@ -355,7 +355,7 @@ int layernorm(const float* x, long long rows, int D, long long ldx, const float*
                            D, ldx, gamma, beta, eps, out_f32, ld_f32, os, ld_split, plane_stride, sat))
   if (mode == 0) {
     if (out_enc == 3)
-      ACLIP_CUDA_OK(launch_serial(layernorm_mx_kernel, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, D, ldx,
+      ACLIP_CUDA_OK(launch_serial(1, layernorm_mx_kernel, dim3(grid), dim3(kWarpsPerCta * 32), 0, stream, x, rows, D, ldx,
                                gamma, beta, eps, static_cast<uint8_t*>(out_split), ld_split, sat));
     else if (out_enc == 2) ACLIP_LN(0, 2);
     else if (out_enc == 1) ACLIP_LN(0, 1);

@@ -32,7 +32,13 @@ __device__ __forceinline__ bool elect_one() {
 // tensor-map prefetch -- before pdl_wait(), which returns once every predecessor grid has completed
 // and flushed.  Nothing produced or still read by a predecessor is touched before pdl_wait().
 // Without the launch attribute both instructions are no-ops.
-__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// The wait makes the predecessors' (generic-proxy) stores visible to this grid's generic proxy; the
+// TMA engine reads through the async proxy, so a cross-proxy fence follows before any
+// cp.async.bulk.tensor may read what a predecessor wrote.  (Required by the memory model; it did NOT
+// remove the rare fault seen with programmatic launch, which is why that launch mode is opt-in.)
+__device__ __forceinline__ void pdl_wait() {
+  asm volatile("griddepcontrol.wait;\n\tfence.proxy.async.global;" ::: "memory");
+}
 __device__ __forceinline__ void pdl_launch_dependents() {
   asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 }

@@ -1,11 +1,10 @@
 #!/usr/bin/env python
 """Stress: the ViT-B/16 encoder on the same 512 frames REPS times in one process (two micro-batches of
 256, kernels queued back to back), every result compared bit for bit with the first.  Found the one
-timing-dependent fault of round 2: with the f16mx kernels (mode 7) launched programmatically
-(ACLIP_MX_PDL=1) about 1 run in 300 returned the first frames of the SECOND micro-batch slightly off
-(1.6e-4 .. 2e-3); never without programmatic launch (ACLIP_NO_PDL=1), never with one micro-batch
-(MB=512), never in mode 5.  The f16mx kernels are therefore launched stream-ordered
-(common.h launch_serial): 0 of 1 200.   MODE=5|7  REPS=400  MB=256  LAYERS=12"""
+timing-dependent fault of round 2: with programmatic dependent launch (ACLIP_PDL=1) about one run in
+1 500 - 4 000 (mode 5) or in 500 - 1 500 (mode 7) returns the first 9-12 frames of a micro-batch
+slightly off (1.5e-4 .. 3e-3 of the maximum); 0 of 2 800 runs without it -- which is why programmatic
+launch is opt-in.   MODE=5|7  REPS=400  MB=256  LAYERS=12  ACLIP_PDL=1  ACLIP_MX_PDL=1|ln|gemm"""
 import os, sys, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from anomalyclip_b200 import synthetic as syn
@@ -27,4 +26,4 @@ for i in range(N):
     if d.max().item() != 0.0:
         rows = (d.amax(1) > 0).nonzero().flatten()
         bad.append((i, round(d.max().item() / ref.abs().max().item(), 5), rows.numel(), rows.min().item(), rows.max().item()))
-print(f"mode {mode} layers={layers} mb={mb} MX_PDL={os.environ.get('ACLIP_MX_PDL')} NO_PDL={os.environ.get('ACLIP_NO_PDL')}: {len(bad)} of {N} repeats differ (rep, max rel, rows, first, last):", bad[:6])
+print(f"mode {mode} layers={layers} mb={mb} MX_PDL={os.environ.get('ACLIP_MX_PDL')} PDL={os.environ.get('ACLIP_PDL')}: {len(bad)} of {N} repeats differ (rep, max rel, rows, first, last):", bad[:6])
