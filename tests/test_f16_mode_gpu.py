@@ -229,3 +229,19 @@ def test_vit_b16_mode6(vitb16):
     e = assert_parity(enc6(u8.cuda()), oracle.vit_forward(sd, normalise_frames(u8)),
                       "ViT-B/16 features from uint8 frames, mode 6", rtol=3e-4)
     print(f"mode 6 rel-L2 vs oracle: {e:.3e}")
+
+
+def test_encoder_is_bit_deterministic_across_back_to_back_calls(vitb16):
+    """512 frames (two micro-batches of 256, kernels queued back to back) through the default operand
+    mode twenty times: every result must equal the first bit for bit.  Guards the finding of
+    scripts/stress_determinism.py (a rare timing-dependent fault under programmatic dependent
+    launch, which is therefore opt-in); the script runs thousands of repeats, this is the smoke
+    version."""
+    from anomalyclip_b200.engine import PackedVit, VitEncoder
+    frames = make_frames_u8(512, seed=4).cuda()
+    enc = VitEncoder(PackedVit(vitb16, torch.device("cuda"), passes=5), 256, 5)
+    first = enc(frames).clone()
+    out = torch.empty_like(first)
+    for i in range(20):
+        enc(frames, out)
+        assert torch.equal(out, first), f"call {i + 1} differs from the first"
